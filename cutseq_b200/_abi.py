@@ -7,7 +7,7 @@ import ctypes as C
 ABI_VERSION = 1
 
 CSQ_MAX_ADAPTER = 128
-CSQ_MAX_READ_LEN = 1792
+CSQ_MAX_READ_LEN = 895
 CSQ_MAX_OPS = 32
 CSQ_MAX_SUFFIX = 8
 CSQ_N_DEST = 3

@@ -1,0 +1,118 @@
+// Internal definitions shared by the CUDA kernels (kernels.cu) and the host side of the
+// C ABI (plan.cu). Nothing here is part of the public boundary (include/cutseq_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cutseq_b200.h"
+
+// ---- limits of the packed DP word (see kernels.cu, "DP cell encoding") -------------------
+// origin is stored biased by 128 in 10 bits  -> read length <= 895
+// cost is stored in 10 bits                  -> m + n <= 1023
+#define CSQ_FAST_MAX_READ 895
+#define CSQ_MAX_PRE 12 /* scalar ops executed in front of one ALIGN op */
+
+// Scalar (O(1)) ops that sit between alignments: CUT, COND_CUT, RENAME(capture).
+struct DevOp {
+    int32_t kind;    // csq_op_kind
+    int32_t length;  // CUT / COND_CUT
+    int32_t fmin;    // COND_CUT
+    uint32_t rename_parts;
+};
+
+// Per-mate, per-read state carried between kernels: the read is original[a:b].
+// Slices of the original read are packed as (offset << 16 | length); length 0 == None/"".
+struct __align__(16) ReadState {
+    uint16_t a, b;
+    uint32_t matched;  // bit31: any AdapterCutter matched (bool(info.matches)); bits 0..30: adapter_id set
+    uint32_t cp, cs;   // info.cut_prefix / info.cut_suffix as last assigned
+    uint32_t ren_cp, ren_cs;  // ... as they were when the RENAME op ran
+    uint16_t id_start, id_end;  // Renamer.parse_name() id within the (suffix-stripped) header
+    uint32_t qtrim;    // bases removed by QTRIM (statistics)
+};
+static_assert(sizeof(ReadState) == 32, "ReadState must stay 32 bytes");
+
+struct MateDev {  // device pointers of one mate of one slot
+    const uint8_t* seq;
+    const uint8_t* qual;
+    const uint32_t* seq_off;
+    const uint32_t* seq_len;
+    const uint8_t* name;
+    const uint32_t* name_off;
+    ReadState* state;
+};
+
+struct AlignParams {
+    MateDev md;
+    csq_match* matches;    // nullable: per-read record of this ALIGN op
+    const uint32_t* list;  // nullable: indices of the reads to process (prefilter survivors)
+    const uint32_t* list_count;  // with list: number of entries (device side)
+    uint32_t n;            // reads in the batch
+    int32_t first;         // 1: state is initialised here (first segment of the program)
+    int32_t n_pre;
+    DevOp pre[CSQ_MAX_PRE];
+    // the adapter
+    int32_t m, flags, reversed, trim_front, min_overlap, k, adapter_bit, homopolymer;
+    uint8_t thr[CSQ_MAX_ADAPTER + 1];  // thr[L] = floor(L * max_error_rate) with host doubles
+    uint32_t peq[4][4];                // [A,C,G,T][word]: bit i-1 set <=> adapter[i-1] == letter
+    uint8_t letter;                    // homopolymer base
+    unsigned long long* counters;      // csq_counters on the device
+    int32_t counter_index;             // word index of with_adapters[mate][op] inside csq_counters
+};
+
+struct FinishParams {
+    MateDev md;
+    uint32_t n;
+    int32_t first;  // program without any ALIGN op: initialise state here
+    int32_t n_post;
+    DevOp post[CSQ_MAX_PRE];
+    int32_t has_qtrim, cutoff_front, cutoff_back, qbase;
+    int32_t n_suffix;
+    int32_t suffix_len[4];
+    char suffix[4][CSQ_MAX_SUFFIX];
+    int32_t mate;
+    int32_t has_rename;  // 0: the header is written unchanged (after suffix stripping)
+    unsigned long long* counters;
+};
+
+#define CSQ_PAIR_BLOCK 256  // pairs per CTA in the pair/emit kernels (scan granule)
+
+struct PairParams {
+    MateDev md[2];
+    uint32_t n;
+    int32_t n_mates;
+    int32_t min_length, untrimmed_enabled;
+    uint32_t required[2];
+    uint32_t rename_parts;  // of the RENAME op (same on both mates)
+    int32_t check_ids;      // paired RENAME present: mate ids must be equal
+    int32_t revcomp;        // single-end REVCOMP op present
+    uint8_t* dest;          // [n]
+    uint32_t* rec_len;      // [2][n] bytes of the FASTQ record of each mate
+    uint32_t* block_tot;    // [nblk][8]: bytes per (dest,mate) stream (6 used)
+    uint32_t* block_cnt;    // [nblk][4]: records per dest
+    unsigned long long* counters;
+    int32_t* error_flag;
+};
+
+struct EmitParams {
+    PairParams pp;
+    const unsigned long long* block_off;  // [nblk][8] exclusive byte offsets per stream
+    uint8_t* out[CSQ_N_DEST][2];
+};
+
+// word indices inside csq_counters viewed as uint64[]
+enum {
+    CNT_N = 0, CNT_TOTAL_BP = 1, CNT_WRITTEN = 3, CNT_WRITTEN_BP = 4, CNT_TOO_SHORT = 6, CNT_UNTRIMMED = 7,
+    CNT_QTRIM_BP = 8, CNT_WITH_ADAPTERS = 10
+};
+
+// launchers implemented in kernels.cu (all asynchronous on `stream`)
+cudaError_t csq_launch_align(const AlignParams& p, uint32_t n_items, cudaStream_t stream);
+cudaError_t csq_launch_finish(const FinishParams& p, cudaStream_t stream);
+cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream);
+cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
+                            unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream);
+cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream);
+bool csq_align_has_exact_kernel(int m);
+cudaError_t csq_launch_int_peak(int variant, int iters, unsigned int* sink, int blocks, int threads, cudaStream_t stream);

@@ -1,0 +1,748 @@
+// sm_100a kernels of the trimming chain.
+//
+//   k_align<M>     exact adapter alignment, one thread per read, whole DP column in registers
+//   k_finish       trailing cuts, quality trimming, header suffix stripping + id parsing
+//   k_pair         TooShort / IsUntrimmedAny decision, record sizes, per-CTA stream totals
+//   k_scan         exclusive scan of the per-CTA totals (6 output streams)
+//   k_emit         order-preserving FASTQ text emission, one warp per record
+//   k_int_peak     integer-issue microbenchmark (roofline denominator of the DP)
+//
+// Semantics follow cutadapt 5.x as restated in oracle/cutseq_oracle.c (Aligner.locate of
+// upstream _align.pyx etc.); the call sites are reference run.py:326-471 / 533-792.
+//
+// DP cell encoding.  cutadapt keeps (cost, score, origin) per cell and picks, on a
+// mismatch, diag if cost_diag <= both others, else insertion if <= deletion, else deletion;
+// score and origin are inherited from the chosen neighbour (+1 match, -1 mismatch, -2 indel).
+// Here a cell is ONE 32-bit word
+//        [31:22] cost | [21:20] direction priority (transient) | [19:10] s' | [9:0] origin+128
+// with s' = score + 2*cost, which only ever grows (match +1, mismatch +1, indel +0), so no field
+// ever borrows from its neighbour.  The three candidates get cost+1 and their priority
+// (diag 0 < insertion 1 < deletion 2) added in one IADD each; one 3-input unsigned minimum
+// (VIMNMX3) then implements cutadapt's tie-breaking exactly, and one LOP3 clears the priority.
+// On a match the diagonal candidate keeps its cost and always wins (|D(i-1,j-1) - D(i-1,j)| <= 1),
+// which is cutadapt's "characters equal -> take the diagonal" rule.
+// cutadapt's Ukkonen band is not reproduced: cells it skips have cost > k and can neither be
+// accepted nor lie on the path of an accepted cell, so the full DP yields identical results.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "csq_internal.h"
+
+namespace {
+
+constexpr int SP_SHIFT = 10, PRIO_SHIFT = 20, COST_SHIFT = 22;
+constexpr int ORG_BIAS = 128;
+constexpr uint32_t D_MATCH = 1u << SP_SHIFT;
+constexpr uint32_t D_MIS = (1u << COST_SHIFT) + (1u << SP_SHIFT);
+constexpr uint32_t D_INS = (1u << COST_SHIFT) + (1u << PRIO_SHIFT);
+constexpr uint32_t D_DEL = (1u << COST_SHIFT) + (2u << PRIO_SHIFT);
+constexpr uint32_t PRIO_CLEAR = ~(3u << PRIO_SHIFT);
+
+__device__ __forceinline__ uint32_t pack_cell(int cost, int origin) {
+    return ((uint32_t)cost << COST_SHIFT) | ((uint32_t)(2 * cost) << SP_SHIFT) | (uint32_t)(origin + ORG_BIAS);
+}
+__device__ __forceinline__ int cell_cost(uint32_t w) { return (int)(w >> COST_SHIFT); }
+__device__ __forceinline__ int cell_origin(uint32_t w) { return (int)(w & 0x3FFu) - ORG_BIAS; }
+__device__ __forceinline__ int cell_score(uint32_t w) { return (int)((w >> SP_SHIFT) & 0x3FFu) - 2 * cell_cost(w); }
+
+struct Best {
+    int cost, origin, score, ref_stop, query_stop;
+};
+
+__device__ __forceinline__ void init_cell(int i, int min_n, bool sir, bool siq, int& cost, int& origin) {
+    if (!sir && !siq) {
+        cost = max(i, min_n);
+        origin = 0;
+    } else if (sir && !siq) {
+        cost = min_n;
+        origin = min(0, min_n - i);
+    } else if (!sir && siq) {
+        cost = i;
+        origin = max(0, min_n - i);
+    } else {
+        cost = min(i, min_n);
+        origin = min_n - i;
+    }
+}
+
+// Row-m rule of Aligner.locate (only evaluated where cost[m] <= k, as upstream's band does).
+__device__ __forceinline__ void row_m_update(uint32_t wm, int j, int m, int n, const AlignParams& P, Best& best) {
+    const int cost = cell_cost(wm);
+    if (cost > P.k) return;
+    const int origin = cell_origin(wm), score = cell_score(wm);
+    const int length = m + min(origin, 0);
+    const bool acceptable = length >= P.min_overlap && cost <= (int)P.thr[length];
+    if (!acceptable) return;
+    const int best_length = m + min(best.origin, 0);
+    if (best.cost == m + n + 1 || (origin <= best.origin + m / 2 && score > best.score) ||
+        (length > best_length && score > best.score)) {
+        best.score = score;
+        best.cost = cost;
+        best.origin = origin;
+        best.ref_stop = m;
+        best.query_stop = j;
+    }
+}
+
+__device__ __forceinline__ void last_col_update(uint32_t w, int i, int n, const AlignParams& P, Best& best) {
+    const int cost = cell_cost(w), origin = cell_origin(w), score = cell_score(w);
+    const int length = i + min(origin, 0);
+    if (length >= P.min_overlap && length >= 0 && cost <= (int)P.thr[max(length, 0)] &&
+        (score > best.score || (score == best.score && cost < best.cost))) {
+        best.score = score;
+        best.cost = cost;
+        best.origin = origin;
+        best.ref_stop = i;
+        best.query_stop = n;
+    }
+}
+
+__device__ __forceinline__ void best_to_match(const Best& best, int m, int n, bool reversed, csq_match& r) {
+    r.reserved = 0;
+    if (best.cost == m + n + 1) {
+        r.found = 0;
+        r.ref_start = r.ref_stop = r.query_start = r.query_stop = r.score = r.errors = 0;
+        return;
+    }
+    int ref_start = best.origin >= 0 ? 0 : -best.origin;
+    int query_start = best.origin >= 0 ? best.origin : 0;
+    int ref_stop = best.ref_stop, query_stop = best.query_stop;
+    if (reversed) {  // RightmostFrontAdapter.match_to coordinate mapping
+        int rs = m - ref_stop, re = m - ref_start, qs = n - query_stop, qe = n - query_start;
+        ref_start = rs;
+        ref_stop = re;
+        query_start = qs;
+        query_stop = qe;
+    }
+    r.found = 1;
+    r.ref_start = (int16_t)ref_start;
+    r.ref_stop = (int16_t)ref_stop;
+    r.query_start = (int16_t)query_start;
+    r.query_stop = (int16_t)query_stop;
+    r.score = (int16_t)best.score;
+    r.errors = (int16_t)best.cost;
+}
+
+// Exact DP for a compile-time adapter length M: the column lives in registers W[0..M].
+template <int M, bool HOMO>
+__device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P,
+                                         const uint32_t* __restrict__ lut, csq_match& r) {
+    constexpr int NW = (M + 31) / 32;
+    const int n = b - a;
+    const int k = P.k;
+    const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
+    int max_n = n, min_n = 0;
+    if (!siq) max_n = min(n, M + k);
+    if (!eiq) min_n = max(0, n - M - k);
+
+    uint32_t W[M + 1];
+#pragma unroll
+    for (int i = 0; i <= M; i++) {
+        int cost, origin;
+        init_cell(i, min_n, sir, siq, cost, origin);
+        W[i] = pack_cell(cost, origin);
+    }
+    Best best = {M + n + 1, 0, 0, M, n};
+    const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
+    const int step = P.reversed ? -1 : 1;
+    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+
+    for (int j = min_n + 1; j <= max_n; j++, p += step) {
+        const uint32_t c = *p;
+        uint32_t pm[NW];
+        uint32_t dcol = 0;
+        if constexpr (HOMO) {
+            dcol = ((c & 0xDFu) == (uint32_t)P.letter) ? D_MATCH : D_MIS;
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; w++) pm[w] = lut[c * NW + w];
+        }
+        uint32_t wd = W[0];
+        W[0] += row0_delta;
+#pragma unroll
+        for (int i = 1; i <= M; i++) {
+            const uint32_t wl = W[i];
+            uint32_t dd;
+            if constexpr (HOMO)
+                dd = dcol;
+            else
+                dd = (pm[(i - 1) >> 5] & (1u << ((i - 1) & 31))) ? D_MATCH : D_MIS;
+            const uint32_t cd = wd + dd;
+            const uint32_t cu = W[i - 1] + D_INS;
+            const uint32_t cl = wl + D_DEL;
+            W[i] = __vimin3_u32(cd, cu, cl) & PRIO_CLEAR;
+            wd = wl;
+        }
+        if (eiq) row_m_update(W[M], j, M, n, P, best);
+    }
+    if (max_n == n) {
+        const int first_i = eir ? 0 : M;
+#pragma unroll
+        for (int i = M; i >= 0; i--)
+            if (i >= first_i) last_col_update(W[i], i, n, P, best);
+    }
+    best_to_match(best, M, n, P.reversed != 0, r);
+}
+
+// Same recurrence for any m <= CSQ_MAX_ADAPTER with the column in local memory (slow path for
+// adapter lengths without a register-resident instantiation).
+__device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P,
+                                        csq_match& r) {
+    const int m = P.m, n = b - a, k = P.k;
+    const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
+    int max_n = n, min_n = 0;
+    if (!siq) max_n = min(n, m + k);
+    if (!eiq) min_n = max(0, n - m - k);
+    uint32_t W[CSQ_MAX_ADAPTER + 1];
+    for (int i = 0; i <= m; i++) {
+        int cost, origin;
+        init_cell(i, min_n, sir, siq, cost, origin);
+        W[i] = pack_cell(cost, origin);
+    }
+    Best best = {m + n + 1, 0, 0, m, n};
+    const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
+    const int step = P.reversed ? -1 : 1;
+    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    for (int j = min_n + 1; j <= max_n; j++, p += step) {
+        const uint32_t c = *p & 0xDFu;
+        const int li = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+        uint32_t wd = W[0];
+        W[0] += row0_delta;
+        for (int i = 1; i <= m; i++) {
+            const uint32_t wl = W[i];
+            const bool eq = li >= 0 && ((P.peq[li][(i - 1) >> 5] >> ((i - 1) & 31)) & 1u);
+            const uint32_t cd = wd + (eq ? D_MATCH : D_MIS);
+            const uint32_t cu = W[i - 1] + D_INS;
+            const uint32_t cl = wl + D_DEL;
+            W[i] = __vimin3_u32(cd, cu, cl) & PRIO_CLEAR;
+            wd = wl;
+        }
+        if (eiq) row_m_update(W[m], j, m, n, P, best);
+    }
+    if (max_n == n) {
+        const int first_i = eir ? 0 : m;
+        for (int i = m; i >= first_i; i--) last_col_update(W[i], i, n, P, best);
+    }
+    best_to_match(best, m, n, P.reversed != 0, r);
+}
+
+// CUT / COND_CUT / RENAME(capture) on the interval state.
+__device__ __forceinline__ void apply_scalar(const DevOp& op, ReadState& st) {
+    const int len = (int)st.b - (int)st.a;
+    if (op.kind == CSQ_OP_RENAME) {
+        st.ren_cp = st.cp;
+        st.ren_cs = st.cs;
+        return;
+    }
+    if (op.kind == CSQ_OP_COND_CUT && !(st.matched & 0x80000000u) && len < op.fmin) return;  // run.py:154-155
+    if (op.kind == CSQ_OP_CUT || op.kind == CSQ_OP_COND_CUT) {
+        if (op.length > 0) {
+            const int c = min(op.length, len);
+            st.cp = ((uint32_t)st.a << 16) | (uint32_t)c;
+            st.a = (uint16_t)(st.a + c);
+        } else if (op.length < 0) {
+            const int c = min(-op.length, len);
+            st.cs = ((uint32_t)(st.b - c) << 16) | (uint32_t)c;
+            st.b = (uint16_t)(st.b - c);
+        }
+    }
+}
+
+__device__ __forceinline__ ReadState fresh_state(uint32_t len) {
+    ReadState st;
+    st.a = 0;
+    st.b = (uint16_t)len;
+    st.matched = 0;
+    st.cp = st.cs = st.ren_cp = st.ren_cs = 0;
+    st.id_start = st.id_end = 0;
+    st.qtrim = 0;
+    return st;
+}
+
+__device__ __forceinline__ ReadState load_state(const ReadState* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 x = q[0], y = q[1];
+    ReadState st;
+    st.a = (uint16_t)(x.x & 0xFFFFu);
+    st.b = (uint16_t)(x.x >> 16);
+    st.matched = x.y;
+    st.cp = x.z;
+    st.cs = x.w;
+    st.ren_cp = y.x;
+    st.ren_cs = y.y;
+    st.id_start = (uint16_t)(y.z & 0xFFFFu);
+    st.id_end = (uint16_t)(y.z >> 16);
+    st.qtrim = y.w;
+    return st;
+}
+
+__device__ __forceinline__ void store_state(ReadState* p, const ReadState& st) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4((uint32_t)st.a | ((uint32_t)st.b << 16), st.matched, st.cp, st.cs);
+    q[1] = make_uint4(st.ren_cp, st.ren_cs, (uint32_t)st.id_start | ((uint32_t)st.id_end << 16), st.qtrim);
+}
+
+template <int M, bool HOMO>
+__global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
+    constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
+    __shared__ uint32_t lut[(HOMO || M == 0) ? 1 : 256 * NW];
+    if constexpr (!HOMO && M > 0) {
+        for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+            const int u = c & 0xDF;
+            const int li = u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : -1;
+#pragma unroll
+            for (int w = 0; w < NW; w++) lut[c * NW + w] = li >= 0 ? P.peq[li][w] : 0u;
+        }
+        __syncthreads();
+    }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = P.list ? *P.list_count : P.n;
+    if (t >= count) return;
+    const uint32_t idx = P.list ? P.list[t] : t;
+    ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
+    for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
+
+    const uint8_t* s = P.md.seq + P.md.seq_off[idx];
+    csq_match r;
+    if constexpr (M > 0)
+        dp_exact<M, HOMO>(s, st.a, st.b, P, lut, r);
+    else
+        dp_generic(s, st.a, st.b, P, r);
+    if (r.found) {
+        st.matched |= 0x80000000u | (P.adapter_bit >= 0 ? (1u << P.adapter_bit) : 0u);
+        if (P.trim_front)
+            st.a = (uint16_t)(st.a + r.query_stop);  // RemoveBeforeMatch: read[rstop:]
+        else
+            st.b = (uint16_t)(st.a + r.query_start);  // RemoveAfterMatch: read[:rstart]
+        atomicAdd(P.counters + P.counter_index, 1ULL);
+    }
+    if (P.matches) P.matches[idx] = r;
+    store_state(P.md.state + idx, st);
+}
+
+__device__ __forceinline__ bool is_py_space(uint32_t c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
+
+// Trailing scalar ops, QualityTrimmer (quality_trim_index of qualtrim.pyx), SuffixRemover on the
+// header and Renamer.parse_name's id.
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishParams P) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long qsum = 0, bpsum = 0;
+    if (idx < P.n) {
+        const uint32_t len0 = P.md.seq_len[idx];
+        ReadState st = P.first ? fresh_state(len0) : load_state(P.md.state + idx);
+        for (int q = 0; q < P.n_post; q++) apply_scalar(P.post[q], st);
+        if (P.has_qtrim) {
+            const uint8_t* ql = P.md.qual + P.md.seq_off[idx];
+            const int a = st.a, n = (int)st.b - (int)st.a;
+            int start = 0, stop = n, s = 0, mx = 0;
+            for (int i = 0; i < n; i++) {
+                s += P.cutoff_front - ((int)ql[a + i] - P.qbase);
+                if (s < 0) break;
+                if (s > mx) {
+                    mx = s;
+                    start = i + 1;
+                }
+            }
+            mx = 0;
+            s = 0;
+            for (int i = n - 1; i >= 0; i--) {
+                s += P.cutoff_back - ((int)ql[a + i] - P.qbase);
+                if (s < 0) break;
+                if (s > mx) {
+                    mx = s;
+                    stop = i;
+                }
+            }
+            if (start >= stop) start = stop = 0;
+            st.qtrim = (uint32_t)(n - (stop - start));
+            st.b = (uint16_t)(a + stop);
+            st.a = (uint16_t)(a + start);
+            qsum = st.qtrim;
+        }
+        // header: SuffixRemover ops in order, then the id of Renamer.parse_name
+        const uint8_t* nm = P.md.name + P.md.name_off[idx];
+        int nl = (int)(P.md.name_off[idx + 1] - P.md.name_off[idx]);
+        for (int q = 0; q < P.n_suffix; q++) {
+            const int sl = P.suffix_len[q];
+            if (nl >= sl) {
+                bool eq = true;
+                for (int x = 0; x < sl; x++) eq = eq && (nm[nl - sl + x] == (uint8_t)P.suffix[q][x]);
+                if (eq) nl -= sl;
+            }
+        }
+        int p = 0;
+        while (p < nl && is_py_space(nm[p])) p++;
+        const int s0 = p;
+        while (p < nl && !is_py_space(nm[p])) p++;
+        const int e0 = p;
+        while (p < nl && is_py_space(nm[p])) p++;
+        if (P.has_rename && e0 > s0 && p < nl) {
+            st.id_start = (uint16_t)s0;
+            st.id_end = (uint16_t)e0;
+        } else {
+            st.id_start = 0;
+            st.id_end = (uint16_t)min(nl, 65535);
+        }
+        store_state(P.md.state + idx, st);
+        bpsum = len0;
+    }
+    // block-level reduction of the two statistics
+    __shared__ unsigned long long sh[2];
+    if (threadIdx.x == 0) sh[0] = sh[1] = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        qsum += __shfl_down_sync(0xffffffffu, qsum, o);
+        bpsum += __shfl_down_sync(0xffffffffu, bpsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh[0], qsum);
+        atomicAdd(&sh[1], bpsum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh[0]) atomicAdd(P.counters + CNT_QTRIM_BP + P.mate, sh[0]);
+        if (sh[1]) atomicAdd(P.counters + CNT_TOTAL_BP + P.mate, sh[1]);
+    }
+}
+
+struct RecordShape {
+    uint32_t id_len, umi_len, seq_len, total;
+    uint32_t lenA, lenB;
+};
+
+__device__ __forceinline__ RecordShape record_shape(const PairParams& P, const ReadState& own, const ReadState& r1,
+                                                    const ReadState& r2) {
+    RecordShape rs;
+    rs.id_len = (uint32_t)own.id_end - (uint32_t)own.id_start;
+    rs.lenA = rs.lenB = 0;
+    if (P.rename_parts & CSQ_REN_OWN_PREFIX) rs.lenA = own.ren_cp & 0xFFFFu;
+    if (P.rename_parts & CSQ_REN_OWN_SUFFIX) rs.lenB = own.ren_cs & 0xFFFFu;
+    if (P.rename_parts & CSQ_REN_R1_PREFIX) rs.lenA = r1.ren_cp & 0xFFFFu;
+    if (P.rename_parts & CSQ_REN_R2_PREFIX) rs.lenB = r2.ren_cp & 0xFFFFu;
+    rs.umi_len = (P.rename_parts ? 1u : 0u) + rs.lenA + rs.lenB;
+    rs.seq_len = (uint32_t)own.b - (uint32_t)own.a;
+    rs.total = 1 + rs.id_len + rs.umi_len + 1 + rs.seq_len + 3 + rs.seq_len + 1;
+    return rs;
+}
+
+// Filters + sink of run.py:446-471 / 763-792 and the byte size of every record.
+__global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_pair(const __grid_constant__ PairParams P) {
+    __shared__ unsigned int tot[8];
+    __shared__ unsigned int cnt[4];
+    __shared__ unsigned long long stat[8];
+    if (threadIdx.x < 8) {
+        tot[threadIdx.x] = 0;
+        stat[threadIdx.x] = 0;
+    }
+    if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * CSQ_PAIR_BLOCK + threadIdx.x;
+    if (idx < P.n) {
+        const bool paired = P.n_mates == 2;
+        const ReadState s1 = load_state(P.md[0].state + idx);
+        const ReadState s2 = paired ? load_state(P.md[1].state + idx) : s1;
+        const int l1 = (int)s1.b - (int)s1.a, l2 = (int)s2.b - (int)s2.a;
+        int dest;
+        if (l1 < P.min_length || (paired && l2 < P.min_length))
+            dest = CSQ_DEST_SHORT;
+        else if (P.untrimmed_enabled && ((P.required[0] & ~s1.matched) != 0 || (paired && (P.required[1] & ~s2.matched) != 0)))
+            dest = CSQ_DEST_UNTRIMMED;
+        else
+            dest = CSQ_DEST_TRIMMED;
+        P.dest[idx] = (uint8_t)dest;
+        const RecordShape a = record_shape(P, s1, s1, s2);
+        P.rec_len[idx] = a.total;
+        atomicAdd(&tot[dest * 2 + 0], a.total);
+        if (paired) {
+            const RecordShape b = record_shape(P, s2, s1, s2);
+            P.rec_len[P.n + idx] = b.total;
+            atomicAdd(&tot[dest * 2 + 1], b.total);
+        }
+        atomicAdd(&cnt[dest], 1u);
+        if (dest == CSQ_DEST_TRIMMED) {
+            atomicAdd(&stat[0], 1ULL);
+            atomicAdd(&stat[1], (unsigned long long)l1);
+            if (paired) atomicAdd(&stat[2], (unsigned long long)l2);
+        } else if (dest == CSQ_DEST_SHORT) {
+            atomicAdd(&stat[3], 1ULL);
+        } else {
+            atomicAdd(&stat[4], 1ULL);
+        }
+        if (P.check_ids && paired) {  // PairedEndRenamer: ids must be identical
+            const uint32_t n1 = (uint32_t)s1.id_end - s1.id_start, n2 = (uint32_t)s2.id_end - s2.id_start;
+            bool same = n1 == n2;
+            if (same) {
+                const uint8_t* p1 = P.md[0].name + P.md[0].name_off[idx] + s1.id_start;
+                const uint8_t* p2 = P.md[1].name + P.md[1].name_off[idx] + s2.id_start;
+                for (uint32_t x = 0; x < n1; x++) same = same && (p1[x] == p2[x]);
+            }
+            if (!same) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) P.block_tot[blockIdx.x * 8 + threadIdx.x] = tot[threadIdx.x];
+    if (threadIdx.x < 4) P.block_cnt[blockIdx.x * 4 + threadIdx.x] = cnt[threadIdx.x];
+    if (threadIdx.x == 0) {
+        atomicAdd(P.counters + CNT_N, (unsigned long long)min((uint32_t)CSQ_PAIR_BLOCK, P.n - blockIdx.x * CSQ_PAIR_BLOCK));
+        if (stat[0]) atomicAdd(P.counters + CNT_WRITTEN, stat[0]);
+        if (stat[1]) atomicAdd(P.counters + CNT_WRITTEN_BP, stat[1]);
+        if (stat[2]) atomicAdd(P.counters + CNT_WRITTEN_BP + 1, stat[2]);
+        if (stat[3]) atomicAdd(P.counters + CNT_TOO_SHORT, stat[3]);
+        if (stat[4]) atomicAdd(P.counters + CNT_UNTRIMMED, stat[4]);
+    }
+}
+
+// Exclusive scan over CTAs of the 8 stream totals (6 used) -> byte offset of every CTA in every
+// output stream; totals[0..7] = bytes per stream, totals[8..11] = records per destination.
+__global__ void __launch_bounds__(1024) k_scan(uint32_t nblk, const uint32_t* __restrict__ block_tot,
+                                               const uint32_t* __restrict__ block_cnt,
+                                               unsigned long long* __restrict__ block_off,
+                                               unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long warp_sums[32];
+    __shared__ unsigned long long carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int stream = 0; stream < 8; stream++) {
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < nblk; base += 1024) {
+            const uint32_t i = base + threadIdx.x;
+            const unsigned long long v = i < nblk ? block_tot[i * 8 + stream] : 0ULL;
+            unsigned long long x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) warp_sums[wid] = x;
+            __syncthreads();
+            if (wid == 0) {
+                unsigned long long ws = warp_sums[lane];
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned long long y = __shfl_up_sync(0xffffffffu, ws, o);
+                    if (lane >= o) ws += y;
+                }
+                warp_sums[lane] = ws;
+            }
+            __syncthreads();
+            const unsigned long long before = carry + (wid ? warp_sums[wid - 1] : 0ULL) + (x - v);
+            if (i < nblk) block_off[i * 8 + stream] = before;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = before + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) totals[stream] = carry;
+        __syncthreads();
+    }
+    // record counts per destination
+    for (int d = 0; d < 4; d++) {
+        unsigned long long s = 0;
+        for (uint32_t i = threadIdx.x; i < nblk; i += 1024) s += block_cnt[i * 4 + d];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (lane == 0) warp_sums[wid] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int w = 0; w < 32; w++) t += warp_sums[w];
+            totals[8 + d] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint8_t complement_base(uint8_t c) {
+    // dnaio reverse_complement table: ACGTUMRWSYKVHDBN -> TGCAAKYWSRMBDHVN (case kept), others unchanged
+    const char* from = "ACGTUMRWSYKVHDBNacgtumrwsykvhdbn";
+    const char* to = "TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn";
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+        if (c == (uint8_t)from[i]) return (uint8_t)to[i];
+    return c;
+}
+
+// FASTQ text, "@name\nseq\n+\nqual\n" (dnaio), one warp per record, streams in input order.
+__global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__ EmitParams E) {
+    const PairParams& P = E.pp;
+    __shared__ unsigned int loc[2][CSQ_PAIR_BLOCK];  // exclusive offset of each record inside its stream, CTA-local
+    __shared__ unsigned int run[8];
+    const uint32_t base = blockIdx.x * CSQ_PAIR_BLOCK;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool paired = P.n_mates == 2;
+    if (threadIdx.x < 8) run[threadIdx.x] = 0;
+    __syncthreads();
+    // CTA-local exclusive offsets: warp w owns pairs [32w, 32w+32); warps go in order.
+    for (int w = 0; w < CSQ_PAIR_BLOCK / 32; w++) {
+        if (wid == w) {
+            const uint32_t idx = base + threadIdx.x;
+            const bool live = idx < P.n;
+            const int dest = live ? P.dest[idx] : -1;
+            for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
+                const uint32_t len = live ? P.rec_len[mt * P.n + idx] : 0u;
+                uint32_t myoff = 0;
+                for (int d = 0; d < CSQ_N_DEST; d++) {
+                    const uint32_t v = dest == d ? len : 0u;
+                    uint32_t x = v;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                        if (lane >= o) x += y;
+                    }
+                    const uint32_t r0 = run[d * 2 + mt];
+                    if (dest == d) myoff = r0 + x - v;
+                    const uint32_t tot = __shfl_sync(0xffffffffu, x, 31);
+                    __syncwarp();
+                    if (lane == 0) run[d * 2 + mt] = r0 + tot;
+                    __syncwarp();
+                }
+                loc[mt][threadIdx.x] = myoff;
+            }
+        }
+        __syncthreads();
+    }
+    // copy: each warp writes its 32 pairs, all lanes cooperate on one record at a time
+    for (int q = 0; q < 32; q++) {
+        const uint32_t idx = base + wid * 32 + q;
+        if (idx >= P.n) break;
+        const int dest = P.dest[idx];
+        const ReadState s1 = load_state(P.md[0].state + idx);
+        const ReadState s2 = paired ? load_state(P.md[1].state + idx) : s1;
+        for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
+            const ReadState& own = mt ? s2 : s1;
+            const RecordShape rs = record_shape(P, own, s1, s2);
+            const MateDev& md = P.md[mt];
+            const uint8_t* nm = md.name + md.name_off[idx] + own.id_start;
+            const uint8_t* sq = md.seq + md.seq_off[idx];
+            const uint8_t* ql = md.qual + md.seq_off[idx];
+            const uint8_t *pa = nullptr, *pb = nullptr;
+            if (P.rename_parts & CSQ_REN_OWN_PREFIX) pa = sq + (own.ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_OWN_SUFFIX) pb = sq + (own.ren_cs >> 16);
+            if (P.rename_parts & CSQ_REN_R1_PREFIX) pa = P.md[0].seq + P.md[0].seq_off[idx] + (s1.ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_R2_PREFIX) pb = P.md[1].seq + P.md[1].seq_off[idx] + (s2.ren_cp >> 16);
+            uint8_t* out = E.out[dest][mt] + E.block_off[(size_t)blockIdx.x * 8 + dest * 2 + mt] + loc[mt][wid * 32 + q];
+            const uint32_t e_name = 1 + rs.id_len;
+            const uint32_t e_umi = e_name + rs.umi_len;  // position of the '\n' after the header
+            const uint32_t e_seq = e_umi + 1 + rs.seq_len;
+            const uint32_t e_qual = e_seq + 3 + rs.seq_len;
+            const uint32_t a = own.a, b = own.b;
+            for (uint32_t p = lane; p < rs.total; p += 32) {
+                uint8_t ch;
+                if (p < e_name) {
+                    ch = p == 0 ? (uint8_t)'@' : nm[p - 1];
+                } else if (p < e_umi) {
+                    uint32_t x = p - e_name;
+                    if (x == 0)
+                        ch = '_';
+                    else {
+                        x -= 1;
+                        ch = x < rs.lenA ? pa[x] : pb[x - rs.lenA];
+                    }
+                } else if (p == e_umi) {
+                    ch = '\n';
+                } else if (p < e_seq) {
+                    const uint32_t x = p - e_umi - 1;
+                    ch = P.revcomp ? complement_base(sq[b - 1 - x]) : sq[a + x];
+                } else if (p < e_seq + 3) {
+                    ch = (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
+                } else if (p < e_qual) {
+                    const uint32_t x = p - e_seq - 3;
+                    ch = P.revcomp ? ql[b - 1 - x] : ql[a + x];
+                } else {
+                    ch = '\n';
+                }
+                out[p] = ch;
+            }
+        }
+    }
+}
+
+// Integer-issue microbenchmark: 8 independent dependency chains per thread.
+// variant 0: IADD3 / LOP3 / VIMNMX only (ALU pipe); variant 1: the same mixed with IMAD (FMA pipe).
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_int_peak(int iters, unsigned int* sink) {
+    unsigned int x[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = threadIdx.x * 8 + q + blockIdx.x;
+    const unsigned int c1 = sink[0] | 1u, c2 = sink[1] | 3u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (VARIANT == 0) {
+                    x[q] = min(x[q] + c1, x[q] ^ c2);  // IADD, LOP3, VIMNMX  (3 ops)
+                } else {
+                    x[q] = min(x[q] * c1 + c2, x[q] ^ c2);  // IMAD, LOP3, VIMNMX (3 ops)
+                }
+            }
+        }
+    }
+    unsigned int acc = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc ^= x[q];
+    if (acc == 0x12345678u) sink[2] = acc;
+}
+
+template <int M>
+cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t stream) {
+    const dim3 grid((n_items + 127) / 128), block(128);
+    if constexpr (M == 100) {  // the poly-A / poly-T adapters of run.py:389-404
+        if (p.homopolymer) {
+            k_align<M, true><<<grid, block, 0, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
+    k_align<M, false><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool csq_align_has_exact_kernel(int m) { return (m >= 1 && m <= 34) || m == 100; }
+
+cudaError_t csq_launch_align(const AlignParams& p, uint32_t n_items, cudaStream_t stream) {
+    if (n_items == 0) return cudaSuccess;
+    switch (p.m) {
+#define CSQ_CASE(M) \
+    case M: return launch_align_m<M>(p, n_items, stream);
+        CSQ_CASE(1) CSQ_CASE(2) CSQ_CASE(3) CSQ_CASE(4) CSQ_CASE(5) CSQ_CASE(6) CSQ_CASE(7) CSQ_CASE(8)
+        CSQ_CASE(9) CSQ_CASE(10) CSQ_CASE(11) CSQ_CASE(12) CSQ_CASE(13) CSQ_CASE(14) CSQ_CASE(15) CSQ_CASE(16)
+        CSQ_CASE(17) CSQ_CASE(18) CSQ_CASE(19) CSQ_CASE(20) CSQ_CASE(21) CSQ_CASE(22) CSQ_CASE(23) CSQ_CASE(24)
+        CSQ_CASE(25) CSQ_CASE(26) CSQ_CASE(27) CSQ_CASE(28) CSQ_CASE(29) CSQ_CASE(30) CSQ_CASE(31) CSQ_CASE(32)
+        CSQ_CASE(33) CSQ_CASE(34) CSQ_CASE(100)
+#undef CSQ_CASE
+        default: {
+            const dim3 grid((n_items + 127) / 128), block(128);
+            k_align<0, false><<<grid, block, 0, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
+}
+
+cudaError_t csq_launch_finish(const FinishParams& p, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    k_finish<<<(p.n + 255) / 256, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    k_pair<<<(p.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
+                            unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream) {
+    k_scan<<<1, 1024, 0, stream>>>(nblk, block_tot, block_cnt, block_off, totals);
+    return cudaGetLastError();
+}
+
+cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream) {
+    if (p.pp.n == 0) return cudaSuccess;
+    k_emit<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t csq_launch_int_peak(int variant, int iters, unsigned int* sink, int blocks, int threads, cudaStream_t stream) {
+    if (variant == 0)
+        k_int_peak<0><<<blocks, threads, 0, stream>>>(iters, sink);
+    else
+        k_int_peak<1><<<blocks, threads, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
+}

@@ -1,0 +1,773 @@
+// Host side of the C ABI: plans (compiled op programs), slots (stream + device buffers),
+// batch submit/wait, resident-mode measurement, result accessors.
+// Boundary: include/cutseq_b200.h.  Replaces runner.run(pipeline, ...) of reference
+// run.py:472-473 / 793-794 for one batch of reads.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "csq_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? CSQ_ERR_NOMEM : CSQ_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                           \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(CSQ_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Segment {  // one ALIGN op with the scalar ops in front of it
+    AlignParams ap;
+    int op_index;
+    const char* name;
+};
+
+struct MateProgram {
+    std::vector<Segment> segs;
+    FinishParams fin;
+    uint32_t rename_parts = 0;
+    bool has_rename = false, revcomp = false;
+    int n_ops = 0;
+    std::vector<int> align_slot;  // op index -> index among ALIGN ops, or -1
+    int n_align = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    DevBuf seq[2], qual[2], seq_off[2], seq_len[2], name[2], name_off[2], state[2], matches[2];
+    DevBuf dest, rec_len, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
+    unsigned long long* totals_host = nullptr;  // pinned: 12 totals + error flag
+    uint32_t n = 0;
+    int n_mates = 0;
+    csq_batch_out* pending = nullptr;
+    bool front_done = false;
+    float total_ms = 0, kernel_ms = 0;
+    std::vector<std::pair<const char*, float>> ktimes;
+};
+
+}  // namespace
+
+struct csq_plan {
+    int device = 0;
+    uint32_t flags = 0;
+    int n_mates = 1;
+    MateProgram prog[2];
+    csq_filters flt;
+    Slot slots[CSQ_N_SLOTS];
+    unsigned long long* counters = nullptr;  // device csq_counters
+    int* error_flag = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+const char* kind_name(int k) {
+    switch (k) {
+        case CSQ_AD_BACK: return "k_align(back)";
+        case CSQ_AD_BACK_ANYWHERE: return "k_align(back,anywhere)";
+        case CSQ_AD_RIGHTMOST_FRONT: return "k_align(rightmost_front)";
+        case CSQ_AD_PREFIX: return "k_align(prefix)";
+        case CSQ_AD_SUFFIX: return "k_align(suffix)";
+        case CSQ_AD_NI_FRONT: return "k_align(noninternal_front)";
+        case CSQ_AD_NI_BACK: return "k_align(noninternal_back)";
+        case CSQ_AD_FRONT: return "k_align(front)";
+    }
+    return "k_align";
+}
+
+// csq_op(ALIGN) -> aligner parameters (SingleAdapter.__init__ / _make_aligner of adapters.py)
+int build_align(const csq_op& op, AlignParams& ap) {
+    memset(&ap, 0, sizeof(ap));
+    const int m = op.adapter_len;
+    if (m < 1 || m > CSQ_MAX_ADAPTER) return fail(CSQ_ERR_LIMIT, "adapter length %d outside 1..%d", m, CSQ_MAX_ADAPTER);
+    int flags, reversed = 0, front = 0;
+    switch (op.adapter_kind) {
+        case CSQ_AD_BACK: flags = 14; break;
+        case CSQ_AD_BACK_ANYWHERE: flags = 15; break;
+        case CSQ_AD_RIGHTMOST_FRONT: flags = 14; reversed = 1; front = 1; break;
+        case CSQ_AD_PREFIX: flags = 8; front = 1; break;
+        case CSQ_AD_SUFFIX: flags = 2; break;
+        case CSQ_AD_NI_FRONT: flags = 9; front = 1; break;
+        case CSQ_AD_NI_BACK: flags = 6; break;
+        case CSQ_AD_FRONT: flags = 11; front = 1; break;
+        default: return fail(CSQ_ERR_INVALID, "unknown adapter kind %d", op.adapter_kind);
+    }
+    double rate = op.max_error_rate;
+    if (rate >= 1.0) rate /= m;  // an absolute error count (SingleAdapter.__init__)
+    if (!(rate >= 0.0)) return fail(CSQ_ERR_INVALID, "bad max_error_rate");
+    int mo = op.min_overlap < m ? op.min_overlap : m;
+    if (op.adapter_kind == CSQ_AD_PREFIX || op.adapter_kind == CSQ_AD_SUFFIX) mo = m;
+    if (mo < 1) return fail(CSQ_ERR_INVALID, "min_overlap must be >= 1");
+    ap.m = m;
+    ap.flags = flags;
+    ap.reversed = reversed;
+    ap.trim_front = front;
+    ap.min_overlap = mo;
+    ap.k = (int)(rate * m);
+    ap.adapter_bit = (op.adapter_id >= 0 && op.adapter_id <= 30) ? op.adapter_id : -1;
+    for (int L = 0; L <= m; L++) {
+        // largest integer cost with cost <= L * rate in IEEE double, as Aligner.locate compares
+        double lim = L * rate;
+        int t = (int)floor(lim);
+        if (t > 255) t = 255;
+        ap.thr[L] = (uint8_t)t;
+    }
+    bool homo = true;
+    for (int i = 0; i < m; i++) {
+        char c = op.adapter[reversed ? (m - 1 - i) : i];
+        if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+        if (c == 'U') c = 'T';
+        int li = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+        if (li < 0) return fail(CSQ_ERR_INVALID, "adapter character '%c' is not one of ACGT", c);
+        ap.peq[li][i >> 5] |= 1u << (i & 31);
+        if (i == 0) ap.letter = (uint8_t)c;
+        if ((uint8_t)c != ap.letter) homo = false;
+    }
+    ap.homopolymer = homo ? 1 : 0;
+    return 0;
+}
+
+int build_mate_program(const csq_op* ops, int n, int mate, MateProgram& mp) {
+    if (n < 0 || n > CSQ_MAX_OPS) return fail(CSQ_ERR_INVALID, "program of %d ops (max %d)", n, CSQ_MAX_OPS);
+    mp = MateProgram();
+    mp.n_ops = n;
+    mp.align_slot.assign(n, -1);
+    memset(&mp.fin, 0, sizeof(mp.fin));
+    mp.fin.mate = mate;
+    std::vector<DevOp> pending;
+    bool seen_qtrim = false;
+    for (int t = 0; t < n; t++) {
+        const csq_op& op = ops[t];
+        if (seen_qtrim && op.kind != CSQ_OP_REVCOMP)
+            return fail(CSQ_ERR_INVALID, "op %d: only REVCOMP may follow QTRIM", t);
+        switch (op.kind) {
+            case CSQ_OP_STRIP_SUFFIX:
+                if (mp.has_rename) return fail(CSQ_ERR_INVALID, "op %d: STRIP_SUFFIX must come before RENAME", t);
+                if (mp.fin.n_suffix >= 4 || op.suffix_len < 0 || op.suffix_len > CSQ_MAX_SUFFIX)
+                    return fail(CSQ_ERR_INVALID, "op %d: too many / too long name suffixes", t);
+                mp.fin.suffix_len[mp.fin.n_suffix] = op.suffix_len;
+                memcpy(mp.fin.suffix[mp.fin.n_suffix], op.suffix, (size_t)op.suffix_len);
+                mp.fin.n_suffix++;
+                break;
+            case CSQ_OP_CUT:
+            case CSQ_OP_COND_CUT:
+            case CSQ_OP_RENAME: {
+                DevOp d = {op.kind, op.length, op.force_trim_min_length, op.rename_parts};
+                if (op.kind == CSQ_OP_RENAME) {
+                    if (mp.has_rename) return fail(CSQ_ERR_INVALID, "op %d: more than one RENAME", t);
+                    mp.has_rename = true;
+                    mp.rename_parts = op.rename_parts;
+                }
+                if (op.kind != CSQ_OP_RENAME && (op.length > 65535 || op.length < -65535))
+                    return fail(CSQ_ERR_INVALID, "op %d: cut length out of range", t);
+                pending.push_back(d);
+                if (pending.size() > CSQ_MAX_PRE) return fail(CSQ_ERR_INVALID, "more than %d scalar ops in a row", CSQ_MAX_PRE);
+                break;
+            }
+            case CSQ_OP_ALIGN: {
+                Segment s;
+                int rc = build_align(op, s.ap);
+                if (rc) return rc;
+                s.op_index = t;
+                s.name = kind_name(op.adapter_kind);
+                s.ap.n_pre = (int)pending.size();
+                for (size_t q = 0; q < pending.size(); q++) s.ap.pre[q] = pending[q];
+                pending.clear();
+                s.ap.first = mp.segs.empty() ? 1 : 0;
+                s.ap.counter_index = CNT_WITH_ADAPTERS + mate * CSQ_MAX_OPS + t;
+                mp.align_slot[t] = mp.n_align++;
+                mp.segs.push_back(s);
+                break;
+            }
+            case CSQ_OP_QTRIM:
+                seen_qtrim = true;
+                mp.fin.has_qtrim = 1;
+                mp.fin.cutoff_front = op.cutoff_front;
+                mp.fin.cutoff_back = op.cutoff_back;
+                mp.fin.qbase = op.quality_base;
+                break;
+            case CSQ_OP_REVCOMP:
+                if (t != n - 1) return fail(CSQ_ERR_INVALID, "REVCOMP must be the last op");
+                mp.revcomp = true;
+                break;
+            default: return fail(CSQ_ERR_INVALID, "op %d: unknown kind %d", t, op.kind);
+        }
+    }
+    mp.fin.n_post = (int)pending.size();
+    for (size_t q = 0; q < pending.size(); q++) mp.fin.post[q] = pending[q];
+    mp.fin.first = mp.segs.empty() ? 1 : 0;
+    mp.fin.has_rename = mp.has_rename ? 1 : 0;
+    return 0;
+}
+
+int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CSQ_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(CSQ_ERR_NO_DEVICE, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(CSQ_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor);
+    return 0;
+}
+
+MateDev mate_dev(Slot& s, int m) {
+    MateDev d;
+    d.seq = (const uint8_t*)s.seq[m].p;
+    d.qual = (const uint8_t*)s.qual[m].p;
+    d.seq_off = (const uint32_t*)s.seq_off[m].p;
+    d.seq_len = (const uint32_t*)s.seq_len[m].p;
+    d.name = (const uint8_t*)s.name[m].p;
+    d.name_off = (const uint32_t*)s.name_off[m].p;
+    d.state = (ReadState*)s.state[m].p;
+    return d;
+}
+
+int validate_batch(const csq_plan* plan, const csq_batch_in* in) {
+    if (!in) return fail(CSQ_ERR_INVALID, "null batch");
+    if ((int)in->n_mates != plan->n_mates) return fail(CSQ_ERR_INVALID, "batch has %u mates, plan has %d", in->n_mates, plan->n_mates);
+    for (int m = 0; m < plan->n_mates; m++) {
+        const csq_mate_in& mi = in->mate[m];
+        if (in->n_reads && (!mi.seq || !mi.qual || !mi.seq_off || !mi.seq_len || !mi.name || !mi.name_off))
+            return fail(CSQ_ERR_INVALID, "mate %d: null array (FASTA input without qualities is not supported)", m + 1);
+        if (mi.seq_bytes >= (1ull << 32) || mi.name_bytes >= (1ull << 32)) return fail(CSQ_ERR_LIMIT, "batch pools must stay below 4 GiB");
+        uint32_t mx = 0;
+        for (uint32_t i = 0; i < in->n_reads; i++) mx = mi.seq_len[i] > mx ? mi.seq_len[i] : mx;
+        if (mx > CSQ_MAX_READ_LEN) return fail(CSQ_ERR_LIMIT, "mate %d: read of %u bases exceeds the supported %d", m + 1, mx, CSQ_MAX_READ_LEN);
+    }
+    return 0;
+}
+
+int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
+    const uint32_t n = in->n_reads;
+    s.n = n;
+    s.n_mates = plan->n_mates;
+    s.front_done = false;
+    const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
+    for (int m = 0; m < plan->n_mates; m++) {
+        const csq_mate_in& mi = in->mate[m];
+        int rc;
+        if ((rc = s.seq[m].ensure(mi.seq_bytes + 16))) return rc;
+        if ((rc = s.qual[m].ensure(mi.seq_bytes + 16))) return rc;
+        if ((rc = s.seq_off[m].ensure((size_t)n * 4 + 4))) return rc;
+        if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 4))) return rc;
+        if ((rc = s.name[m].ensure(mi.name_bytes + 16))) return rc;
+        if ((rc = s.name_off[m].ensure(((size_t)n + 1) * 4))) return rc;
+        if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
+        if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
+            if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
+        if (n) {
+            CUDA_TRY(cudaMemcpyAsync(s.seq[m].p, mi.seq, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.qual[m].p, mi.qual, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.seq_off[m].p, mi.seq_off, (size_t)n * 4, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.seq_len[m].p, mi.seq_len, (size_t)n * 4, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.name[m].p, mi.name, mi.name_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.name_off[m].p, mi.name_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+        }
+    }
+    int rc;
+    if ((rc = s.dest.ensure((size_t)n + 16))) return rc;
+    if ((rc = s.rec_len.ensure((size_t)n * 8 + 16))) return rc;
+    if ((rc = s.block_tot.ensure((size_t)nblk * 32 + 32))) return rc;
+    if ((rc = s.block_cnt.ensure((size_t)nblk * 16 + 16))) return rc;
+    if ((rc = s.block_off.ensure((size_t)nblk * 64 + 64))) return rc;
+    if ((rc = s.totals.ensure(16 * 8))) return rc;
+    return 0;
+}
+
+struct KernelTimer {  // optional per-kernel CUDA-event timing (resident mode, last iteration)
+    bool on = false;
+    cudaStream_t stream;
+    std::vector<cudaEvent_t> evs;
+    std::vector<const char*> names;
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        evs.push_back(e);
+        names.push_back(name);
+    }
+};
+
+PairParams pair_params(csq_plan* plan, Slot& s) {
+    PairParams pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int m = 0; m < plan->n_mates; m++) pp.md[m] = mate_dev(s, m);
+    pp.n = s.n;
+    pp.n_mates = plan->n_mates;
+    pp.min_length = plan->flt.min_length;
+    pp.untrimmed_enabled = plan->flt.untrimmed_enabled;
+    pp.required[0] = plan->flt.required_r1;
+    pp.required[1] = plan->flt.required_r2;
+    pp.rename_parts = plan->prog[0].rename_parts;
+    pp.check_ids = (plan->n_mates == 2 && plan->prog[0].has_rename) ? 1 : 0;
+    pp.revcomp = plan->prog[0].revcomp ? 1 : 0;
+    pp.dest = (uint8_t*)s.dest.p;
+    pp.rec_len = (uint32_t*)s.rec_len.p;
+    pp.block_tot = (uint32_t*)s.block_tot.p;
+    pp.block_cnt = (uint32_t*)s.block_cnt.p;
+    pp.counters = plan->counters;
+    pp.error_flag = plan->error_flag;
+    return pp;
+}
+
+// align ... scan, then the 12 totals + error flag to pinned host memory
+int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt) {
+    const uint32_t n = s.n;
+    const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
+    if (kt) kt->mark("begin");
+    for (int m = 0; m < plan->n_mates; m++) {
+        MateProgram& mp = plan->prog[m];
+        for (Segment& sg : mp.segs) {
+            AlignParams ap = sg.ap;
+            ap.md = mate_dev(s, m);
+            ap.n = n;
+            ap.list = nullptr;
+            ap.list_count = nullptr;
+            ap.counters = plan->counters;
+            ap.matches = (plan->flags & CSQ_PLAN_KEEP_MATCHES)
+                             ? (csq_match*)s.matches[m].p + (size_t)mp.align_slot[sg.op_index] * n
+                             : nullptr;
+            CUDA_TRY(csq_launch_align(ap, n, s.stream));
+            plan->launches += n ? 1 : 0;
+            if (kt) kt->mark(sg.name);
+        }
+        FinishParams fp = mp.fin;
+        fp.md = mate_dev(s, m);
+        fp.n = n;
+        fp.counters = plan->counters;
+        CUDA_TRY(csq_launch_finish(fp, s.stream));
+        plan->launches += n ? 1 : 0;
+        if (kt) kt->mark(m == 0 ? "k_finish.r1" : "k_finish.r2");
+    }
+    PairParams pp = pair_params(plan, s);
+    CUDA_TRY(csq_launch_pair(pp, s.stream));
+    plan->launches += n ? 1 : 0;
+    if (kt) kt->mark("k_pair");
+    CUDA_TRY(csq_launch_scan(nblk, (const uint32_t*)s.block_tot.p, (const uint32_t*)s.block_cnt.p,
+                             (unsigned long long*)s.block_off.p, (unsigned long long*)s.totals.p, s.stream));
+    plan->launches += 1;
+    if (kt) kt->mark("k_scan");
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host, s.totals.p, 12 * 8, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 12, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    s.front_done = true;
+    return 0;
+}
+
+int size_outputs(Slot& s) {
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < 2; m++) {
+            int rc = s.out[d][m].ensure((size_t)s.totals_host[d * 2 + m] + 64);
+            if (rc) return rc;
+        }
+    return 0;
+}
+
+int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt) {
+    EmitParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.pp = pair_params(plan, s);
+    ep.block_off = (const unsigned long long*)s.block_off.p;
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < 2; m++) ep.out[d][m] = (uint8_t*)s.out[d][m].p;
+    CUDA_TRY(csq_launch_emit(ep, s.stream));
+    plan->launches += s.n ? 1 : 0;
+    if (kt) kt->mark("k_emit");
+    return 0;
+}
+
+int check_device_error(Slot& s) {
+    int flag = *(int*)(s.totals_host + 12);
+    if (flag == CSQ_ERR_PAIRING) return fail(CSQ_ERR_PAIRING, "Input read IDs not identical in a pair");
+    if (flag) return fail(flag, "device reported error %d", flag);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int csq_abi_version(void) { return CSQ_ABI_VERSION; }
+
+const char* csq_last_error(void) { return g_err; }
+
+int csq_device_count(int* count) {
+    if (!count) return fail(CSQ_ERR_INVALID, "null argument");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(CSQ_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    int ok = 0;
+    for (int d = 0; d < c; d++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ok++;
+    }
+    *count = ok;
+    return 0;
+}
+
+int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, const csq_filters* filters, int device,
+                    uint32_t flags, csq_plan** out) {
+    if (!out || !filters || (n1 > 0 && !ops_r1) || (n2 > 0 && !ops_r2)) return fail(CSQ_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    csq_plan* plan = new csq_plan();
+    plan->device = device;
+    plan->flags = flags;
+    plan->flt = *filters;
+    plan->n_mates = n2 > 0 ? 2 : 1;
+    if ((rc = build_mate_program(ops_r1, n1, 0, plan->prog[0])) || (n2 > 0 && (rc = build_mate_program(ops_r2, n2, 1, plan->prog[1])))) {
+        delete plan;
+        return rc;
+    }
+    if (plan->n_mates == 2) {
+        if (plan->prog[0].has_rename != plan->prog[1].has_rename || plan->prog[0].rename_parts != plan->prog[1].rename_parts) {
+            delete plan;
+            return fail(CSQ_ERR_INVALID, "paired programs must carry the same RENAME");
+        }
+        if (plan->prog[0].revcomp || plan->prog[1].revcomp) {
+            delete plan;
+            return fail(CSQ_ERR_INVALID, "REVCOMP is a single-end op (paired --auto-rc swaps the sink instead)");
+        }
+        if (plan->prog[0].rename_parts & (CSQ_REN_OWN_PREFIX | CSQ_REN_OWN_SUFFIX)) {
+            delete plan;
+            return fail(CSQ_ERR_INVALID, "paired RENAME uses r1/r2 parts");
+        }
+    } else if (plan->prog[0].rename_parts & (CSQ_REN_R1_PREFIX | CSQ_REN_R2_PREFIX)) {
+        delete plan;
+        return fail(CSQ_ERR_INVALID, "single-end RENAME uses own parts");
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&plan->counters, sizeof(csq_counters));
+    if (e == cudaSuccess) e = cudaMemset(plan->counters, 0, sizeof(csq_counters));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&plan->error_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(plan->error_flag, 0, sizeof(int));
+    for (int i = 0; i < CSQ_N_SLOTS && e == cudaSuccess; i++) {
+        Slot& s = plan->slots[i];
+        e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&s.ev[k]);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.totals_host, 16 * 8, cudaHostAllocDefault);
+        if (e == cudaSuccess) memset(s.totals_host, 0, 16 * 8);
+    }
+    if (e != cudaSuccess) {
+        rc = fail(CSQ_ERR_CUDA, "plan setup: %s", cudaGetErrorString(e));
+        csq_plan_destroy(plan);
+        return rc;
+    }
+    *out = plan;
+    return 0;
+}
+
+void csq_plan_destroy(csq_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    for (Slot& s : plan->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        for (int m = 0; m < 2; m++) {
+            s.seq[m].release(); s.qual[m].release(); s.seq_off[m].release(); s.seq_len[m].release();
+            s.name[m].release(); s.name_off[m].release(); s.state[m].release(); s.matches[m].release();
+            for (int d = 0; d < CSQ_N_DEST; d++) s.out[d][m].release();
+        }
+        s.dest.release(); s.rec_len.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
+        for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);
+        if (s.totals_host) cudaFreeHost(s.totals_host);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (plan->counters) cudaFree(plan->counters);
+    if (plan->error_flag) cudaFree(plan->error_flag);
+    delete plan;
+}
+
+int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* out) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || !out) return fail(CSQ_ERR_INVALID, "bad plan/slot/out");
+    int rc = validate_batch(plan, in);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (s.pending) return fail(CSQ_ERR_INVALID, "slot %d still has a batch in flight (call csq_wait)", slot);
+    CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
+    if ((rc = upload(plan, s, in))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
+    if ((rc = enqueue_front(plan, s, nullptr))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
+    s.pending = out;
+    return 0;
+}
+
+int csq_wait(csq_plan* plan, int slot) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS) return fail(CSQ_ERR_INVALID, "bad plan/slot");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (!s.pending) return fail(CSQ_ERR_INVALID, "nothing submitted on slot %d", slot);
+    csq_batch_out* out = s.pending;
+    s.pending = nullptr;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    int rc = check_device_error(s);
+    if (rc) return rc;
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < 2; m++) {
+            csq_text_out& t = out->text[d][m];
+            t.bytes = s.totals_host[d * 2 + m];
+            t.records = (m < s.n_mates) ? s.totals_host[8 + d] : 0;
+            if (t.bytes > t.capacity || (t.bytes && !t.data))
+                return fail(CSQ_ERR_CAPACITY, "output buffer [%d][%d] holds %llu bytes, %llu needed", d, m,
+                            (unsigned long long)t.capacity, (unsigned long long)t.bytes);
+        }
+    if ((rc = size_outputs(s))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[3], s.stream));
+    if ((rc = enqueue_emit(plan, s, nullptr))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[4], s.stream));
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < s.n_mates; m++) {
+            csq_text_out& t = out->text[d][m];
+            if (t.bytes) CUDA_TRY(cudaMemcpyAsync(t.data, s.out[d][m].p, t.bytes, cudaMemcpyDeviceToHost, s.stream));
+        }
+    CUDA_TRY(cudaEventRecord(s.ev[5], s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    float h2d = 0, front = 0, emit = 0, d2h = 0;
+    cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]);
+    cudaEventElapsedTime(&front, s.ev[1], s.ev[2]);
+    cudaEventElapsedTime(&emit, s.ev[3], s.ev[4]);
+    cudaEventElapsedTime(&d2h, s.ev[4], s.ev[5]);
+    s.kernel_ms = front + emit;
+    s.total_ms = h2d + front + emit + d2h;
+    return 0;
+}
+
+int csq_slot_times(csq_plan* plan, int slot, float* total_ms, float* kernel_ms) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS) return fail(CSQ_ERR_INVALID, "bad plan/slot");
+    if (total_ms) *total_ms = plan->slots[slot].total_ms;
+    if (kernel_ms) *kernel_ms = plan->slots[slot].kernel_ms;
+    return 0;
+}
+
+int csq_upload(csq_plan* plan, int slot, const csq_batch_in* in) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS) return fail(CSQ_ERR_INVALID, "bad plan/slot");
+    int rc = validate_batch(plan, in);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if ((rc = upload(plan, s, in))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || iters < 1) return fail(CSQ_ERR_INVALID, "bad plan/slot/iters");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    int rc;
+    // sizing pass (not timed): totals are needed on the host before the emit buffers exist
+    if ((rc = enqueue_front(plan, s, nullptr))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if ((rc = check_device_error(s))) return rc;
+    if ((rc = size_outputs(s))) return rc;
+    if ((rc = enqueue_emit(plan, s, nullptr))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (iters == 1) {  // the sizing pass already did the work once
+        if (ms_per_iter) *ms_per_iter = 0.f;
+        return 0;
+    }
+    KernelTimer kt;
+    kt.stream = s.stream;
+    CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
+    for (int it = 1; it < iters; it++) {
+        kt.on = (it == iters - 1);
+        if ((rc = enqueue_front(plan, s, &kt))) return rc;
+        if ((rc = enqueue_emit(plan, s, &kt))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
+    if (ms_per_iter) *ms_per_iter = ms / (float)(iters - 1);
+    s.ktimes.clear();
+    for (size_t i = 1; i < kt.evs.size(); i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, kt.evs[i - 1], kt.evs[i]);
+        s.ktimes.push_back({kt.names[i], t});
+    }
+    for (cudaEvent_t e : kt.evs) cudaEventDestroy(e);
+    return 0;
+}
+
+int csq_kernel_times(csq_plan* plan, int slot, const char** names, float* ms, int cap) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS) return fail(CSQ_ERR_INVALID, "bad plan/slot");
+    Slot& s = plan->slots[slot];
+    int n = (int)s.ktimes.size() < cap ? (int)s.ktimes.size() : cap;
+    for (int i = 0; i < n; i++) {
+        if (names) names[i] = s.ktimes[i].first;
+        if (ms) ms[i] = s.ktimes[i].second;
+    }
+    return n;
+}
+
+int csq_launch_count(csq_plan* plan, uint64_t* launches) {
+    if (!plan || !launches) return fail(CSQ_ERR_INVALID, "null argument");
+    *launches = plan->launches;
+    return 0;
+}
+
+int csq_fetch_results(csq_plan* plan, int slot, int mate, csq_read_result* out, uint32_t n) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || mate < 0 || mate >= plan->n_mates || !out) return fail(CSQ_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (n > s.n) n = s.n;
+    std::vector<ReadState> st(n);
+    std::vector<uint8_t> dest(n);
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (n) {
+        CUDA_TRY(cudaMemcpy(st.data(), s.state[mate].p, (size_t)n * sizeof(ReadState), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(dest.data(), s.dest.p, n, cudaMemcpyDeviceToHost));
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        out[i].start = st[i].a;
+        out[i].stop = st[i].b;
+        out[i].dest = dest[i];
+        out[i].matched = st[i].matched;
+    }
+    return 0;
+}
+
+int csq_fetch_matches(csq_plan* plan, int slot, int mate, int op_index, csq_match* out, uint32_t n) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || mate < 0 || mate >= plan->n_mates || !out) return fail(CSQ_ERR_INVALID, "bad argument");
+    if (!(plan->flags & CSQ_PLAN_KEEP_MATCHES)) return fail(CSQ_ERR_INVALID, "plan was created without CSQ_PLAN_KEEP_MATCHES");
+    MateProgram& mp = plan->prog[mate];
+    if (op_index < 0 || op_index >= mp.n_ops || mp.align_slot[op_index] < 0) return fail(CSQ_ERR_INVALID, "op %d is not an ALIGN op", op_index);
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (n > s.n) n = s.n;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (n)
+        CUDA_TRY(cudaMemcpy(out, (csq_match*)s.matches[mate].p + (size_t)mp.align_slot[op_index] * s.n, (size_t)n * sizeof(csq_match),
+                            cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int csq_fetch_text(csq_plan* plan, int slot, csq_batch_out* out) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || !out) return fail(CSQ_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < 2; m++) {
+            csq_text_out& t = out->text[d][m];
+            t.bytes = m < s.n_mates ? s.totals_host[d * 2 + m] : 0;
+            t.records = m < s.n_mates ? s.totals_host[8 + d] : 0;
+            if (t.bytes > t.capacity) return fail(CSQ_ERR_CAPACITY, "output buffer [%d][%d] too small (%llu needed)", d, m, (unsigned long long)t.bytes);
+            if (t.bytes) CUDA_TRY(cudaMemcpy(t.data, s.out[d][m].p, t.bytes, cudaMemcpyDeviceToHost));
+        }
+    return 0;
+}
+
+int csq_stats(csq_plan* plan, csq_counters* out) {
+    if (!plan || !out) return fail(CSQ_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    for (Slot& s : plan->slots) CUDA_TRY(cudaStreamSynchronize(s.stream));
+    CUDA_TRY(cudaMemcpy(out, plan->counters, sizeof(csq_counters), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int csq_locate_batch(int device, const csq_op* align_op, const csq_mate_in* reads, uint32_t n_reads, uint32_t plan_flags,
+                     csq_match* out) {
+    if (!align_op || !reads || !out || align_op->kind != CSQ_OP_ALIGN) return fail(CSQ_ERR_INVALID, "bad argument");
+    csq_filters flt = {0, 0, 0, 0};
+    csq_plan* plan = nullptr;
+    int rc = csq_plan_create(align_op, 1, nullptr, 0, &flt, device, plan_flags | CSQ_PLAN_KEEP_MATCHES, &plan);
+    if (rc) return rc;
+    csq_batch_in in;
+    memset(&in, 0, sizeof(in));
+    in.n_reads = n_reads;
+    in.n_mates = 1;
+    in.mate[0] = *reads;
+    rc = csq_upload(plan, 0, &in);
+    if (!rc) rc = csq_run_resident(plan, 0, 1, nullptr);
+    if (!rc) rc = csq_fetch_matches(plan, 0, 0, 0, out, n_reads);
+    csq_plan_destroy(plan);
+    return rc;
+}
+
+int csq_int_peak(int device, double* alu_ops_per_s, double* mixed_ops_per_s) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    unsigned int* sink = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&sink, 16));
+    CUDA_TRY(cudaMemset(sink, 0, 16));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2000;
+    double res[2] = {0, 0};
+    for (int v = 0; v < 2; v++) {
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            CUDA_TRY(cudaEventRecord(e0, 0));
+            CUDA_TRY(csq_launch_int_peak(v, iters, sink, blocks, threads, 0));
+            CUDA_TRY(cudaEventRecord(e1, 0));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            // 3 integer ops per statement, 64 statements per iteration per thread
+            double ops = 3.0 * 64.0 * iters * (double)blocks * threads;
+            double r = ops / (ms * 1e-3);
+            if (rep > 0 && r > best) best = r;
+        }
+        res[v] = best;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (alu_ops_per_s) *alu_ops_per_s = res[0];
+    if (mixed_ops_per_s) *mixed_ops_per_s = res[1];
+    return 0;
+}
+
+}  // extern "C"

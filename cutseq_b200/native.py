@@ -1,0 +1,232 @@
+"""ctypes binding of libcutseq_b200.so (the C ABI of include/cutseq_b200.h).
+
+This is the only execution path of the package: if the CUDA library is missing or no
+B200 is visible, calls fail loudly (``NativeError``); there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcutseq_b200.so")
+_lib = None
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"cutseq_b200 native error {code}: {message}")
+        self.code = code
+
+
+def lib():
+    """Load the CUDA library (built by ``cutseq_b200.build.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(A.ERR_NO_DEVICE, f"{LIB_PATH} is missing - build it with `python -m cutseq_b200.build` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.csq_last_error.restype = C.c_char_p
+    vp, i32, u32, u64p = C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)
+    L.csq_plan_create.argtypes = [C.POINTER(A.csq_op), i32, C.POINTER(A.csq_op), i32, C.POINTER(A.csq_filters), i32, u32, C.POINTER(vp)]
+    L.csq_plan_destroy.argtypes = [vp]
+    L.csq_plan_destroy.restype = None
+    L.csq_submit.argtypes = [vp, i32, C.POINTER(A.csq_batch_in), C.POINTER(A.csq_batch_out)]
+    L.csq_wait.argtypes = [vp, i32]
+    L.csq_slot_times.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.csq_upload.argtypes = [vp, i32, C.POINTER(A.csq_batch_in)]
+    L.csq_run_resident.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
+    L.csq_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]
+    L.csq_launch_count.argtypes = [vp, u64p]
+    L.csq_fetch_results.argtypes = [vp, i32, i32, vp, u32]
+    L.csq_fetch_matches.argtypes = [vp, i32, i32, i32, vp, u32]
+    L.csq_fetch_text.argtypes = [vp, i32, C.POINTER(A.csq_batch_out)]
+    L.csq_stats.argtypes = [vp, C.POINTER(A.csq_counters)]
+    L.csq_locate_batch.argtypes = [i32, C.POINTER(A.csq_op), C.POINTER(A.csq_mate_in), u32, u32, vp]
+    L.csq_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.csq_device_count.argtypes = [C.POINTER(i32)]
+    if hasattr(L, "csq_run_files"):
+        L.csq_run_files.argtypes = [C.POINTER(A.csq_op), i32, C.POINTER(A.csq_op), i32, C.POINTER(A.csq_filters), u32,
+                                    C.POINTER(A.csq_files), C.POINTER(A.csq_counters), C.POINTER(A.csq_timing)]
+        L.csq_reader_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+        L.csq_reader_next.argtypes = [vp, i32, u32, C.POINTER(A.csq_batch_in)]
+        L.csq_reader_close.argtypes = [vp]
+        L.csq_reader_close.restype = None
+        L.csq_parse_fastq_mem.argtypes = [vp, C.c_uint64, u32, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp,
+                                          C.POINTER(u32), u64p, u64p]
+    if hasattr(L, "csq_synth_batch"):
+        L.csq_synth_batch.argtypes = [C.POINTER(A.csq_synth), C.c_uint64, u32, i32, C.POINTER(A.csq_batch_in)]
+        L.csq_synth_free.restype = None
+    if L.csq_abi_version() != A.ABI_VERSION:
+        raise NativeError(A.ERR_INVALID, "ABI version mismatch between libcutseq_b200.so and cutseq_b200/_abi.py")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise NativeError(rc, lib().csq_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().csq_device_count(C.byref(n)))
+    return n.value
+
+
+MATCH_DTYPE = np.dtype([(k, "i2") for k in ("found", "ref_start", "ref_stop", "query_start", "query_stop", "score", "errors", "reserved")])
+RESULT_DTYPE = np.dtype([("start", "u4"), ("stop", "u4"), ("dest", "u4"), ("matched", "u4")])
+
+
+class Plan:
+    """A compiled op program bound to one GPU (``csq_plan``)."""
+
+    def __init__(self, program, device: int = 0, flags: int = 0):
+        self.program = program
+        self._ops1, self._n1 = program.c_ops(0)
+        self._ops2, self._n2 = program.c_ops(1)
+        self._flt = program.filters.to_c()
+        self._h = C.c_void_p()
+        self.device = device
+        check(lib().csq_plan_create(self._ops1, self._n1, self._ops2, self._n2 if program.paired else 0,
+                                    C.byref(self._flt), device, flags, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().csq_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- batch execution with host buffers (the end-to-end path) ----
+    def submit(self, slot: int, batch: A.csq_batch_in, out: A.csq_batch_out):
+        check(lib().csq_submit(self._h, slot, C.byref(batch), C.byref(out)))
+
+    def wait(self, slot: int):
+        check(lib().csq_wait(self._h, slot))
+
+    def slot_times(self, slot: int):
+        t, k = C.c_float(), C.c_float()
+        check(lib().csq_slot_times(self._h, slot, C.byref(t), C.byref(k)))
+        return t.value, k.value
+
+    def run_batch(self, batch: A.csq_batch_in, capacity: int | None = None, slot: int = 0):
+        """submit + wait with freshly allocated numpy output buffers. -> text[d][m] bytes, records[d][m]"""
+        if capacity is None:
+            capacity = 64
+            for m in range(batch.n_mates):
+                capacity = max(capacity, int(batch.mate[m].name_bytes) + 2 * int(batch.mate[m].seq_bytes) + 80 * int(batch.n_reads) + 64)
+        out = A.csq_batch_out()
+        bufs = [[np.empty(capacity, dtype=np.uint8) for _ in range(2)] for _ in range(A.CSQ_N_DEST)]
+        for d in range(A.CSQ_N_DEST):
+            for m in range(2):
+                out.text[d][m].data = bufs[d][m].ctypes.data
+                out.text[d][m].capacity = capacity
+        self.submit(slot, batch, out)
+        self.wait(slot)
+        text = [[bufs[d][m][: out.text[d][m].bytes].tobytes() for m in range(2)] for d in range(A.CSQ_N_DEST)]
+        records = [[int(out.text[d][m].records) for m in range(2)] for d in range(A.CSQ_N_DEST)]
+        return text, records
+
+    # ---- resident mode (measurement) ----
+    def upload(self, slot: int, batch: A.csq_batch_in):
+        check(lib().csq_upload(self._h, slot, C.byref(batch)))
+
+    def run_resident(self, slot: int, iters: int) -> float:
+        ms = C.c_float()
+        check(lib().csq_run_resident(self._h, slot, iters, C.byref(ms)))
+        return ms.value
+
+    def kernel_times(self, slot: int):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().csq_kernel_times(self._h, slot, names, ms, 64)
+        return [(names[i].decode(), ms[i]) for i in range(n)]
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        check(lib().csq_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def results(self, slot: int, mate: int, n: int):
+        out = np.zeros(max(n, 1), dtype=RESULT_DTYPE)
+        check(lib().csq_fetch_results(self._h, slot, mate, out.ctypes.data, n))
+        return out[:n]
+
+    def matches(self, slot: int, mate: int, op_index: int, n: int):
+        out = np.zeros(max(n, 1), dtype=MATCH_DTYPE)
+        check(lib().csq_fetch_matches(self._h, slot, mate, op_index, out.ctypes.data, n))
+        return out[:n]
+
+    def fetch_text(self, slot: int, capacity: int):
+        out = A.csq_batch_out()
+        bufs = [[np.empty(capacity, dtype=np.uint8) for _ in range(2)] for _ in range(A.CSQ_N_DEST)]
+        for d in range(A.CSQ_N_DEST):
+            for m in range(2):
+                out.text[d][m].data = bufs[d][m].ctypes.data
+                out.text[d][m].capacity = capacity
+        check(lib().csq_fetch_text(self._h, slot, C.byref(out)))
+        return [[bufs[d][m][: out.text[d][m].bytes].tobytes() for m in range(2)] for d in range(A.CSQ_N_DEST)]
+
+    def stats(self) -> A.csq_counters:
+        c = A.csq_counters()
+        check(lib().csq_stats(self._h, C.byref(c)))
+        return c
+
+
+def locate_batch(op, mate_in: A.csq_mate_in, n_reads: int, device: int = 0, flags: int = 0):
+    """Aligner.locate for a batch of reads on the GPU (``csq_locate_batch``)."""
+    cop = op.to_c() if hasattr(op, "to_c") else op
+    out = np.zeros(max(n_reads, 1), dtype=MATCH_DTYPE)
+    check(lib().csq_locate_batch(device, C.byref(cop), C.byref(mate_in), n_reads, flags, out.ctypes.data))
+    return out[:n_reads]
+
+
+def int_peak(device: int = 0):
+    a, b = C.c_double(), C.c_double()
+    check(lib().csq_int_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def run_files(program, inputs, outputs, gpus: int = 1, threads: int = 1, batch_reads: int = 0, flags: int = 0,
+              gzip_level: int = 0):
+    """Whole-file run (``csq_run_files``). outputs = {"trimmed": [p1, p2], "short": [...], "untrimmed": [...]}."""
+    L = lib()
+    if not hasattr(L, "csq_run_files"):
+        raise NativeError(A.ERR_INVALID, "library was built without the file pipeline")
+    ops1, n1 = program.c_ops(0)
+    ops2, n2 = program.c_ops(1)
+    flt = program.filters.to_c()
+    f = A.csq_files()
+    for i, p in enumerate(inputs):
+        f.in_[i] = os.fsencode(p)
+    for d, key in enumerate(("trimmed", "short", "untrimmed")):
+        paths = outputs.get(key) or []
+        for m, p in enumerate(paths):
+            if p is not None:
+                f.out[d][m] = os.fsencode(p)
+    f.batch_reads = batch_reads
+    f.gzip_level = gzip_level
+    f.n_threads = threads
+    f.n_devices = gpus
+    f.swap_sink = int(program.swap_sink)
+    counters, timing = A.csq_counters(), A.csq_timing()
+    check(L.csq_run_files(ops1, n1, ops2, n2 if program.paired else 0, C.byref(flt), flags, C.byref(f), C.byref(counters), C.byref(timing)))
+    return counters, timing

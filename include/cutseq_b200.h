@@ -52,7 +52,7 @@ typedef enum csq_status {
 
 /* Limits of this build. */
 #define CSQ_MAX_ADAPTER 128      /* adapter length m                             */
-#define CSQ_MAX_READ_LEN 1792    /* bases per read                               */
+#define CSQ_MAX_READ_LEN 895     /* bases per read (10-bit origin field of the DP word) */
 #define CSQ_MAX_OPS 32           /* ops per mate program                         */
 #define CSQ_MAX_SUFFIX 8         /* bytes of a STRIP_SUFFIX text                 */
 

@@ -1,0 +1,219 @@
+"""Parity tests proper: the CUDA chain (through the C ABI, ctypes) against the CPU oracle and the
+committed golden vectors. Bit-exact: every comparison is ==."""
+
+import random
+
+import numpy as np
+import pytest
+
+from cutseq_b200 import _abi as A
+from cutseq_b200 import native
+from cutseq_b200.program import Filters, Op, Program
+from oracle import oracle
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [A.AD_BACK, A.AD_BACK_ANYWHERE, A.AD_RIGHTMOST_FRONT, A.AD_PREFIX, A.AD_SUFFIX, A.AD_NI_FRONT, A.AD_NI_BACK, A.AD_FRONT]
+
+
+def random_reads(rng, adapter, n_reads, max_len=160, alphabet="ACGT"):
+    reads = []
+    m = len(adapter)
+    for i in range(n_reads):
+        n = rng.choice([0, 1, 2, 3, 7, 20, 36, 50, 75, 100, 150, max_len])
+        q = [rng.choice(alphabet + "N") if rng.random() < 0.02 else rng.choice(alphabet) for _ in range(n)]
+        r = rng.random()
+        if n and r < 0.75:  # plant a (partial, mutated) adapter copy, sometimes two
+            for _ in range(1 + (rng.random() < 0.15)):
+                cut = rng.randint(1, m)
+                piece = list(adapter[:cut] if rng.random() < 0.5 else adapter[m - cut:])
+                for _ in range(rng.choice([0, 0, 1, 1, 2, 3, 5])):
+                    if not piece:
+                        break
+                    pos = rng.randrange(len(piece))
+                    t = rng.random()
+                    if t < 0.5:
+                        piece[pos] = rng.choice(alphabet)
+                    elif t < 0.75:
+                        del piece[pos]
+                    else:
+                        piece.insert(pos, rng.choice(alphabet))
+                where = rng.random()
+                pos = 0 if where < 0.25 else (max(0, n - len(piece)) if where < 0.6 else rng.randint(0, max(0, n - 1)))
+                q[pos : pos + len(piece)] = piece
+            q = q[:max_len]
+        s = "".join(q)
+        if rng.random() < 0.05:
+            s = s.lower()
+        reads.append((f"r{i}", s, "I" * len(s)))
+    return reads
+
+
+def check_locate(op, reads):
+    batch, keep = oracle.make_batch(reads)
+    got = native.locate_batch(op, batch.mate[0], len(reads))
+    for i, (_, s, _) in enumerate(reads):
+        want = oracle.adapter_match(op, s)
+        g = got[i]
+        have = None if not g["found"] else tuple(int(g[k]) for k in ("ref_start", "ref_stop", "query_start", "query_stop", "score", "errors"))
+        assert have == want, (op.adapter, op.adapter_kind, op.max_error_rate, op.min_overlap, s, have, want)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_locate_matches_oracle(kind):
+    rng = random.Random(1000 + kind)
+    for m, rate, mo in [(20, 0.2, 3), (20, 0.2, 10), (19, 0.2, 3), (6, 0.2, 3), (1, 0.2, 1), (3, 0.34, 1), (13, 0.1, 5),
+                        (32, 0.2, 3), (33, 0.15, 3), (34, 0.3, 4), (40, 0.2, 3), (57, 0.12, 3), (20, 0.0, 3), (8, 0.5, 2)]:
+        adapter = "".join(rng.choice("ACGT") for _ in range(m))
+        op = Op(A.OP_ALIGN, adapter_kind=kind, adapter=adapter, min_overlap=mo, max_error_rate=rate)
+        check_locate(op, random_reads(rng, adapter, 700))
+
+
+@pytest.mark.parametrize("kind", [A.AD_NI_FRONT, A.AD_NI_BACK, A.AD_BACK, A.AD_RIGHTMOST_FRONT])
+def test_locate_homopolymer_and_low_complexity(kind):
+    rng = random.Random(77 + kind)
+    for adapter, rate in [("A" * 100, 0.15), ("T" * 100, 0.15), ("AC" * 50, 0.15), ("A" * 30, 0.2), ("G" * 100, 0.1)]:
+        op = Op(A.OP_ALIGN, adapter_kind=kind, adapter=adapter, min_overlap=3, max_error_rate=rate)
+        reads = []
+        for i in range(500):
+            n = rng.randint(0, 150)
+            body = "".join(rng.choice("ACGT") for _ in range(n))
+            run = adapter[0] * rng.randint(0, 60)
+            s = (body + run) if rng.random() < 0.5 else (run + body)
+            s = "".join(c if rng.random() > 0.04 else rng.choice("ACGTN") for c in s)[:160]
+            reads.append((f"h{i}", s, "I" * len(s)))
+        check_locate(op, reads)
+
+
+def test_locate_two_letter_alphabet_ties():
+    # low-complexity sequence space maximises cost ties, i.e. exercises the tie-breaking rules
+    rng = random.Random(5)
+    for kind in KINDS:
+        for m in (5, 12, 20):
+            adapter = "".join(rng.choice("AC") for _ in range(m))
+            op = Op(A.OP_ALIGN, adapter_kind=kind, adapter=adapter, min_overlap=2, max_error_rate=0.25)
+            check_locate(op, random_reads(rng, adapter, 400, max_len=60, alphabet="AC"))
+
+
+def run_gpu(prog, mates):
+    batch, keep = oracle.make_batch(*mates)
+    with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES) as plan:
+        text, records = plan.run_batch(batch)
+        n = batch.n_reads
+        results = [plan.results(0, m, n) for m in range(batch.n_mates)]
+        matches = []
+        for m in range(batch.n_mates):
+            ops = prog.ops_r1 if m == 0 else prog.ops_r2
+            matches.append({t: plan.matches(0, m, t, n) for t, op in enumerate(ops) if op.kind == A.OP_ALIGN})
+        stats = plan.stats()
+    return text, records, results, matches, stats, batch, keep
+
+
+COUNTER_FIELDS = ("n", "written", "too_short", "untrimmed")
+
+
+def compare_with_oracle(prog, mates):
+    text, records, results, matches, stats, batch, keep = run_gpu(prog, mates)
+    want = oracle.run_batch(prog, batch, n_threads=4)
+    n_mates = batch.n_mates
+    for m in range(n_mates):
+        for t, got in matches[m].items():
+            w = want["matches"][m][t]
+            for f in ("found", "ref_start", "ref_stop", "query_start", "query_stop", "score", "errors"):
+                bad = np.nonzero(got[f] != w[f])[0]
+                assert bad.size == 0, (m, t, f, int(bad[0]), got[bad[0]], w[bad[0]], mates[m][int(bad[0])])
+        for f in ("start", "stop", "dest", "matched"):
+            if prog.ops_r1[-1].kind == A.OP_REVCOMP and f in ("start", "stop"):
+                continue
+            bad = np.nonzero(results[m][f] != want["results"][m][f])[0]
+            assert bad.size == 0, (m, f, int(bad[0]), results[m][bad[0]], want["results"][m][bad[0]])
+    for d in range(A.CSQ_N_DEST):
+        for m in range(n_mates):
+            assert text[d][m] == want["text"][d][m], (d, m)
+            assert records[d][m] == want["records"][d][m]
+    for f in COUNTER_FIELDS:
+        assert getattr(stats, f) == getattr(want["counters"], f), f
+    for m in range(n_mates):
+        assert stats.total_bp[m] == want["counters"].total_bp[m]
+        assert stats.written_bp[m] == want["counters"].written_bp[m]
+        assert stats.quality_trimmed_bp[m] == want["counters"].quality_trimmed_bp[m]
+        assert list(stats.with_adapters[m]) == list(want["counters"].with_adapters[m])
+    return text
+
+
+@pytest.mark.parametrize("case", helpers.golden_cases(), ids=lambda c: c["case"])
+def test_golden_vectors(case):
+    prog = helpers.program_for(case["argv"], case["n_mates"])
+    mates = helpers.golden_inputs(case)
+    text = compare_with_oracle(prog, mates)
+    for (d, m), data in helpers.expected_by_dest(case, prog).items():
+        assert text[d][m] == data, (case["case"], helpers.DEST_KEYS[d], m)
+
+
+def test_empty_and_tiny_batches():
+    prog = helpers.program_for(["-A", "TAKARAV3", "--trim-polyA"], 2)
+    compare_with_oracle(prog, [[], []])
+    compare_with_oracle(prog, [[("a 1", "", "")], [("a 2", "", "")]])
+    compare_with_oracle(prog, [[("a", "ACGT", "IIII")], [("a", "TTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "I" * 29)]])
+
+
+def test_pairing_error_is_reported():
+    prog = helpers.program_for(["-A", "TAKARAV3"], 2)
+    batch, keep = oracle.make_batch([("x 1", "ACGT" * 10, "I" * 40)], [("y 2", "ACGT" * 10, "I" * 40)])
+    with native.Plan(prog) as plan:
+        with pytest.raises(native.NativeError) as e:
+            plan.run_batch(batch)
+        assert e.value.code == A.ERR_PAIRING
+    assert oracle.run_batch(prog, batch)["status"] == A.ERR_PAIRING
+
+
+def test_read_length_limit_is_an_error():
+    prog = helpers.program_for(["-A", "TAKARAV3"], 1)
+    batch, keep = oracle.make_batch([("x", "A" * 1000, "I" * 1000)])
+    with native.Plan(prog) as plan:
+        with pytest.raises(native.NativeError) as e:
+            plan.run_batch(batch)
+        assert e.value.code == A.ERR_LIMIT
+
+
+def test_odd_headers_and_names():
+    prog = helpers.program_for(["-A", "TAKARAV3"], 1)
+    seq, q = "ACGTTGCA" * 10, "I" * 80
+    names = ["plain", "with comment here", " leading space", "trailing ", "tab\tsep", "x/1", "x.1", "x/1.1", "x.1/1", "a  b  c", "", " ", "id /1"]
+    compare_with_oracle(prog, [[(nm, seq, q) for nm in names]])
+
+
+def test_random_programs_against_oracle():
+    rng = random.Random(2024)
+    for it in range(12):
+        def part(n):
+            return "".join(rng.choice("ACGT") for _ in range(n))
+
+        scheme = part(rng.choice([12, 19, 20, 25]))
+        if rng.random() < 0.5:
+            scheme += "(" + part(rng.choice([4, 6, 8])) + ")"
+        scheme += "N" * rng.choice([0, 0, 5, 8]) + "X" * rng.choice([0, 1, 3])
+        scheme += rng.choice("<>-")
+        scheme += "X" * rng.choice([0, 2, 6]) + "N" * rng.choice([0, 0, 6, 10])
+        if rng.random() < 0.5:
+            scheme += "(" + part(rng.choice([4, 6, 8])) + ")"
+        scheme += part(rng.choice([12, 19, 20, 25]))
+        argv = ["-a", scheme]
+        for flag, p in (("--trim-polyA", 0.5), ("--trim-polyA-wo-direction", 0.3), ("--no-conditional-cutter", 0.3),
+                        ("--force-anywhere", 0.3), ("--ensure-inline-barcode", 0.5), ("--auto-rc", 0.3)):
+            if rng.random() < p:
+                argv.append(flag)
+        argv += ["-q", str(rng.choice([0, 10, 20, 30])), "-m", str(rng.choice([0, 15, 20, 40]))]
+        n_mates = rng.choice([1, 2])
+        prog = helpers.program_for(argv, n_mates)
+        from cutseq_b200.common import BarcodeConfig
+
+        bc = BarcodeConfig(scheme.upper())
+        import scripts.make_golden as mg
+
+        r1, r2 = mg.synth_pairs(rng.randint(0, 1 << 30), 300, read_len=rng.choice([50, 100, 150]), p5=bc.p5.fw, p7=bc.p7.fw,
+                                inline5=bc.inline5.fw, inline3=bc.inline3.fw, umi5=bc.umi5.len, umi3=bc.umi3.len,
+                                mask5=bc.mask5.len, mask3=bc.mask3.len, strand=bc.strand or "+", readthrough=0.5,
+                                polya=0.2, bc_error=0.03, wrong_bc=0.1, suffix_style=rng.choice([None, "slash", "dot", "bare"]))
+        compare_with_oracle(prog, [r1, r2] if n_mates == 2 else [r1])
