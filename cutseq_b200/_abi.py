@@ -11,7 +11,7 @@ CSQ_MAX_READ_LEN = 895
 CSQ_MAX_OPS = 32
 CSQ_MAX_SUFFIX = 8
 CSQ_N_DEST = 3
-CSQ_N_SLOTS = 2
+CSQ_N_SLOTS = 8
 
 # csq_status
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
@@ -123,6 +123,7 @@ class csq_counters(C.Structure):
         ("untrimmed", C.c_uint64),
         ("quality_trimmed_bp", C.c_uint64 * 2),
         ("with_adapters", (C.c_uint64 * CSQ_MAX_OPS) * 2),
+        ("dp_cells", (C.c_uint64 * CSQ_MAX_OPS) * 2),
     ]
 
 

@@ -104,7 +104,7 @@ struct EmitParams {
 // word indices inside csq_counters viewed as uint64[]
 enum {
     CNT_N = 0, CNT_TOTAL_BP = 1, CNT_WRITTEN = 3, CNT_WRITTEN_BP = 4, CNT_TOO_SHORT = 6, CNT_UNTRIMMED = 7,
-    CNT_QTRIM_BP = 8, CNT_WITH_ADAPTERS = 10
+    CNT_QTRIM_BP = 8, CNT_WITH_ADAPTERS = 10, CNT_DP_CELLS = 10 + 2 * CSQ_MAX_OPS
 };
 
 // launchers implemented in kernels.cu (all asynchronous on `stream`)

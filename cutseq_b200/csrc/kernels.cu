@@ -304,6 +304,21 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
 
     const uint8_t* s = P.md.seq + P.md.seq_off[idx];
     csq_match r;
+    {  // nominal DP cells of this alignment, m * (max_n - min_n)  (statistics / GCUPS numerator)
+        const int n = (int)st.b - (int)st.a;
+        int max_n = n, min_n = 0;
+        if (!(P.flags & 2)) max_n = min(n, P.m + P.k);
+        if (!(P.flags & 8)) min_n = max(0, n - P.m - P.k);
+        const unsigned int mine = (unsigned int)(P.m * (max_n - min_n));
+        unsigned long long* dst = P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS);
+        if (__activemask() == 0xffffffffu) {
+            unsigned int cells = mine;
+            for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(dst, (unsigned long long)cells);
+        } else {
+            atomicAdd(dst, (unsigned long long)mine);
+        }
+    }
     if constexpr (M > 0)
         dp_exact<M, HOMO>(s, st.a, st.b, P, lut, r);
     else

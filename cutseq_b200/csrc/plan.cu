@@ -354,7 +354,7 @@ PairParams pair_params(csq_plan* plan, Slot& s) {
 }
 
 // align ... scan, then the 12 totals + error flag to pinned host memory
-int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt) {
+int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     const uint32_t n = s.n;
     const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
     if (kt) kt->mark("begin");
@@ -370,7 +370,7 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt) {
             ap.matches = (plan->flags & CSQ_PLAN_KEEP_MATCHES)
                              ? (csq_match*)s.matches[m].p + (size_t)mp.align_slot[sg.op_index] * n
                              : nullptr;
-            CUDA_TRY(csq_launch_align(ap, n, s.stream));
+            CUDA_TRY(csq_launch_align(ap, n, st));
             plan->launches += n ? 1 : 0;
             if (kt) kt->mark(sg.name);
         }
@@ -378,20 +378,20 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt) {
         fp.md = mate_dev(s, m);
         fp.n = n;
         fp.counters = plan->counters;
-        CUDA_TRY(csq_launch_finish(fp, s.stream));
+        CUDA_TRY(csq_launch_finish(fp, st));
         plan->launches += n ? 1 : 0;
         if (kt) kt->mark(m == 0 ? "k_finish.r1" : "k_finish.r2");
     }
     PairParams pp = pair_params(plan, s);
-    CUDA_TRY(csq_launch_pair(pp, s.stream));
+    CUDA_TRY(csq_launch_pair(pp, st));
     plan->launches += n ? 1 : 0;
     if (kt) kt->mark("k_pair");
     CUDA_TRY(csq_launch_scan(nblk, (const uint32_t*)s.block_tot.p, (const uint32_t*)s.block_cnt.p,
-                             (unsigned long long*)s.block_off.p, (unsigned long long*)s.totals.p, s.stream));
+                             (unsigned long long*)s.block_off.p, (unsigned long long*)s.totals.p, st));
     plan->launches += 1;
     if (kt) kt->mark("k_scan");
-    CUDA_TRY(cudaMemcpyAsync(s.totals_host, s.totals.p, 12 * 8, cudaMemcpyDeviceToHost, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 12, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host, s.totals.p, 12 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 12, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     s.front_done = true;
     return 0;
 }
@@ -405,14 +405,14 @@ int size_outputs(Slot& s) {
     return 0;
 }
 
-int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt) {
+int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     EmitParams ep;
     memset(&ep, 0, sizeof(ep));
     ep.pp = pair_params(plan, s);
     ep.block_off = (const unsigned long long*)s.block_off.p;
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < 2; m++) ep.out[d][m] = (uint8_t*)s.out[d][m].p;
-    CUDA_TRY(csq_launch_emit(ep, s.stream));
+    CUDA_TRY(csq_launch_emit(ep, st));
     plan->launches += s.n ? 1 : 0;
     if (kt) kt->mark("k_emit");
     return 0;
@@ -533,7 +533,7 @@ int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* 
     CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
     if ((rc = upload(plan, s, in))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
-    if ((rc = enqueue_front(plan, s, nullptr))) return rc;
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
     s.pending = out;
     return 0;
@@ -560,7 +560,7 @@ int csq_wait(csq_plan* plan, int slot) {
         }
     if ((rc = size_outputs(s))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[3], s.stream));
-    if ((rc = enqueue_emit(plan, s, nullptr))) return rc;
+    if ((rc = enqueue_emit(plan, s, nullptr, s.stream))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[4], s.stream));
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < s.n_mates; m++) {
@@ -603,11 +603,11 @@ int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
     Slot& s = plan->slots[slot];
     int rc;
     // sizing pass (not timed): totals are needed on the host before the emit buffers exist
-    if ((rc = enqueue_front(plan, s, nullptr))) return rc;
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     if ((rc = check_device_error(s))) return rc;
     if ((rc = size_outputs(s))) return rc;
-    if ((rc = enqueue_emit(plan, s, nullptr))) return rc;
+    if ((rc = enqueue_emit(plan, s, nullptr, s.stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     if (iters == 1) {  // the sizing pass already did the work once
         if (ms_per_iter) *ms_per_iter = 0.f;
@@ -618,8 +618,8 @@ int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
     CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
     for (int it = 1; it < iters; it++) {
         kt.on = (it == iters - 1);
-        if ((rc = enqueue_front(plan, s, &kt))) return rc;
-        if ((rc = enqueue_emit(plan, s, &kt))) return rc;
+        if ((rc = enqueue_front(plan, s, &kt, s.stream))) return rc;
+        if ((rc = enqueue_emit(plan, s, &kt, s.stream))) return rc;
     }
     CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
@@ -631,6 +631,48 @@ int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
         float t = 0;
         cudaEventElapsedTime(&t, kt.evs[i - 1], kt.evs[i]);
         s.ktimes.push_back({kt.names[i], t});
+    }
+    for (cudaEvent_t e : kt.evs) cudaEventDestroy(e);
+    return 0;
+}
+
+int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, float* total_ms) {
+    if (!plan || !slots || n_slots < 1 || steps < 1) return fail(CSQ_ERR_INVALID, "bad argument");
+    for (int i = 0; i < n_slots; i++)
+        if (slots[i] < 0 || slots[i] >= CSQ_N_SLOTS) return fail(CSQ_ERR_INVALID, "bad slot");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s0 = plan->slots[slots[0]];
+    cudaStream_t st = s0.stream;
+    int rc;
+    for (int i = 0; i < n_slots; i++) {  // untimed sizing pass: emit buffers must exist
+        Slot& s = plan->slots[slots[i]];
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        if ((rc = enqueue_front(plan, s, nullptr, st))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = check_device_error(s))) return rc;
+        if ((rc = size_outputs(s))) return rc;
+        if ((rc = enqueue_emit(plan, s, nullptr, st))) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    KernelTimer kt;
+    kt.stream = st;
+    CUDA_TRY(cudaEventRecord(s0.ev[0], st));
+    for (int it = 0; it < steps; it++) {
+        Slot& s = plan->slots[slots[it % n_slots]];
+        kt.on = (it == steps - 1);
+        if ((rc = enqueue_front(plan, s, &kt, st))) return rc;
+        if ((rc = enqueue_emit(plan, s, &kt, st))) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(s0.ev[1], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s0.ev[0], s0.ev[1]));
+    if (total_ms) *total_ms = ms;
+    s0.ktimes.clear();
+    for (size_t i = 1; i < kt.evs.size(); i++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, kt.evs[i - 1], kt.evs[i]);
+        s0.ktimes.push_back({kt.names[i], t});
     }
     for (cudaEvent_t e : kt.evs) cudaEventDestroy(e);
     return 0;

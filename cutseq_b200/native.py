@@ -43,6 +43,7 @@ def lib():
     L.csq_slot_times.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.csq_upload.argtypes = [vp, i32, C.POINTER(A.csq_batch_in)]
     L.csq_run_resident.argtypes = [vp, i32, i32, C.POINTER(C.c_float)]
+    L.csq_run_steps.argtypes = [vp, C.POINTER(i32), i32, i32, C.POINTER(C.c_float)]
     L.csq_kernel_times.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]
     L.csq_launch_count.argtypes = [vp, u64p]
     L.csq_fetch_results.argtypes = [vp, i32, i32, vp, u32]
@@ -154,6 +155,13 @@ class Plan:
         check(lib().csq_run_resident(self._h, slot, iters, C.byref(ms)))
         return ms.value
 
+    def run_steps(self, slots, steps: int) -> float:
+        """`steps` resident steps round-robin over `slots`, back to back on one stream. -> total ms (CUDA events)"""
+        arr = (C.c_int * len(slots))(*slots)
+        ms = C.c_float()
+        check(lib().csq_run_steps(self._h, arr, len(slots), steps, C.byref(ms)))
+        return ms.value
+
     def kernel_times(self, slot: int):
         names = (C.c_char_p * 64)()
         ms = (C.c_float * 64)()
@@ -197,6 +205,23 @@ def locate_batch(op, mate_in: A.csq_mate_in, n_reads: int, device: int = 0, flag
     out = np.zeros(max(n_reads, 1), dtype=MATCH_DTYPE)
     check(lib().csq_locate_batch(device, C.byref(cop), C.byref(mate_in), n_reads, flags, out.ctypes.data))
     return out[:n_reads]
+
+
+def synth_batch(config: int, n_reads: int, first_index: int = 0, buffer: int = 0, seed: int | None = None,
+                read_len: int | None = None, paired: bool | None = None) -> A.csq_batch_in:
+    """BASELINE.json configs 2-5 as packed SoA batches in pinned host memory (``csq_synth_batch``)."""
+    defaults = {2: (20240419, 150, True), 3: (20240420, 150, True), 4: (20240421, 75, False), 5: (20240419, 150, True)}
+    dseed, dlen, dpaired = defaults[config]
+    cfg = A.csq_synth(dseed if seed is None else seed, dlen if read_len is None else read_len,
+                      int(dpaired if paired is None else paired), 2 if config == 5 else config)
+    b = A.csq_batch_in()
+    check_plain(lib().csq_synth_batch(C.byref(cfg), first_index, n_reads, buffer, C.byref(b)))
+    return b
+
+
+def check_plain(rc: int):
+    if rc != 0:
+        raise NativeError(rc, "synthetic generator failed")
 
 
 def int_peak(device: int = 0):

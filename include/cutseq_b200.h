@@ -193,6 +193,8 @@ typedef struct csq_counters {
     uint64_t untrimmed;          /* reads / pairs filtered by IsUntrimmedAny */
     uint64_t quality_trimmed_bp[2];
     uint64_t with_adapters[2][CSQ_MAX_OPS]; /* matches per ALIGN op, indexed by op position */
+    uint64_t dp_cells[2][CSQ_MAX_OPS];      /* nominal DP cells m*(max_n-min_n) per ALIGN op
+                                               (the GCUPS numerator)         */
 } csq_counters;
 
 typedef struct csq_plan csq_plan;
@@ -213,7 +215,7 @@ void csq_plan_destroy(csq_plan* plan);
 /* Asynchronous batch execution on slot 0..CSQ_N_SLOTS-1 (each slot = one stream +
  * device buffers): submit copies the batch to the device, runs the chain, emits FASTQ
  * text and copies it back into `out`; wait blocks until that is complete. */
-#define CSQ_N_SLOTS 2
+#define CSQ_N_SLOTS 8
 int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* out);
 int csq_wait(csq_plan* plan, int slot);
 /* Device time of the last completed submit on this slot, in ms, by CUDA events on the
@@ -224,7 +226,12 @@ int csq_slot_times(csq_plan* plan, int slot, float* total_ms, float* kernel_ms);
  * stays in HBM; ms_per_iter is measured with CUDA events on the slot's stream. */
 int csq_upload(csq_plan* plan, int slot, const csq_batch_in* in);
 int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter);
-/* Per-kernel device times (ms, averaged over the last csq_run_resident call). names
+/* The same over several uploaded slots: after an untimed sizing pass per slot, `steps` steps run
+ * back to back on one stream, step i on slots[i % n_slots]; total_ms is the CUDA-event time of
+ * the whole loop (so consecutive steps touch different data, each far larger than L2). */
+int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, float* total_ms);
+/* Per-kernel device times (ms, last step of the last csq_run_resident / csq_run_steps call; for
+ * csq_run_steps query the first slot of the list). names
  * points at static strings. Returns the number of kernels recorded (<= cap). */
 int csq_kernel_times(csq_plan* plan, int slot, const char** names, float* ms, int cap);
 int csq_launch_count(csq_plan* plan, uint64_t* launches);   /* kernels launched so far */

@@ -194,6 +194,8 @@ static int kind_is_front(int kind) {
 int orc_adapter_match(const csq_op* op, const char* seq, int n, orc_match* out) {
     int m = op->adapter_len;
     int min_overlap = imin(op->min_overlap, m);
+    /* SingleAdapter.__init__: max_errors >= 1 is an absolute count */
+    const double rate = op->max_error_rate >= 1.0 ? op->max_error_rate / m : op->max_error_rate;
     if (op->adapter_kind == CSQ_AD_PREFIX || op->adapter_kind == CSQ_AD_SUFFIX) min_overlap = m;
     if (op->adapter_kind == CSQ_AD_RIGHTMOST_FRONT) {
         char ref[CSQ_MAX_ADAPTER];
@@ -201,7 +203,7 @@ int orc_adapter_match(const csq_op* op, const char* seq, int n, orc_match* out) 
         for (int i = 0; i < m; i++) ref[i] = op->adapter[m - 1 - i];
         for (int j = 0; j < n; j++) q[j] = seq[n - 1 - j];
         orc_match r;
-        int found = orc_locate(ref, m, op->max_error_rate, 14, min_overlap, q, n, &r);
+        int found = orc_locate(ref, m, rate, 14, min_overlap, q, n, &r);
         free(q);
         memset(out, 0, sizeof(*out));
         if (!found) return 0;
@@ -214,7 +216,7 @@ int orc_adapter_match(const csq_op* op, const char* seq, int n, orc_match* out) 
         out->errors = r.errors;
         return 1;
     }
-    return orc_locate(op->adapter, m, op->max_error_rate, kind_flags(op->adapter_kind), min_overlap, seq, n, out);
+    return orc_locate(op->adapter, m, rate, kind_flags(op->adapter_kind), min_overlap, seq, n, out);
 }
 
 /* quality_trim_index (upstream qualtrim.pyx) */
@@ -242,6 +244,16 @@ void orc_quality_trim_index(const char* q, int n, int cutoff_front, int cutoff_b
     if (start >= stop) start = stop = 0;
     *start_out = start;
     *stop_out = stop;
+}
+
+/* Nominal DP cells of one alignment, m * (max_n - min_n): the GCUPS numerator of SURVEY.md 8(d). */
+static uint64_t nominal_cells(const csq_op* op, int n) {
+    int m = op->adapter_len, flags = kind_flags(op->adapter_kind);
+    double rate = op->max_error_rate >= 1.0 ? op->max_error_rate / m : op->max_error_rate;
+    int k = (int)(rate * m), max_n = n, min_n = 0;
+    if (!(flags & 2)) max_n = imin(n, m + k);
+    if (!(flags & 8)) min_n = imax(0, n - m - k);
+    return (uint64_t)m * (uint64_t)(max_n - min_n);
 }
 
 /* ---- per-read working record (the SequenceRecord + ModificationInfo of one mate) ---- */
@@ -498,6 +510,8 @@ static void* chunk_worker(void* arg) {
             }
             orc_match mt;
             memset(&mt, 0, sizeof(mt));
+            if (ops1[t].kind == CSQ_OP_ALIGN) k->dp_cells[0][t] += nominal_cells(&ops1[t], r[0].len);
+            if (paired && ops2[t].kind == CSQ_OP_ALIGN) k->dp_cells[1][t] += nominal_cells(&ops2[t], r[1].len);
             apply_single(&ops1[t], &r[0], &mt, &k->quality_trimmed_bp[0]);
             if (ops1[t].kind == CSQ_OP_ALIGN) {
                 if (mt.found) k->with_adapters[0][t]++;

@@ -139,6 +139,7 @@ def compare_with_oracle(prog, mates):
         assert stats.written_bp[m] == want["counters"].written_bp[m]
         assert stats.quality_trimmed_bp[m] == want["counters"].quality_trimmed_bp[m]
         assert list(stats.with_adapters[m]) == list(want["counters"].with_adapters[m])
+        assert list(stats.dp_cells[m]) == list(want["counters"].dp_cells[m])
     return text
 
 
