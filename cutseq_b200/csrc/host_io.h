@@ -1,0 +1,68 @@
+// Host-side I/O helpers shared by fastq_io.cpp and pipeline.cpp (not part of the public ABI).
+#pragma once
+
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cutseq_b200.h"
+
+namespace csqio {
+
+int io_fail(int code, const char* fmt, ...);
+const char* io_error();
+
+struct PinnedBuf {  // growable host buffer, pinned when a CUDA context is available
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    ~PinnedBuf();
+    bool reserve(size_t bytes, size_t keep);
+    void release();
+};
+
+struct MateSoA {  // csq_mate_in backing store
+    PinnedBuf seq, qual, seq_off, seq_len, name, name_off;
+    uint32_t n = 0;
+    uint64_t seq_bytes = 0, name_bytes = 0, total_bases = 0;
+    void clear();
+    void view(csq_mate_in* mi) const;
+};
+
+struct ByteSource {
+    void* gz = nullptr;
+    std::string name;
+    ~ByteSource();
+    int open(const char* path);
+    long read(uint8_t* dst, size_t n);
+    void close();
+};
+
+struct MateParser {
+    ByteSource src;
+    std::vector<uint8_t> carry;
+    size_t carry_pos = 0;
+    bool eof = false;
+    uint64_t line_no = 0;
+    int open(const char* path);
+    int next(uint32_t max_reads, MateSoA& out);
+};
+
+int parse_records(const uint8_t* text, size_t n_bytes, bool at_eof, uint32_t max_reads, MateSoA& out, size_t* consumed,
+                  uint64_t* line_no, const char* fname);
+
+struct OutFile {
+    FILE* f = nullptr;
+    std::string path;
+    bool gzip = false, wrote_any = false;
+    int gz_level = 1;
+    int open(const char* p, int level);
+    int write_raw(const uint8_t* data, size_t n);
+    int close();
+};
+
+int gzip_member(const uint8_t* src, size_t n, int level, std::vector<uint8_t>& dst);
+
+}  // namespace csqio

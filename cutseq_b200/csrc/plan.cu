@@ -427,6 +427,8 @@ int check_device_error(Slot& s) {
 
 }  // namespace
 
+void csq_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
+
 extern "C" {
 
 int csq_abi_version(void) { return CSQ_ABI_VERSION; }
@@ -554,9 +556,17 @@ int csq_wait(csq_plan* plan, int slot) {
             csq_text_out& t = out->text[d][m];
             t.bytes = s.totals_host[d * 2 + m];
             t.records = (m < s.n_mates) ? s.totals_host[8 + d] : 0;
-            if (t.bytes > t.capacity || (t.bytes && !t.data))
+        }
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < 2; m++) {
+            csq_text_out& t = out->text[d][m];
+            if (t.bytes > t.capacity || (t.bytes && !t.data)) {
+                // every .bytes field already holds the needed size: the caller may enlarge its buffers
+                // and call csq_wait() again for this slot
+                s.pending = out;
                 return fail(CSQ_ERR_CAPACITY, "output buffer [%d][%d] holds %llu bytes, %llu needed", d, m,
                             (unsigned long long)t.capacity, (unsigned long long)t.bytes);
+            }
         }
     if ((rc = size_outputs(s))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[3], s.stream));

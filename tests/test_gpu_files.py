@@ -1,0 +1,74 @@
+"""End-to-end through the CLI surface (cutseq_b200.run.main -> csq_run_files): FASTQ(.gz) files in, files out,
+compared with the files the unmodified reference wrote (tests/golden, decompressed content)."""
+
+import gzip
+import os
+
+import pytest
+
+from cutseq_b200 import run
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def read_maybe_gz(path):
+    with open(path, "rb") as f:
+        head = f.read(2)
+    return gzip.open(path).read() if head == b"\x1f\x8b" else open(path, "rb").read()
+
+
+@pytest.mark.parametrize("case", helpers.golden_cases(), ids=lambda c: c["case"])
+def test_cli_reproduces_reference_files(case, tmp_path, capsys):
+    prefix = str(tmp_path / "out")
+    run.main(case["argv"] + ["-O", prefix, "--batch-reads", "257"] + helpers.golden_input_paths(case))
+    err = capsys.readouterr().err
+    for key, meta in case["outputs"].items():
+        got = read_maybe_gz(f"{prefix}_{key}.fastq.gz")
+        assert got == helpers.golden_expected(case, key), key
+    produced = sorted(f for f in os.listdir(tmp_path))
+    assert produced == sorted(f"out_{k}.fastq.gz" for k in case["outputs"])
+    if case["minimal_report"]:
+        assert case["minimal_report"][-1] in err.splitlines()
+
+
+def test_plain_outputs_and_explicit_names(tmp_path):
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_synth_polya"][0]
+    o1, o2, s1, s2 = (str(tmp_path / n) for n in ("t1.fq", "t2.fq", "s1.fq.gz", "s2.fq"))
+    run.main(case["argv"] + ["-o", o1, o2, "-s", s1, s2, "-t", "3"] + helpers.golden_input_paths(case))
+    assert open(o1, "rb").read() == helpers.golden_expected(case, "trimmed_R1")
+    assert open(o2, "rb").read() == helpers.golden_expected(case, "trimmed_R2")
+    assert gzip.open(s1).read() == helpers.golden_expected(case, "short_R1")
+    assert open(s2, "rb").read() == helpers.golden_expected(case, "short_R2")
+
+
+def test_batch_size_does_not_change_output(tmp_path):
+    case = [c for c in helpers.golden_cases() if c["case"] == "inline_custom_ensure"][0]
+    outs = []
+    for i, br in enumerate(("1", "64", "100000")):
+        prefix = str(tmp_path / f"o{i}")
+        run.main(case["argv"] + ["-O", prefix, "--batch-reads", br] + helpers.golden_input_paths(case))
+        outs.append({k: read_maybe_gz(f"{prefix}_{k}.fastq.gz") for k in case["outputs"]})
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0]["untrimmed_R1"] == helpers.golden_expected(case, "untrimmed_R1")
+
+
+def test_json_report(tmp_path):
+    import json
+
+    case = helpers.golden_cases()[0]
+    jf = str(tmp_path / "r.json")
+    run.main(case["argv"] + ["-O", str(tmp_path / "o"), "--json-file", jf] + helpers.golden_input_paths(case))
+    d = json.load(open(jf))
+    fields = case["minimal_report"][-1].split("\t")
+    assert d["read_counts"]["input"] == int(fields[1]) and d["read_counts"]["output"] == int(fields[6])
+    assert d["barcode"]["p5"] == "ACACGACGCTCTTCCGATCT" and d["input"]["paired"] is True
+
+
+def test_malformed_input_fails_loudly(tmp_path):
+    from cutseq_b200 import native
+
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"@r1\nACGT\n+\nII\n")
+    with pytest.raises(native.NativeError):
+        run.main(["-A", "SMALLRNA", "-O", str(tmp_path / "o"), str(bad)])

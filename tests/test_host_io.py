@@ -1,0 +1,167 @@
+"""Host FASTQ parser (csq_parse_fastq_mem / csq_reader_*) - runs without a GPU."""
+
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from cutseq_b200 import _abi as A
+from cutseq_b200 import native
+from tests import helpers
+
+
+def parse_mem(text: bytes, max_reads=1 << 20):
+    L = native.lib()
+    cap = len(text) * 2 + 1024
+    seq = np.zeros(cap, np.uint8)
+    qual = np.zeros(cap, np.uint8)
+    name = np.zeros(cap, np.uint8)
+    n_max = text.count(b"\n") // 4 + 2
+    seq_off = np.zeros(n_max, np.uint32)
+    seq_len = np.zeros(n_max, np.uint32)
+    name_off = np.zeros(n_max + 1, np.uint32)
+    n, sb, used = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    buf = np.frombuffer(text + b"\0", dtype=np.uint8)
+    rc = L.csq_parse_fastq_mem(buf.ctypes.data, len(text), max_reads, seq.ctypes.data, qual.ctypes.data, cap, seq_off.ctypes.data,
+                               seq_len.ctypes.data, name.ctypes.data, cap, name_off.ctypes.data, C.byref(n), C.byref(sb), C.byref(used))
+    if rc:
+        raise native.NativeError(rc, L.csq_last_error().decode())
+    recs = []
+    for i in range(n.value):
+        o, l = int(seq_off[i]), int(seq_len[i])
+        assert o % 16 == 0
+        recs.append((name[name_off[i]:name_off[i + 1]].tobytes().decode(), seq[o:o + l].tobytes().decode(), qual[o:o + l].tobytes().decode()))
+    return recs, used.value
+
+
+def test_parse_basic_and_edge_cases():
+    recs, used = parse_mem(b"@r1 c\nACGT\n+\nIIII\n@r2\n\n+\n\n@r3\nAC\n+r3\n#I")
+    assert recs == [("r1 c", "ACGT", "IIII"), ("r2", "", ""), ("r3", "AC", "#I")]
+    recs, _ = parse_mem(b"@r1\r\nACGT\r\n+\r\nIIII\r\n")
+    assert recs == [("r1", "ACGT", "IIII")]
+    recs, _ = parse_mem(b"")
+    assert recs == []
+    recs, _ = parse_mem(b"@a\nA\n+\nI\n\n\n")
+    assert recs == [("a", "A", "I")]
+    recs, used = parse_mem(b"@a\nA\n+\nI\n@b\nC\n+\nI\n", max_reads=1)
+    assert recs == [("a", "A", "I")] and used == 9
+
+
+@pytest.mark.parametrize("text,code", [
+    (b"r1\nACGT\n+\nIIII\n", A.ERR_FORMAT),
+    (b"@r1\nACGT\n-\nIIII\n", A.ERR_FORMAT),
+    (b"@r1\nACGT\n+\nIII\n", A.ERR_FORMAT),
+    (b"@r1\nACGT\n+\n", A.ERR_FORMAT),
+    (b"@r1\n" + b"A" * 900 + b"\n+\n" + b"I" * 900 + b"\n", A.ERR_LIMIT),
+])
+def test_parse_errors(text, code):
+    with pytest.raises(native.NativeError) as e:
+        parse_mem(text)
+    assert e.value.code == code
+
+
+def test_reader_matches_python_parse():
+    L = native.lib()
+    case = helpers.golden_cases()[0]
+    paths = helpers.golden_input_paths(case)
+    want = helpers.golden_inputs(case)
+    h = C.c_void_p()
+    native.check(L.csq_reader_open(os.fsencode(paths[0]), os.fsencode(paths[1]), C.byref(h)))
+    got = [[], []]
+    buf = 0
+    while True:
+        b = A.csq_batch_in()
+        native.check(L.csq_reader_next(h, buf, 333, C.byref(b)))
+        if b.n_reads == 0:
+            break
+        assert b.n_reads <= 333 and b.n_mates == 2
+        for m in range(2):
+            mi = b.mate[m]
+            n = b.n_reads
+            seq_off = np.ctypeslib.as_array(C.cast(mi.seq_off, C.POINTER(C.c_uint32)), (n,))
+            seq_len = np.ctypeslib.as_array(C.cast(mi.seq_len, C.POINTER(C.c_uint32)), (n,))
+            name_off = np.ctypeslib.as_array(C.cast(mi.name_off, C.POINTER(C.c_uint32)), (n + 1,))
+            for i in range(n):
+                got[m].append((C.string_at(mi.name + int(name_off[i]), int(name_off[i + 1] - name_off[i])).decode(),
+                               C.string_at(mi.seq + int(seq_off[i]), int(seq_len[i])).decode(),
+                               C.string_at(mi.qual + int(seq_off[i]), int(seq_len[i])).decode()))
+        buf ^= 1
+    L.csq_reader_close(h)
+    assert got[0] == want[0] and got[1] == want[1]
+
+
+def test_reader_rejects_unequal_pairs(tmp_path):
+    p1, p2 = tmp_path / "a.fq", tmp_path / "b.fq.gz"
+    p1.write_bytes(b"@a\nA\n+\nI\n@b\nA\n+\nI\n")
+    with gzip.open(p2, "wb") as f:
+        f.write(b"@a\nA\n+\nI\n")
+    L = native.lib()
+    h = C.c_void_p()
+    native.check(L.csq_reader_open(os.fsencode(str(p1)), os.fsencode(str(p2)), C.byref(h)))
+    b = A.csq_batch_in()
+    assert L.csq_reader_next(h, 0, 100, C.byref(b)) == A.ERR_FORMAT
+    L.csq_reader_close(h)
+
+
+def test_missing_file_is_an_io_error():
+    L = native.lib()
+    h = C.c_void_p()
+    assert L.csq_reader_open(b"/nonexistent/x.fq", None, C.byref(h)) == A.ERR_IO
+
+
+def test_synth_generator_is_counter_based():
+    from oracle import oracle  # noqa: F401  (only to make sure both sides read the same batch layout)
+
+    a = native.synth_batch(2, 1000, first_index=500, buffer=0)
+    seq_a = C.string_at(a.mate[0].seq, a.mate[0].seq_bytes)
+    name_a = C.string_at(a.mate[1].name, a.mate[1].name_bytes)
+    b = native.synth_batch(2, 1500, first_index=0, buffer=1)
+    seq_b = C.string_at(b.mate[0].seq, b.mate[0].seq_bytes)
+    assert seq_b[500 * 160:] == seq_a  # record i depends only on (seed, index)
+    assert name_a.count(b" 2:N:0:") == 1000
+    c = native.synth_batch(4, 100, buffer=2)
+    assert c.n_mates == 1 and c.mate[0].seq_bytes == 100 * 80
+
+
+def test_abi_exports_every_declared_symbol():
+    import re
+
+    hdr = open(os.path.join(helpers.ROOT, "include", "cutseq_b200.h")).read()
+    names = set(re.findall(r"\b(csq_[a-z_0-9]+)\s*\(", hdr))
+    names -= {"csq_plan", "csq_reader"}
+    L = native.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.csq_abi_version() == A.ABI_VERSION
+
+
+def test_struct_sizes_match_header(tmp_path):
+    """Compile a tiny C program against include/cutseq_b200.h and compare sizeof() with the ctypes mirror."""
+    import subprocess
+
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "cutseq_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(csq_op),sizeof(csq_filters),sizeof(csq_mate_in),sizeof(csq_batch_in),sizeof(csq_text_out),"
+                   "sizeof(csq_batch_out),sizeof(csq_match),sizeof(csq_counters),sizeof(csq_files),sizeof(csq_timing));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(helpers.ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(t) for t in (A.csq_op, A.csq_filters, A.csq_mate_in, A.csq_batch_in, A.csq_text_out, A.csq_batch_out,
+                                  A.csq_match, A.csq_counters, A.csq_files, A.csq_timing)]
+    assert got == want
+
+
+def test_no_gpu_means_loud_failure():
+    """Without a CUDA device the compute entry points must fail (no CPU fallback)."""
+    try:
+        n = native.device_count()
+    except native.NativeError:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is present")
+    prog = helpers.program_for(["-A", "TAKARAV3"], 2)
+    with pytest.raises(native.NativeError) as e:
+        native.Plan(prog)
+    assert e.value.code == A.ERR_NO_DEVICE
