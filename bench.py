@@ -156,44 +156,34 @@ def main():
     from cutseq_b200 import _abi as A
     from cutseq_b200 import build, native
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+    from cutseq_b200 import dist as csq_dist
 
-        dist = dist_mod
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank)
+    group = csq_dist.Group()  # NCCL process group when launched by torchrun with WORLD_SIZE > 1
+    rank, local_rank, world = group.rank, group.local_rank, group.world
+    dist = group.dist
+    torch.cuda.set_device(local_rank)
     build.build()
     native.lib()  # fails loudly when the CUDA library is missing
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        group.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = group.max
 
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
     plan = native.Plan(prog, local_rank, 0)
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
+    # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
+    # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
     batches = []
     for b in range(B):
-        batch = native.synth_batch(2, P, first_index=(rank * B + b) * P, buffer=b)
+        batch = native.synth_batch(2, P, first_index=(rank * B + b) * P, buffer=min(b, 2))
         plan.upload(b, batch)
-        batches.append(batch)
+        if b < 2:
+            batches.append(batch)
     slots = list(range(B))
 
     # ---- kernel throughput, inputs resident in HBM ----
@@ -210,6 +200,7 @@ def main():
     barrier()
     launches = plan.launch_count() - l0
     c1 = plan.stats()
+    job_counters = group.sum_counters(c1)  # the one reduction of trim statistics (NCCL all-reduce when N > 1)
     ktimes = plan.kernel_times(slots[0])
     ms = max_over_ranks(ms)
     value = world * args.steps * P / (ms * 1e-3)
@@ -247,7 +238,7 @@ def main():
             plan.submit(e2e_slots[0], batches[0], outs[0])
             for i in range(1, k + 1):
                 if i < k:
-                    plan.submit(e2e_slots[i % 2], batches[i % B], outs[i % 2])
+                    plan.submit(e2e_slots[i % 2], batches[i % len(batches)], outs[i % 2])
                 plan.wait(e2e_slots[(i - 1) % 2])
                 o = outs[(i - 1) % 2]
                 d2h += sum(o.text[d][m].bytes for d in range(A.CSQ_N_DEST) for m in range(2))
@@ -267,8 +258,7 @@ def main():
 
     if rank != 0:
         plan.close()
-        if dist is not None:
-            dist.destroy_process_group()
+        group.close()
         return 0
 
     # ---- roofline of the dominant kernel (per-kernel CUDA events of the last timed step) ----
@@ -330,11 +320,11 @@ def main():
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
         "roofline": roofline, "roofline_hbm": scan_roofline, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
         "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "clocks": clocks,
+        "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
     }
     print(json.dumps(line))
     plan.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    group.close()
     return 0
 
 

@@ -246,10 +246,13 @@ def main():
                 files[key] = {"sha256": hashlib.sha256(data).hexdigest(), "bytes": len(data)}
             manifest.append({"case": case, "input": inset, "n_mates": n_mates, "argv": argv, "outputs": files, "minimal_report": report})
             print(case, {k: v["bytes"] for k, v in files.items()}, report[-1:] if report else "")
-    # full bundled set: hashes only (inputs live in /root/reference, absent on the GPU box)
+    # BASELINE.json config 1 = the reference's bundled 10 000 pairs: the two input DATA files are copied
+    # byte for byte (the GPU box has no /root/reference); expected outputs are kept as hashes only
+    for mate in (1, 2):
+        shutil.copyfile(f"/root/reference/test/input_R{mate}.fq.gz", os.path.join(GOLD, f"in_bundled_full_R{mate}.fq.gz"))
     for case, argv in (("full_takarav3", ["-A", "TAKARAV3"]), ("full_takarav3_polya", ["-A", "TAKARAV3", "--trim-polyA"])):
         with tempfile.TemporaryDirectory() as tmp:
-            sys.argv = ["cutseq"] + argv + ["-O", os.path.join(tmp, "out"), "/root/reference/test/input_R1.fq.gz", "/root/reference/test/input_R2.fq.gz"]
+            sys.argv = ["cutseq"] + argv + ["-O", os.path.join(tmp, "out"), os.path.join(GOLD, "in_bundled_full_R1.fq.gz"), os.path.join(GOLD, "in_bundled_full_R2.fq.gz")]
             err = io.StringIO()
             with redirect_stderr(err):
                 ref_run.main()
@@ -258,7 +261,7 @@ def main():
                 data = gzip.open(os.path.join(tmp, fn)).read()
                 files[fn[len("out_"):].replace(".fastq.gz", "")] = {"sha256": hashlib.sha256(data).hexdigest(), "bytes": len(data)}
             report = [l for l in err.getvalue().splitlines() if l.startswith(("status", "OK", "WARN"))]
-            manifest.append({"case": case, "input": "reference_test_dir", "n_mates": 2, "argv": argv, "outputs": files, "minimal_report": report})
+            manifest.append({"case": case, "input": "bundled_full", "hash_only": True, "n_mates": 2, "argv": argv, "outputs": files, "minimal_report": report})
             print(case, report[-1:])
     with open(os.path.join(GOLD, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)

@@ -18,8 +18,9 @@ def manifest():
         return json.load(f)
 
 
-def golden_cases(with_full=False):
-    return [c for c in manifest() if with_full or c["input"] != "reference_test_dir"]
+def golden_cases(hash_only=False):
+    """Cases with expected files committed (default) or the hash-only cases over the full bundled input."""
+    return [c for c in manifest() if bool(c.get("hash_only")) == hash_only]
 
 
 def read_fastq_gz(path):
@@ -32,14 +33,10 @@ def read_fastq_gz(path):
 
 
 def golden_inputs(case):
-    if case["input"] == "reference_test_dir":
-        return [read_fastq_gz(os.path.join(REFERENCE, "test", f"input_R{m}.fq.gz")) for m in (1, 2)]
     return [read_fastq_gz(os.path.join(GOLD, f"in_{case['input']}_R{m}.fq.gz")) for m in range(1, case["n_mates"] + 1)]
 
 
 def golden_input_paths(case):
-    if case["input"] == "reference_test_dir":
-        return [os.path.join(REFERENCE, "test", f"input_R{m}.fq.gz") for m in (1, 2)]
     return [os.path.join(GOLD, f"in_{case['input']}_R{m}.fq.gz") for m in range(1, case["n_mates"] + 1)]
 
 

@@ -72,3 +72,17 @@ def test_malformed_input_fails_loudly(tmp_path):
     bad.write_bytes(b"@r1\nACGT\n+\nII\n")
     with pytest.raises(native.NativeError):
         run.main(["-A", "SMALLRNA", "-O", str(tmp_path / "o"), str(bad)])
+
+
+@pytest.mark.parametrize("case", helpers.golden_cases(hash_only=True), ids=lambda c: c["case"])
+def test_config1_full_bundled_input(case, tmp_path, capsys):
+    """BASELINE.json config 1: the reference's bundled 10 000 pairs through the CLI; outputs by sha256."""
+    import hashlib
+
+    prefix = str(tmp_path / "out")
+    run.main(case["argv"] + ["-O", prefix, "-t", "4"] + helpers.golden_input_paths(case))
+    err = capsys.readouterr().err
+    for key, meta in case["outputs"].items():
+        got = read_maybe_gz(f"{prefix}_{key}.fastq.gz")
+        assert len(got) == meta["bytes"] and hashlib.sha256(got).hexdigest() == meta["sha256"], key
+    assert case["minimal_report"][-1] in err.splitlines()

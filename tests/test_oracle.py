@@ -148,8 +148,7 @@ def test_oracle_reproduces_golden(case):
         assert minimal_report_text(out["counters"], prog).splitlines()[1] == case["minimal_report"][-1]
 
 
-@pytest.mark.skipif(not os.path.isdir(helpers.REFERENCE), reason="reference tree not present")
-@pytest.mark.parametrize("case", [c for c in helpers.manifest() if c["input"] == "reference_test_dir"], ids=lambda c: c["case"])
+@pytest.mark.parametrize("case", helpers.golden_cases(hash_only=True), ids=lambda c: c["case"])
 def test_oracle_full_bundled(case):
     import hashlib
 
