@@ -50,6 +50,7 @@ struct AlignParams {
     const uint32_t* list_count;  // with list: number of entries (device side)
     uint32_t n;            // reads in the batch
     int32_t first;         // 1: state is initialised here (first segment of the program)
+    int32_t count_cells;   // 1: add the nominal DP cells of this launch to the statistics
     int32_t n_pre;
     DevOp pre[CSQ_MAX_PRE];
     // the adapter
@@ -114,5 +115,6 @@ cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream);
 cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
                             unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream);
 cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream);
+cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t* list_count, cudaStream_t stream);
 bool csq_align_has_exact_kernel(int m);
 cudaError_t csq_launch_int_peak(int variant, int iters, unsigned int* sink, int blocks, int threads, cudaStream_t stream);

@@ -27,6 +27,7 @@
 #include <stdint.h>
 
 #include "csq_internal.h"
+#include "device_common.cuh"
 
 namespace {
 
@@ -226,66 +227,12 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
     best_to_match(best, m, n, P.reversed != 0, r);
 }
 
-// CUT / COND_CUT / RENAME(capture) on the interval state.
-__device__ __forceinline__ void apply_scalar(const DevOp& op, ReadState& st) {
-    const int len = (int)st.b - (int)st.a;
-    if (op.kind == CSQ_OP_RENAME) {
-        st.ren_cp = st.cp;
-        st.ren_cs = st.cs;
-        return;
-    }
-    if (op.kind == CSQ_OP_COND_CUT && !(st.matched & 0x80000000u) && len < op.fmin) return;  // run.py:154-155
-    if (op.kind == CSQ_OP_CUT || op.kind == CSQ_OP_COND_CUT) {
-        if (op.length > 0) {
-            const int c = min(op.length, len);
-            st.cp = ((uint32_t)st.a << 16) | (uint32_t)c;
-            st.a = (uint16_t)(st.a + c);
-        } else if (op.length < 0) {
-            const int c = min(-op.length, len);
-            st.cs = ((uint32_t)(st.b - c) << 16) | (uint32_t)c;
-            st.b = (uint16_t)(st.b - c);
-        }
-    }
-}
-
-__device__ __forceinline__ ReadState fresh_state(uint32_t len) {
-    ReadState st;
-    st.a = 0;
-    st.b = (uint16_t)len;
-    st.matched = 0;
-    st.cp = st.cs = st.ren_cp = st.ren_cs = 0;
-    st.id_start = st.id_end = 0;
-    st.qtrim = 0;
-    return st;
-}
-
-__device__ __forceinline__ ReadState load_state(const ReadState* p) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 x = q[0], y = q[1];
-    ReadState st;
-    st.a = (uint16_t)(x.x & 0xFFFFu);
-    st.b = (uint16_t)(x.x >> 16);
-    st.matched = x.y;
-    st.cp = x.z;
-    st.cs = x.w;
-    st.ren_cp = y.x;
-    st.ren_cs = y.y;
-    st.id_start = (uint16_t)(y.z & 0xFFFFu);
-    st.id_end = (uint16_t)(y.z >> 16);
-    st.qtrim = y.w;
-    return st;
-}
-
-__device__ __forceinline__ void store_state(ReadState* p, const ReadState& st) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4((uint32_t)st.a | ((uint32_t)st.b << 16), st.matched, st.cp, st.cs);
-    q[1] = make_uint4(st.ren_cp, st.ren_cs, (uint32_t)st.id_start | ((uint32_t)st.id_end << 16), st.qtrim);
-}
-
 template <int M, bool HOMO>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
     __shared__ uint32_t lut[(HOMO || M == 0) ? 1 : 256 * NW];
+    const uint32_t count = P.list ? *P.list_count : P.n;
+    if (blockIdx.x * blockDim.x >= count) return;  // whole CTA beyond the survivor list
     if constexpr (!HOMO && M > 0) {
         for (int c = threadIdx.x; c < 256; c += blockDim.x) {
             const int u = c & 0xDF;
@@ -296,7 +243,6 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
         __syncthreads();
     }
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = P.list ? *P.list_count : P.n;
     if (t >= count) return;
     const uint32_t idx = P.list ? P.list[t] : t;
     ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
@@ -304,7 +250,7 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
 
     const uint8_t* s = P.md.seq + P.md.seq_off[idx];
     csq_match r;
-    {  // nominal DP cells of this alignment, m * (max_n - min_n)  (statistics / GCUPS numerator)
+    if (P.count_cells) {  // nominal DP cells of this alignment, m * (max_n - min_n)  (statistics / GCUPS numerator)
         const int n = (int)st.b - (int)st.a;
         int max_n = n, min_n = 0;
         if (!(P.flags & 2)) max_n = min(n, P.m + P.k);
@@ -573,95 +519,138 @@ __device__ __forceinline__ uint8_t complement_base(uint8_t c) {
     return c;
 }
 
-// FASTQ text, "@name\nseq\n+\nqual\n" (dnaio), one warp per record, streams in input order.
+// FASTQ text, "@name\nseq\n+\nqual\n" (dnaio), streams in input order.
+// Phase 1 (thread per pair): load the two mate states once, CTA-wide exclusive scan of the record sizes
+// per output stream, one descriptor per record into shared memory.
+// Phase 2 (warp per record): byte gather with EMIT_UNROLL independent loads in flight per lane before
+// the stores (the kernel is latency bound, not issue bound: every source byte is read exactly once).
+struct EmitRec {
+    const uint8_t* nm;   // id bytes
+    const uint8_t* sq;   // original read, bases
+    const uint8_t* ql;   // original read, qualities
+    const uint8_t* pa;   // first UMI part (or null)
+    const uint8_t* pb;   // second UMI part
+    uint8_t* out;        // where the record goes
+    uint16_t id_len, lenA, lenB, a, b;
+    uint16_t umi_len;    // '_' + parts, 0 when the template is "{id}"
+};
+
+constexpr int EMIT_UNROLL = 4;
+
+__device__ __forceinline__ uint8_t emit_byte(const EmitRec& R, uint32_t p, uint32_t e_name, uint32_t e_umi, uint32_t e_seq,
+                                             uint32_t e_qual, bool revcomp) {
+    if (p < e_name) return p == 0 ? (uint8_t)'@' : R.nm[p - 1];
+    if (p < e_umi) {
+        uint32_t x = p - e_name;
+        if (x == 0) return (uint8_t)'_';
+        x -= 1;
+        return x < R.lenA ? R.pa[x] : R.pb[x - R.lenA];
+    }
+    if (p == e_umi) return (uint8_t)'\n';
+    if (p < e_seq) {
+        const uint32_t x = p - e_umi - 1;
+        return revcomp ? complement_base(R.sq[R.b - 1 - x]) : R.sq[R.a + x];
+    }
+    if (p < e_seq + 3) return (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
+    if (p < e_qual) {
+        const uint32_t x = p - e_seq - 3;
+        return revcomp ? R.ql[R.b - 1 - x] : R.ql[R.a + x];
+    }
+    return (uint8_t)'\n';
+}
+
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__ EmitParams E) {
     const PairParams& P = E.pp;
-    __shared__ unsigned int loc[2][CSQ_PAIR_BLOCK];  // exclusive offset of each record inside its stream, CTA-local
-    __shared__ unsigned int run[8];
+    __shared__ EmitRec recs[2][CSQ_PAIR_BLOCK];
+    __shared__ unsigned int wtot[8][CSQ_PAIR_BLOCK / 32];  // per-stream totals of every warp
     const uint32_t base = blockIdx.x * CSQ_PAIR_BLOCK;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool paired = P.n_mates == 2;
-    if (threadIdx.x < 8) run[threadIdx.x] = 0;
-    __syncthreads();
-    // CTA-local exclusive offsets: warp w owns pairs [32w, 32w+32); warps go in order.
-    for (int w = 0; w < CSQ_PAIR_BLOCK / 32; w++) {
-        if (wid == w) {
-            const uint32_t idx = base + threadIdx.x;
-            const bool live = idx < P.n;
-            const int dest = live ? P.dest[idx] : -1;
-            for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
-                const uint32_t len = live ? P.rec_len[mt * P.n + idx] : 0u;
-                uint32_t myoff = 0;
-                for (int d = 0; d < CSQ_N_DEST; d++) {
-                    const uint32_t v = dest == d ? len : 0u;
-                    uint32_t x = v;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                        if (lane >= o) x += y;
-                    }
-                    const uint32_t r0 = run[d * 2 + mt];
-                    if (dest == d) myoff = r0 + x - v;
-                    const uint32_t tot = __shfl_sync(0xffffffffu, x, 31);
-                    __syncwarp();
-                    if (lane == 0) run[d * 2 + mt] = r0 + tot;
-                    __syncwarp();
-                }
-                loc[mt][threadIdx.x] = myoff;
-            }
+    const int n_mates = paired ? 2 : 1;
+
+    // ---- phase 1 ----
+    const uint32_t idx = base + threadIdx.x;
+    const bool live = idx < P.n;
+    int dest = -1;
+    uint32_t len[2] = {0, 0}, incl[2] = {0, 0};
+    ReadState st[2];
+    RecordShape shape[2];
+    if (live) {
+        dest = P.dest[idx];
+        st[0] = load_state(P.md[0].state + idx);
+        st[1] = paired ? load_state(P.md[1].state + idx) : st[0];
+        for (int mt = 0; mt < n_mates; mt++) {
+            shape[mt] = record_shape(P, st[mt], st[0], st[1]);
+            len[mt] = shape[mt].total;
         }
-        __syncthreads();
     }
-    // copy: each warp writes its 32 pairs, all lanes cooperate on one record at a time
-    for (int q = 0; q < 32; q++) {
-        const uint32_t idx = base + wid * 32 + q;
-        if (idx >= P.n) break;
-        const int dest = P.dest[idx];
-        const ReadState s1 = load_state(P.md[0].state + idx);
-        const ReadState s2 = paired ? load_state(P.md[1].state + idx) : s1;
-        for (int mt = 0; mt < (paired ? 2 : 1); mt++) {
-            const ReadState& own = mt ? s2 : s1;
-            const RecordShape rs = record_shape(P, own, s1, s2);
+    // warp-level inclusive scans per (dest, mate) stream; only the thread's own dest contributes
+    for (int mt = 0; mt < n_mates; mt++)
+        for (int d = 0; d < CSQ_N_DEST; d++) {
+            const uint32_t v = dest == d ? len[mt] : 0u;
+            uint32_t x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (dest == d) incl[mt] = x;
+            if (lane == 31) wtot[d * 2 + mt][wid] = x;
+        }
+    __syncthreads();
+    if (live) {
+        for (int mt = 0; mt < n_mates; mt++) {
+            const int stream = dest * 2 + mt;
+            uint32_t off = incl[mt] - len[mt];
+            for (int w = 0; w < wid; w++) off += wtot[stream][w];
             const MateDev& md = P.md[mt];
-            const uint8_t* nm = md.name + md.name_off[idx] + own.id_start;
-            const uint8_t* sq = md.seq + md.seq_off[idx];
-            const uint8_t* ql = md.qual + md.seq_off[idx];
-            const uint8_t *pa = nullptr, *pb = nullptr;
-            if (P.rename_parts & CSQ_REN_OWN_PREFIX) pa = sq + (own.ren_cp >> 16);
-            if (P.rename_parts & CSQ_REN_OWN_SUFFIX) pb = sq + (own.ren_cs >> 16);
-            if (P.rename_parts & CSQ_REN_R1_PREFIX) pa = P.md[0].seq + P.md[0].seq_off[idx] + (s1.ren_cp >> 16);
-            if (P.rename_parts & CSQ_REN_R2_PREFIX) pb = P.md[1].seq + P.md[1].seq_off[idx] + (s2.ren_cp >> 16);
-            uint8_t* out = E.out[dest][mt] + E.block_off[(size_t)blockIdx.x * 8 + dest * 2 + mt] + loc[mt][wid * 32 + q];
-            const uint32_t e_name = 1 + rs.id_len;
-            const uint32_t e_umi = e_name + rs.umi_len;  // position of the '\n' after the header
-            const uint32_t e_seq = e_umi + 1 + rs.seq_len;
-            const uint32_t e_qual = e_seq + 3 + rs.seq_len;
-            const uint32_t a = own.a, b = own.b;
-            for (uint32_t p = lane; p < rs.total; p += 32) {
-                uint8_t ch;
-                if (p < e_name) {
-                    ch = p == 0 ? (uint8_t)'@' : nm[p - 1];
-                } else if (p < e_umi) {
-                    uint32_t x = p - e_name;
-                    if (x == 0)
-                        ch = '_';
-                    else {
-                        x -= 1;
-                        ch = x < rs.lenA ? pa[x] : pb[x - rs.lenA];
-                    }
-                } else if (p == e_umi) {
-                    ch = '\n';
-                } else if (p < e_seq) {
-                    const uint32_t x = p - e_umi - 1;
-                    ch = P.revcomp ? complement_base(sq[b - 1 - x]) : sq[a + x];
-                } else if (p < e_seq + 3) {
-                    ch = (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
-                } else if (p < e_qual) {
-                    const uint32_t x = p - e_seq - 3;
-                    ch = P.revcomp ? ql[b - 1 - x] : ql[a + x];
-                } else {
-                    ch = '\n';
+            const ReadState& own = st[mt];
+            EmitRec R;
+            R.nm = md.name + md.name_off[idx] + own.id_start;
+            R.sq = md.seq + md.seq_off[idx];
+            R.ql = md.qual + md.seq_off[idx];
+            R.pa = R.pb = nullptr;
+            if (P.rename_parts & CSQ_REN_OWN_PREFIX) R.pa = R.sq + (own.ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_OWN_SUFFIX) R.pb = R.sq + (own.ren_cs >> 16);
+            if (P.rename_parts & CSQ_REN_R1_PREFIX) R.pa = P.md[0].seq + P.md[0].seq_off[idx] + (st[0].ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_R2_PREFIX) R.pb = P.md[1].seq + P.md[1].seq_off[idx] + (st[1].ren_cp >> 16);
+            R.out = E.out[dest][mt] + E.block_off[(size_t)blockIdx.x * 8 + stream] + off;
+            R.id_len = (uint16_t)shape[mt].id_len;
+            R.lenA = (uint16_t)shape[mt].lenA;
+            R.lenB = (uint16_t)shape[mt].lenB;
+            R.umi_len = (uint16_t)shape[mt].umi_len;
+            R.a = own.a;
+            R.b = own.b;
+            recs[mt][threadIdx.x] = R;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2 ----
+    const bool revcomp = P.revcomp != 0;
+    for (int q = 0; q < 32; q++) {
+        const int slot = wid * 32 + q;
+        if (base + slot >= P.n) break;
+        for (int mt = 0; mt < n_mates; mt++) {
+            const EmitRec& R = recs[mt][slot];
+            const uint32_t seq_len = (uint32_t)R.b - (uint32_t)R.a;
+            const uint32_t e_name = 1 + R.id_len;
+            const uint32_t e_umi = e_name + R.umi_len;
+            const uint32_t e_seq = e_umi + 1 + seq_len;
+            const uint32_t e_qual = e_seq + 3 + seq_len;
+            const uint32_t total = e_qual + 1;
+            uint8_t* __restrict__ out = R.out;
+            for (uint32_t p0 = lane; p0 < total; p0 += 32 * EMIT_UNROLL) {
+                uint8_t ch[EMIT_UNROLL];
+#pragma unroll
+                for (int u = 0; u < EMIT_UNROLL; u++) {
+                    const uint32_t p = p0 + 32 * u;
+                    ch[u] = p < total ? emit_byte(R, p, e_name, e_umi, e_seq, e_qual, revcomp) : (uint8_t)0;
                 }
-                out[p] = ch;
+#pragma unroll
+                for (int u = 0; u < EMIT_UNROLL; u++) {
+                    const uint32_t p = p0 + 32 * u;
+                    if (p < total) out[p] = ch[u];
+                }
             }
         }
     }

@@ -58,6 +58,7 @@ struct Segment {  // one ALIGN op with the scalar ops in front of it
     AlignParams ap;
     int op_index;
     const char* name;
+    const char* pf_name;
 };
 
 struct MateProgram {
@@ -75,6 +76,7 @@ struct Slot {
     cudaEvent_t ev[6] = {};
     DevBuf seq[2], qual[2], seq_off[2], seq_len[2], name[2], name_off[2], state[2], matches[2];
     DevBuf dest, rec_len, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
+    DevBuf list, list_count;  // prefilter survivors (indices) and their number
     unsigned long long* totals_host = nullptr;  // pinned: 12 totals + error flag
     uint32_t n = 0;
     int n_mates = 0;
@@ -112,6 +114,20 @@ const char* kind_name(int k) {
         case CSQ_AD_FRONT: return "k_align(front)";
     }
     return "k_align";
+}
+
+const char* pf_kind_name(int k) {
+    switch (k) {
+        case CSQ_AD_BACK: return "k_prefilter(back)";
+        case CSQ_AD_BACK_ANYWHERE: return "k_prefilter(back,anywhere)";
+        case CSQ_AD_RIGHTMOST_FRONT: return "k_prefilter(rightmost_front)";
+        case CSQ_AD_PREFIX: return "k_prefilter(prefix)";
+        case CSQ_AD_SUFFIX: return "k_prefilter(suffix)";
+        case CSQ_AD_NI_FRONT: return "k_prefilter(noninternal_front)";
+        case CSQ_AD_NI_BACK: return "k_prefilter(noninternal_back)";
+        case CSQ_AD_FRONT: return "k_prefilter(front)";
+    }
+    return "k_prefilter";
 }
 
 // csq_op(ALIGN) -> aligner parameters (SingleAdapter.__init__ / _make_aligner of adapters.py)
@@ -209,6 +225,7 @@ int build_mate_program(const csq_op* ops, int n, int mate, MateProgram& mp) {
                 if (rc) return rc;
                 s.op_index = t;
                 s.name = kind_name(op.adapter_kind);
+                s.pf_name = pf_kind_name(op.adapter_kind);
                 s.ap.n_pre = (int)pending.size();
                 for (size_t q = 0; q < pending.size(); q++) s.ap.pre[q] = pending[q];
                 pending.clear();
@@ -313,6 +330,10 @@ int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
     if ((rc = s.block_cnt.ensure((size_t)nblk * 16 + 16))) return rc;
     if ((rc = s.block_off.ensure((size_t)nblk * 64 + 64))) return rc;
     if ((rc = s.totals.ensure(16 * 8))) return rc;
+    if (!(plan->flags & CSQ_PLAN_NO_PREFILTER)) {
+        if ((rc = s.list.ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.list_count.ensure(16))) return rc;
+    }
     return 0;
 }
 
@@ -366,10 +387,23 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
             ap.n = n;
             ap.list = nullptr;
             ap.list_count = nullptr;
+            ap.count_cells = 1;
             ap.counters = plan->counters;
             ap.matches = (plan->flags & CSQ_PLAN_KEEP_MATCHES)
                              ? (csq_match*)s.matches[m].p + (size_t)mp.align_slot[sg.op_index] * n
                              : nullptr;
+            if (!(plan->flags & CSQ_PLAN_NO_PREFILTER) && n) {
+                // reject-only bit-parallel filter; the exact DP then runs on the compacted survivors
+                CUDA_TRY(cudaMemsetAsync(s.list_count.p, 0, 4, st));
+                CUDA_TRY(csq_launch_prefilter(ap, (uint32_t*)s.list.p, (uint32_t*)s.list_count.p, st));
+                plan->launches += 1;
+                if (kt) kt->mark(sg.pf_name);
+                ap.list = (const uint32_t*)s.list.p;
+                ap.list_count = (const uint32_t*)s.list_count.p;
+                ap.first = 0;   // the prefilter initialised the state and ran the scalar ops
+                ap.n_pre = 0;
+                ap.count_cells = 0;
+            }
             CUDA_TRY(csq_launch_align(ap, n, st));
             plan->launches += n ? 1 : 0;
             if (kt) kt->mark(sg.name);
@@ -515,6 +549,7 @@ void csq_plan_destroy(csq_plan* plan) {
             s.name[m].release(); s.name_off[m].release(); s.state[m].release(); s.matches[m].release();
             for (int d = 0; d < CSQ_N_DEST; d++) s.out[d][m].release();
         }
+        s.list.release(); s.list_count.release();
         s.dest.release(); s.rec_len.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
         for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.totals_host) cudaFreeHost(s.totals_host);

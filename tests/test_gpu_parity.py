@@ -51,13 +51,15 @@ def random_reads(rng, adapter, n_reads, max_len=160, alphabet="ACGT"):
 
 
 def check_locate(op, reads):
+    """Both execution modes: exact DP on every read, and bit-parallel prefilter + exact DP on the survivors."""
     batch, keep = oracle.make_batch(reads)
-    got = native.locate_batch(op, batch.mate[0], len(reads))
-    for i, (_, s, _) in enumerate(reads):
-        want = oracle.adapter_match(op, s)
-        g = got[i]
-        have = None if not g["found"] else tuple(int(g[k]) for k in ("ref_start", "ref_stop", "query_start", "query_stop", "score", "errors"))
-        assert have == want, (op.adapter, op.adapter_kind, op.max_error_rate, op.min_overlap, s, have, want)
+    wants = [oracle.adapter_match(op, s) for (_, s, _) in reads]
+    for flags in (A.PLAN_NO_PREFILTER, 0):
+        got = native.locate_batch(op, batch.mate[0], len(reads), flags=flags)
+        for i, (_, s, _) in enumerate(reads):
+            g = got[i]
+            have = None if not g["found"] else tuple(int(g[k]) for k in ("ref_start", "ref_stop", "query_start", "query_stop", "score", "errors"))
+            assert have == wants[i], (flags, op.adapter, op.adapter_kind, op.max_error_rate, op.min_overlap, s, have, wants[i])
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -96,9 +98,9 @@ def test_locate_two_letter_alphabet_ties():
             check_locate(op, random_reads(rng, adapter, 400, max_len=60, alphabet="AC"))
 
 
-def run_gpu(prog, mates):
+def run_gpu(prog, mates, flags=0):
     batch, keep = oracle.make_batch(*mates)
-    with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES) as plan:
+    with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES | flags) as plan:
         text, records = plan.run_batch(batch)
         n = batch.n_reads
         results = [plan.results(0, m, n) for m in range(batch.n_mates)]
@@ -113,8 +115,8 @@ def run_gpu(prog, mates):
 COUNTER_FIELDS = ("n", "written", "too_short", "untrimmed")
 
 
-def compare_with_oracle(prog, mates):
-    text, records, results, matches, stats, batch, keep = run_gpu(prog, mates)
+def compare_with_oracle(prog, mates, flags=0):
+    text, records, results, matches, stats, batch, keep = run_gpu(prog, mates, flags)
     want = oracle.run_batch(prog, batch, n_threads=4)
     n_mates = batch.n_mates
     for m in range(n_mates):
@@ -143,11 +145,12 @@ def compare_with_oracle(prog, mates):
     return text
 
 
+@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER], ids=["prefilter", "exact_only"])
 @pytest.mark.parametrize("case", helpers.golden_cases(), ids=lambda c: c["case"])
-def test_golden_vectors(case):
+def test_golden_vectors(case, flags):
     prog = helpers.program_for(case["argv"], case["n_mates"])
     mates = helpers.golden_inputs(case)
-    text = compare_with_oracle(prog, mates)
+    text = compare_with_oracle(prog, mates, flags)
     for (d, m), data in helpers.expected_by_dest(case, prog).items():
         assert text[d][m] == data, (case["case"], helpers.DEST_KEYS[d], m)
 
@@ -218,3 +221,34 @@ def test_random_programs_against_oracle():
                                 mask5=bc.mask5.len, mask3=bc.mask3.len, strand=bc.strand or "+", readthrough=0.5,
                                 polya=0.2, bc_error=0.03, wrong_bc=0.1, suffix_style=rng.choice([None, "slash", "dot", "bare"]))
         compare_with_oracle(prog, [r1, r2] if n_mates == 2 else [r1])
+
+
+def test_synthetic_configs_against_oracle():
+    """BASELINE.json configs 2-4 (synthetic generator), 30 000 units each, whole chain vs the oracle."""
+    cases = [
+        (2, ["-A", "TAKARAV3", "--trim-polyA"], 2),
+        (3, ["-a", "ACACGACGCTCTTCCGATCT(ATCACG)NNNNNNNNXXX<XXX(CGTGAT)AGATCGGAAGAGCACACGTC", "--ensure-inline-barcode"], 2),
+        (3, ["-a", "ACACGACGCTCTTCCGATCT(ATCACG)NNNNNNNNXXX<XXX(CGTGAT)AGATCGGAAGAGCACACGTC"], 2),
+        (4, ["-A", "SMALLRNA"], 1),
+    ]
+    for config, argv, n_mates in cases:
+        prog = helpers.program_for(argv, n_mates)
+        batch = native.synth_batch(config, 30000, first_index=12345, buffer=3)
+        want = oracle.run_batch(prog, batch, n_threads=8)
+        for flags in (0, A.PLAN_NO_PREFILTER):
+            with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES | flags) as plan:
+                text, records = plan.run_batch(batch)
+                stats = plan.stats()
+                for m in range(n_mates):
+                    ops = prog.ops_r1 if m == 0 else prog.ops_r2
+                    for t, op in enumerate(ops):
+                        if op.kind == A.OP_ALIGN:
+                            got = plan.matches(0, m, t, batch.n_reads)
+                            w = want["matches"][m][t]
+                            for f in ("found", "ref_start", "ref_stop", "query_start", "query_stop", "score", "errors"):
+                                assert (got[f] == w[f]).all(), (config, argv, flags, m, t, f)
+            for d in range(A.CSQ_N_DEST):
+                for m in range(n_mates):
+                    assert text[d][m] == want["text"][d][m], (config, argv, flags, d, m)
+            assert list(stats.dp_cells[0]) == list(want["counters"].dp_cells[0])
+            assert stats.written == want["counters"].written and stats.untrimmed == want["counters"].untrimmed
