@@ -152,6 +152,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. NCCL's version banner)
+    # is sent to stderr by pointing fd 1 at fd 2 until the result is written to the saved descriptor.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
 
     from cutseq_b200 import _abi as A
@@ -222,7 +228,8 @@ def main():
     if not args.no_e2e:
         cap = int(max(b.mate[0].name_bytes for b in batches) + 2 * batches[0].mate[0].seq_bytes + 32 * P + 4096)
         outs, keep = [], []
-        for s in range(2):
+        n_e2e = 3 if B + 2 < A.CSQ_N_SLOTS else 2  # batches in flight: keeps the H2D engine busy while a D2H drains
+        for s in range(n_e2e):
             out = A.csq_batch_out()
             for d in range(A.CSQ_N_DEST):
                 for m in range(2):
@@ -232,16 +239,18 @@ def main():
                     out.text[d][m].data = buf.data_ptr()
                     out.text[d][m].capacity = size
             outs.append(out)
-        e2e_slots = (B, B + 1) if B + 1 < A.CSQ_N_SLOTS else (0, 1)
+        e2e_slots = [B + i for i in range(n_e2e)] if B + n_e2e <= A.CSQ_N_SLOTS else list(range(n_e2e))
 
         def e2e_steps(k):
+            """k steps, up to n_e2e batches in flight (submit of step i+n-1 is issued before the wait of step i)."""
             d2h = 0
-            plan.submit(e2e_slots[0], batches[0], outs[0])
-            for i in range(1, k + 1):
-                if i < k:
-                    plan.submit(e2e_slots[i % 2], batches[i % len(batches)], outs[i % 2])
-                plan.wait(e2e_slots[(i - 1) % 2])
-                o = outs[(i - 1) % 2]
+            submitted = 0
+            for i in range(k):
+                while submitted < k and submitted < i + n_e2e:
+                    plan.submit(e2e_slots[submitted % n_e2e], batches[submitted % len(batches)], outs[submitted % n_e2e])
+                    submitted += 1
+                plan.wait(e2e_slots[i % n_e2e])
+                o = outs[i % n_e2e]
                 d2h += sum(o.text[d][m].bytes for d in range(A.CSQ_N_DEST) for m in range(2))
             return d2h
 
@@ -255,7 +264,7 @@ def main():
         e2e_s = max_over_ranks(w1 - w0)
         e2e = {"value": world * args.steps * P / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(batches[0]),
                "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_s / args.steps * 1e3,
-               "timing": "wall clock between device-synchronised points, double-buffered csq_submit/csq_wait, max over ranks"}
+               "timing": f"wall clock between device-synchronised points, {n_e2e} batches in flight through csq_submit/csq_wait, max over ranks"}
 
     if rank != 0:
         plan.close()
@@ -336,7 +345,8 @@ def main():
         "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "clocks": clocks,
         "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(result_fd, (json.dumps(line) + "\n").encode())
     plan.close()
     group.close()
     return 0

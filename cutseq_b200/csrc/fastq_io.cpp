@@ -11,6 +11,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -31,10 +32,14 @@ int io_fail(int code, const char* fmt, ...) {
 const char* io_error() { return g_io_err; }
 
 // ---- pinned (or plain, when no CUDA context can be had) host memory ----------------------
+static std::atomic<int> g_pinning(1);  // cleared after the first failure (CPU-only host): do not retry per buffer
+
 void* host_alloc(size_t bytes) {
+    if (!g_pinning.load(std::memory_order_relaxed)) return nullptr;
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p;
     cudaGetLastError();
+    g_pinning.store(0, std::memory_order_relaxed);
     return nullptr;
 }
 
@@ -51,7 +56,9 @@ void PinnedBuf::release() {
 }
 bool PinnedBuf::reserve(size_t bytes, size_t keep) {
     if (bytes <= cap) return true;
-    size_t want = bytes + bytes / 4 + 4096;
+    // pinned allocations are expensive: grow geometrically (x2) and never below 64 KiB
+    size_t want = bytes > 2 * cap ? bytes : 2 * cap;
+    if (want < (64u << 10)) want = 64u << 10;
     void* q = host_alloc(want);
     bool pin = q != nullptr;
     if (!q) q = malloc(want);
@@ -178,6 +185,15 @@ int parse_records(const uint8_t* text, size_t n_bytes, bool at_eof, uint32_t max
     return 0;
 }
 
+// Reserve room for a batch of `reads` records of about `read_len` bases up front, so that steady-state
+// parsing never reallocates pinned memory.
+bool MateSoA::presize(uint32_t reads, uint32_t read_len, uint32_t name_len) {
+    const size_t stride = ((size_t)read_len + 15) / 16 * 16;
+    return seq.reserve(stride * reads + 64, seq_bytes) && qual.reserve(stride * reads + 64, seq_bytes) &&
+           name.reserve((size_t)name_len * reads + 64, name_bytes) && seq_off.reserve(((size_t)reads + 2) * 4, (size_t)n * 4) &&
+           seq_len.reserve(((size_t)reads + 2) * 4, (size_t)n * 4) && name_off.reserve(((size_t)reads + 3) * 4, ((size_t)n + 1) * 4);
+}
+
 void MateSoA::clear() {
     n = 0;
     seq_bytes = name_bytes = 0;
@@ -198,12 +214,23 @@ void MateSoA::view(csq_mate_in* mi) const {
 
 int MateParser::next(uint32_t max_reads, MateSoA& out) {
     out.clear();
+    if (hint_read_len && !out.presize(max_reads, hint_read_len, hint_name_len))
+        return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
     const size_t CHUNK = 8u << 20;
     for (;;) {
         size_t used = 0;
         int rc = parse_records(carry.data() + carry_pos, carry.size() - carry_pos, eof, max_reads, out, &used, &line_no, src.name.c_str());
         if (rc) return rc;
         carry_pos += used;
+        if (!hint_read_len && out.n >= 64) {
+            // first batch of the file: size the pools from what the first records look like (+10 % slack)
+            hint_read_len = (uint32_t)(out.total_bases / out.n) + 16;
+            hint_read_len += hint_read_len / 10;
+            hint_name_len = (uint32_t)(out.name_bytes / out.n) + 8;
+            hint_name_len += hint_name_len / 4;
+            if (!out.presize(max_reads, hint_read_len, hint_name_len))
+                return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
+        }
         if (out.n >= max_reads || eof) break;
         // need more text: drop what was consumed, append the next chunk
         if (carry_pos) {

@@ -28,6 +28,7 @@ struct MateSoA {  // csq_mate_in backing store
     uint32_t n = 0;
     uint64_t seq_bytes = 0, name_bytes = 0, total_bases = 0;
     void clear();
+    bool presize(uint32_t reads, uint32_t read_len, uint32_t name_len);
     void view(csq_mate_in* mi) const;
 };
 
@@ -46,6 +47,7 @@ struct MateParser {
     size_t carry_pos = 0;
     bool eof = false;
     uint64_t line_no = 0;
+    uint32_t hint_read_len = 0, hint_name_len = 0;  // pool sizing hints learnt from the first records
     int open(const char* path);
     int next(uint32_t max_reads, MateSoA& out);
 };

@@ -148,12 +148,25 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
     const int step = P.reversed ? -1 : 1;
     const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
 
+    // Homopolymer adapter and no free read start: every read character that differs from the adapter base
+    // adds at least 1 to EVERY cell of its column and of all later ones; once more than k such characters
+    // have been seen no cell can be accepted any more (acceptance needs cost <= k), so the scan may stop.
+    int foreign = 0;
+    bool cut_short = false;
     for (int j = min_n + 1; j <= max_n; j++, p += step) {
         const uint32_t c = *p;
         uint32_t pm[NW];
         uint32_t dcol = 0;
         if constexpr (HOMO) {
-            dcol = ((c & 0xDFu) == (uint32_t)P.letter) ? D_MATCH : D_MIS;
+            const bool eq = (c & 0xDFu) == (uint32_t)P.letter;
+            dcol = eq ? D_MATCH : D_MIS;
+            if (!siq) {
+                foreign += eq ? 0 : 1;
+                if (foreign > k) {
+                    cut_short = true;
+                    break;
+                }
+            }
         } else {
 #pragma unroll
             for (int w = 0; w < NW; w++) pm[w] = lut[c * NW + w];
@@ -176,7 +189,7 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
         }
         if (eiq) row_m_update(W[M], j, M, n, P, best);
     }
-    if (max_n == n) {
+    if (max_n == n && !cut_short) {
         const int first_i = eir ? 0 : M;
 #pragma unroll
         for (int i = M; i >= 0; i--)

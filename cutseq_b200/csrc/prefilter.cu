@@ -127,11 +127,69 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
     }
 }
 
+// Homopolymer adapters (the poly-A / poly-T 100-mers of reference run.py:389-404, 674-707) in their two
+// non-internal kinds need no bit-vectors.  With e(l) = number of read characters different from the adapter
+// base among the l characters next to the anchored end (read start for NonInternalFront, read end for
+// NonInternalBack), every alignment that covers those l characters costs at least e(l), and covers at most
+// l + cost adapter characters; thr[] grows by at most 1 per step, so "cost <= thr[min(m, l + cost)]" can
+// only hold for some cost >= e(l) if it holds for cost == e(l).  e(l) never decreases, hence the scan
+// stops at the first l with e(l) > k (about 20 characters into a random read instead of m + k = 115 columns).
+__global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ AlignParams P, uint32_t* __restrict__ list,
+                                                        uint32_t* __restrict__ list_count) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < P.n;
+    bool pass = false;
+    unsigned int cells = 0;
+    if (valid) {
+        ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
+        for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
+        store_state(P.md.state + idx, st);
+        const int m = P.m, k = P.k;
+        const int a = st.a, b = st.b, n = b - a;
+        const int span = min(n, m + k);  // columns the aligner visits (max_n - min_n for both kinds)
+        cells = (unsigned int)(m * span);
+        const bool from_end = (P.flags & 2) != 0;  // NonInternalBack: anchored at the read end
+        const uint8_t* s = P.md.seq + P.md.seq_off[idx];
+        const uint8_t* p = from_end ? (s + b - 1) : (s + a);
+        const int step = from_end ? -1 : 1;
+        int e = 0;
+        for (int l = 1; l <= span; l++, p += step) {
+            e += ((uint32_t)(*p & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
+            if (e > k) break;
+            const int L = min(m, l + e);
+            if (L >= P.min_overlap && e <= (int)P.thr[L]) {
+                pass = true;
+                break;
+            }
+        }
+        if (!pass && P.matches) {
+            csq_match r;
+            r.found = r.ref_start = r.ref_stop = r.query_start = r.query_stop = r.score = r.errors = r.reserved = 0;
+            P.matches[idx] = r;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && cells) atomicAdd(P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS), (unsigned long long)cells);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+    if (ballot) {
+        const int leader = __ffs(ballot) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(list_count, (unsigned int)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass) list[base + __popc(ballot & ((1u << lane) - 1u))] = idx;
+    }
+}
+
 }  // namespace
 
 cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t* list_count, cudaStream_t stream) {
     if (p.n == 0) return cudaSuccess;
     const dim3 grid((p.n + 255) / 256), block(256);
+    if (p.homopolymer && !p.reversed && (p.flags == 9 || p.flags == 6)) {  // NonInternalFront / NonInternalBack
+        k_prefilter_homo<<<grid, block, 0, stream>>>(p, list, list_count);
+        return cudaGetLastError();
+    }
     const int nw = (p.m + 31) / 32;
     switch (nw) {
         case 1: k_prefilter<1><<<grid, block, 0, stream>>>(p, list, list_count); break;

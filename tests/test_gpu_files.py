@@ -86,3 +86,16 @@ def test_config1_full_bundled_input(case, tmp_path, capsys):
         got = read_maybe_gz(f"{prefix}_{key}.fastq.gz")
         assert len(got) == meta["bytes"] and hashlib.sha256(got).hexdigest() == meta["sha256"], key
     assert case["minimal_report"][-1] in err.splitlines()
+
+
+def test_multi_gpu_file_run_is_order_preserving(tmp_path):
+    """csq_run_files sharding batches over 2 GPUs must give the single-GPU bytes (skipped on a 1-GPU box)."""
+    from cutseq_b200 import native
+
+    if native.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_polya"][0]
+    prefix = str(tmp_path / "out")
+    run.main(case["argv"] + ["-O", prefix, "--gpus", "2", "--batch-reads", "97", "-t", "2"] + helpers.golden_input_paths(case))
+    for key in case["outputs"]:
+        assert read_maybe_gz(f"{prefix}_{key}.fastq.gz") == helpers.golden_expected(case, key), key
