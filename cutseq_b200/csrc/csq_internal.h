@@ -12,6 +12,7 @@
 // cost is stored in 10 bits                  -> m + n <= 1023
 #define CSQ_FAST_MAX_READ 895
 #define CSQ_MAX_PRE 12 /* scalar ops executed in front of one ALIGN op */
+#define CSQ_PF_BINS 4   /* prefilter survivor lists (classes of DP columns left for the exact pass) */
 
 // Scalar (O(1)) ops that sit between alignments: CUT, COND_CUT, RENAME(capture).
 struct DevOp {
@@ -46,8 +47,10 @@ struct MateDev {  // device pointers of one mate of one slot
 struct AlignParams {
     MateDev md;
     csq_match* matches;    // nullable: per-read record of this ALIGN op
-    const uint32_t* list;  // nullable: indices of the reads to process (prefilter survivors)
-    const uint32_t* list_count;  // with list: number of entries (device side)
+    // nullable: prefilter survivors. CSQ_PF_BINS lists of read indices, list b at list[b * n ..), followed by the
+    // uint16 first-DP-column of every entry in the same layout (0xFFFF: the aligner's own min_n)
+    const uint32_t* list;
+    const uint32_t* list_count;  // with list: entries per list (device side)
     uint32_t n;            // reads in the batch
     int32_t first;         // 1: state is initialised here (first segment of the program)
     int32_t count_cells;   // 1: add the nominal DP cells of this launch to the statistics
@@ -89,7 +92,6 @@ struct PairParams {
     int32_t check_ids;      // paired RENAME present: mate ids must be equal
     int32_t revcomp;        // single-end REVCOMP op present
     uint8_t* dest;          // [n]
-    uint32_t* rec_len;      // [2][n] bytes of the FASTQ record of each mate
     uint32_t* block_tot;    // [nblk][8]: bytes per (dest,mate) stream (6 used)
     uint32_t* block_cnt;    // [nblk][4]: records per dest
     unsigned long long* counters;

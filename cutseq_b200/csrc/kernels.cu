@@ -25,6 +25,7 @@
 // accepted nor lie on the path of an accepted cell, so the full DP yields identical results.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "csq_internal.h"
 #include "device_common.cuh"
@@ -127,7 +128,7 @@ __device__ __forceinline__ void best_to_match(const Best& best, int m, int n, bo
 // Exact DP for a compile-time adapter length M: the column lives in registers W[0..M].
 template <int M, bool HOMO>
 __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P,
-                                         const uint32_t* __restrict__ lut, csq_match& r) {
+                                         const uint32_t* __restrict__ lut, int j0, csq_match& r) {
     constexpr int NW = (M + 31) / 32;
     const int n = b - a;
     const int k = P.k;
@@ -135,6 +136,13 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
     int max_n = n, min_n = 0;
     if (!siq) max_n = min(n, M + k);
     if (!eiq) min_n = max(0, n - M - k);
+    // Column window (BACK flags, set by the prefilter): the DP starts at column j0 > min_n as if the read began
+    // there.  With a free read start the cost of cell (i, j) is the best alignment of adapter[0:i] ending at j,
+    // which spans at most i + cost columns; a cell that Aligner.locate can accept (cost <= k) and every
+    // neighbour that is compared on its traceback path (cost <= k + 1) therefore has the same cost, and by
+    // induction along the path the same (cost, score, origin), as in the full matrix when
+    // j0 <= j - (m + 3k + 2).  The prefilter guarantees this for all columns that can hold an accepted cell.
+    if (j0 >= 0) min_n = max(min_n, j0);
 
     uint32_t W[M + 1];
 #pragma unroll
@@ -200,13 +208,14 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
 
 // Same recurrence for any m <= CSQ_MAX_ADAPTER with the column in local memory (slow path for
 // adapter lengths without a register-resident instantiation).
-__device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P,
+__device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P, int j0,
                                         csq_match& r) {
     const int m = P.m, n = b - a, k = P.k;
     const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
     int max_n = n, min_n = 0;
     if (!siq) max_n = min(n, m + k);
     if (!eiq) min_n = max(0, n - m - k);
+    if (j0 >= 0) min_n = max(min_n, j0);  // column window, see dp_exact
     uint32_t W[CSQ_MAX_ADAPTER + 1];
     for (int i = 0; i <= m; i++) {
         int cost, origin;
@@ -244,8 +253,25 @@ template <int M, bool HOMO>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
     __shared__ uint32_t lut[(HOMO || M == 0) ? 1 : 256 * NW];
-    const uint32_t count = P.list ? *P.list_count : P.n;
-    if (blockIdx.x * blockDim.x >= count) return;  // whole CTA beyond the survivor list
+    // With survivor lists: CTA c works on 128 consecutive entries of one list, the lists (longest DP first) laid
+    // end to end in units of CTAs; the grid is sized for the worst case, surplus CTAs leave at once.
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, count = P.n;
+    size_t list_base = 0;
+    if (P.list) {
+        uint32_t cta = blockIdx.x;
+        int bin = 0;
+        for (; bin < CSQ_PF_BINS; bin++) {
+            count = P.list_count[bin];
+            const uint32_t ctas = (count + blockDim.x - 1) / blockDim.x;
+            if (cta < ctas) break;
+            cta -= ctas;
+        }
+        if (bin == CSQ_PF_BINS) return;
+        t = cta * blockDim.x + threadIdx.x;
+        list_base = (size_t)bin * P.n;
+    } else if (blockIdx.x * blockDim.x >= count) {
+        return;
+    }
     if constexpr (!HOMO && M > 0) {
         for (int c = threadIdx.x; c < 256; c += blockDim.x) {
             const int u = c & 0xDF;
@@ -255,9 +281,14 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
         }
         __syncthreads();
     }
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    const uint32_t idx = P.list ? P.list[t] : t;
+    uint32_t idx = t;
+    int j0 = -1;
+    if (P.list) {
+        idx = P.list[list_base + t];
+        const uint32_t w = reinterpret_cast<const uint16_t*>(P.list + (size_t)CSQ_PF_BINS * P.n)[list_base + t];
+        if (w != 0xFFFFu) j0 = (int)w;
+    }
     ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
     for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
 
@@ -279,9 +310,9 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
         }
     }
     if constexpr (M > 0)
-        dp_exact<M, HOMO>(s, st.a, st.b, P, lut, r);
+        dp_exact<M, HOMO>(s, st.a, st.b, P, lut, j0, r);
     else
-        dp_generic(s, st.a, st.b, P, r);
+        dp_generic(s, st.a, st.b, P, j0, r);
     if (r.found) {
         st.matched |= 0x80000000u | (P.adapter_bit >= 0 ? (1u << P.adapter_bit) : 0u);
         if (P.trim_front)
@@ -400,57 +431,55 @@ __device__ __forceinline__ RecordShape record_shape(const PairParams& P, const R
 }
 
 // Filters + sink of run.py:446-471 / 763-792 and the byte size of every record.
+// Thread per pair; the per-CTA stream totals are warp-reduced (REDUX) before they touch shared memory.
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_pair(const __grid_constant__ PairParams P) {
-    __shared__ unsigned int tot[8];
-    __shared__ unsigned int cnt[4];
-    __shared__ unsigned long long stat[8];
-    if (threadIdx.x < 8) {
-        tot[threadIdx.x] = 0;
-        stat[threadIdx.x] = 0;
-    }
+    __shared__ unsigned int tot[8];   // bytes per (dest, mate) stream
+    __shared__ unsigned int cnt[4];   // records per dest
+    __shared__ unsigned int bp[2];    // bases written to the trimmed files, per mate
+    if (threadIdx.x < 8) tot[threadIdx.x] = 0;
     if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 2) bp[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t idx = blockIdx.x * CSQ_PAIR_BLOCK + threadIdx.x;
+    const bool paired = P.n_mates == 2;
+    int dest = -1;
+    uint32_t len1 = 0, len2 = 0, l1 = 0, l2 = 0;
     if (idx < P.n) {
-        const bool paired = P.n_mates == 2;
         const ReadState s1 = load_state(P.md[0].state + idx);
         const ReadState s2 = paired ? load_state(P.md[1].state + idx) : s1;
-        const int l1 = (int)s1.b - (int)s1.a, l2 = (int)s2.b - (int)s2.a;
-        int dest;
-        if (l1 < P.min_length || (paired && l2 < P.min_length))
+        l1 = (uint32_t)s1.b - (uint32_t)s1.a;
+        l2 = (uint32_t)s2.b - (uint32_t)s2.a;
+        if ((int)l1 < P.min_length || (paired && (int)l2 < P.min_length))
             dest = CSQ_DEST_SHORT;
         else if (P.untrimmed_enabled && ((P.required[0] & ~s1.matched) != 0 || (paired && (P.required[1] & ~s2.matched) != 0)))
             dest = CSQ_DEST_UNTRIMMED;
         else
             dest = CSQ_DEST_TRIMMED;
         P.dest[idx] = (uint8_t)dest;
-        const RecordShape a = record_shape(P, s1, s1, s2);
-        P.rec_len[idx] = a.total;
-        atomicAdd(&tot[dest * 2 + 0], a.total);
-        if (paired) {
-            const RecordShape b = record_shape(P, s2, s1, s2);
-            P.rec_len[P.n + idx] = b.total;
-            atomicAdd(&tot[dest * 2 + 1], b.total);
+        len1 = record_shape(P, s1, s1, s2).total;
+        if (paired) len2 = record_shape(P, s2, s1, s2).total;
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 0; d < CSQ_N_DEST; d++) {
+        const bool mine = dest == d;
+        const unsigned int c = __popc(__ballot_sync(0xffffffffu, mine));
+        if (c == 0) continue;  // warp-uniform
+        const unsigned int t1 = __reduce_add_sync(0xffffffffu, mine ? len1 : 0u);
+        const unsigned int t2 = __reduce_add_sync(0xffffffffu, mine ? len2 : 0u);
+        unsigned int b1 = 0, b2 = 0;
+        if (d == CSQ_DEST_TRIMMED) {
+            b1 = __reduce_add_sync(0xffffffffu, mine ? l1 : 0u);
+            b2 = __reduce_add_sync(0xffffffffu, (mine && paired) ? l2 : 0u);
         }
-        atomicAdd(&cnt[dest], 1u);
-        if (dest == CSQ_DEST_TRIMMED) {
-            atomicAdd(&stat[0], 1ULL);
-            atomicAdd(&stat[1], (unsigned long long)l1);
-            if (paired) atomicAdd(&stat[2], (unsigned long long)l2);
-        } else if (dest == CSQ_DEST_SHORT) {
-            atomicAdd(&stat[3], 1ULL);
-        } else {
-            atomicAdd(&stat[4], 1ULL);
-        }
-        if (P.check_ids && paired) {  // PairedEndRenamer: ids must be identical
-            const uint32_t n1 = (uint32_t)s1.id_end - s1.id_start, n2 = (uint32_t)s2.id_end - s2.id_start;
-            bool same = n1 == n2;
-            if (same) {
-                const uint8_t* p1 = P.md[0].name + P.md[0].name_off[idx] + s1.id_start;
-                const uint8_t* p2 = P.md[1].name + P.md[1].name_off[idx] + s2.id_start;
-                for (uint32_t x = 0; x < n1; x++) same = same && (p1[x] == p2[x]);
+        if (lane == 0) {
+            atomicAdd(&tot[d * 2 + 0], t1);
+            if (paired) atomicAdd(&tot[d * 2 + 1], t2);
+            atomicAdd(&cnt[d], c);
+            if (d == CSQ_DEST_TRIMMED) {
+                atomicAdd(&bp[0], b1);
+                atomicAdd(&bp[1], b2);
             }
-            if (!same) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
         }
     }
     __syncthreads();
@@ -458,11 +487,11 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_pair(const __grid_constant__
     if (threadIdx.x < 4) P.block_cnt[blockIdx.x * 4 + threadIdx.x] = cnt[threadIdx.x];
     if (threadIdx.x == 0) {
         atomicAdd(P.counters + CNT_N, (unsigned long long)min((uint32_t)CSQ_PAIR_BLOCK, P.n - blockIdx.x * CSQ_PAIR_BLOCK));
-        if (stat[0]) atomicAdd(P.counters + CNT_WRITTEN, stat[0]);
-        if (stat[1]) atomicAdd(P.counters + CNT_WRITTEN_BP, stat[1]);
-        if (stat[2]) atomicAdd(P.counters + CNT_WRITTEN_BP + 1, stat[2]);
-        if (stat[3]) atomicAdd(P.counters + CNT_TOO_SHORT, stat[3]);
-        if (stat[4]) atomicAdd(P.counters + CNT_UNTRIMMED, stat[4]);
+        if (cnt[CSQ_DEST_TRIMMED]) atomicAdd(P.counters + CNT_WRITTEN, (unsigned long long)cnt[CSQ_DEST_TRIMMED]);
+        if (bp[0]) atomicAdd(P.counters + CNT_WRITTEN_BP, (unsigned long long)bp[0]);
+        if (bp[1]) atomicAdd(P.counters + CNT_WRITTEN_BP + 1, (unsigned long long)bp[1]);
+        if (cnt[CSQ_DEST_SHORT]) atomicAdd(P.counters + CNT_TOO_SHORT, (unsigned long long)cnt[CSQ_DEST_SHORT]);
+        if (cnt[CSQ_DEST_UNTRIMMED]) atomicAdd(P.counters + CNT_UNTRIMMED, (unsigned long long)cnt[CSQ_DEST_UNTRIMMED]);
     }
 }
 
@@ -535,41 +564,57 @@ __device__ __forceinline__ uint8_t complement_base(uint8_t c) {
 // FASTQ text, "@name\nseq\n+\nqual\n" (dnaio), streams in input order.
 // Phase 1 (thread per pair): load the two mate states once, CTA-wide exclusive scan of the record sizes
 // per output stream, one descriptor per record into shared memory.
-// Phase 2 (warp per record): byte gather with EMIT_UNROLL independent loads in flight per lane before
-// the stores (the kernel is latency bound, not issue bound: every source byte is read exactly once).
+// Phase 2 (warp per record): bases and qualities, ~85 % of the bytes, as output-aligned 32-bit words built
+// from two aligned source words (funnel shift) - a warp instruction writes 128 contiguous bytes; the id,
+// the UMI, the separators and the up to 3 + 3 bytes of each segment outside the output's word grid go
+// bytewise, one byte per lane, in the same pass, so every 32-byte sector of the output is completed by one
+// warp within a few instructions (scattering these bytes from the per-pair threads of phase 1 doubled the
+// DRAM traffic: partially written sectors were filled from and evicted to HBM).  All loads of a record are
+// issued before its first store; no shared-memory staging and no barrier in the copy loop.
+// Every source byte is read once and every output byte written once.
+// The reverse-complementing single-end sink takes a bytewise path.
 struct EmitRec {
-    const uint8_t* nm;   // id bytes
-    const uint8_t* sq;   // original read, bases
-    const uint8_t* ql;   // original read, qualities
-    const uint8_t* pa;   // first UMI part (or null)
-    const uint8_t* pb;   // second UMI part
     uint8_t* out;        // where the record goes
+    uint32_t nm;         // id bytes: offset into the mate's name pool
+    uint32_t sq, ql;     // original read: offsets into the seq / qual pools
+    uint32_t pa, pb;     // UMI parts: offsets into the pool of the mate they come from
     uint16_t id_len, lenA, lenB, a, b;
     uint16_t umi_len;    // '_' + parts, 0 when the template is "{id}"
 };
 
+struct EmitSrc {  // global pointers of one record
+    const uint8_t *nm, *sq, *ql, *pa, *pb;
+};
+
 constexpr int EMIT_UNROLL = 4;
 
-__device__ __forceinline__ uint8_t emit_byte(const EmitRec& R, uint32_t p, uint32_t e_name, uint32_t e_umi, uint32_t e_seq,
-                                             uint32_t e_qual, bool revcomp) {
-    if (p < e_name) return p == 0 ? (uint8_t)'@' : R.nm[p - 1];
+__device__ __forceinline__ uint8_t emit_byte(const EmitRec& R, const EmitSrc& S, uint32_t p, uint32_t e_name, uint32_t e_umi,
+                                             uint32_t e_seq, uint32_t e_qual, bool revcomp) {
+    if (p < e_name) return p == 0 ? (uint8_t)'@' : S.nm[p - 1];
     if (p < e_umi) {
         uint32_t x = p - e_name;
         if (x == 0) return (uint8_t)'_';
         x -= 1;
-        return x < R.lenA ? R.pa[x] : R.pb[x - R.lenA];
+        return x < R.lenA ? S.pa[x] : S.pb[x - R.lenA];
     }
     if (p == e_umi) return (uint8_t)'\n';
     if (p < e_seq) {
         const uint32_t x = p - e_umi - 1;
-        return revcomp ? complement_base(R.sq[R.b - 1 - x]) : R.sq[R.a + x];
+        return revcomp ? complement_base(S.sq[R.b - 1 - x]) : S.sq[R.a + x];
     }
     if (p < e_seq + 3) return (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
     if (p < e_qual) {
         const uint32_t x = p - e_seq - 3;
-        return revcomp ? R.ql[R.b - 1 - x] : R.ql[R.a + x];
+        return revcomp ? S.ql[R.b - 1 - x] : S.ql[R.a + x];
     }
     return (uint8_t)'\n';
+}
+
+// Split of a len-byte segment that goes to byte address `dst`: `head` bytes up to the next 4-byte boundary,
+// `nw` whole words, then the rest.
+__device__ __forceinline__ void word_split(const uint8_t* dst, uint32_t len, uint32_t& head, uint32_t& nw) {
+    head = min((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u, len);
+    nw = (len - head) >> 2;
 }
 
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__ EmitParams E) {
@@ -580,6 +625,10 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool paired = P.n_mates == 2;
     const int n_mates = paired ? 2 : 1;
+    const bool revcomp = P.revcomp != 0;
+    // pools the UMI parts come from: the mate itself (single-end template) or R1 / R2 (paired template)
+    const uint8_t* const poolA = (P.rename_parts & CSQ_REN_R1_PREFIX) ? P.md[0].seq : nullptr;
+    const uint8_t* const poolB = (P.rename_parts & CSQ_REN_R2_PREFIX) ? P.md[1].seq : nullptr;
 
     // ---- phase 1 ----
     const uint32_t idx = base + threadIdx.x;
@@ -618,14 +667,14 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
             const MateDev& md = P.md[mt];
             const ReadState& own = st[mt];
             EmitRec R;
-            R.nm = md.name + md.name_off[idx] + own.id_start;
-            R.sq = md.seq + md.seq_off[idx];
-            R.ql = md.qual + md.seq_off[idx];
-            R.pa = R.pb = nullptr;
+            R.nm = md.name_off[idx] + own.id_start;
+            R.sq = md.seq_off[idx];
+            R.ql = md.seq_off[idx];
+            R.pa = R.pb = 0;
             if (P.rename_parts & CSQ_REN_OWN_PREFIX) R.pa = R.sq + (own.ren_cp >> 16);
             if (P.rename_parts & CSQ_REN_OWN_SUFFIX) R.pb = R.sq + (own.ren_cs >> 16);
-            if (P.rename_parts & CSQ_REN_R1_PREFIX) R.pa = P.md[0].seq + P.md[0].seq_off[idx] + (st[0].ren_cp >> 16);
-            if (P.rename_parts & CSQ_REN_R2_PREFIX) R.pb = P.md[1].seq + P.md[1].seq_off[idx] + (st[1].ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_R1_PREFIX) R.pa = P.md[0].seq_off[idx] + (st[0].ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_R2_PREFIX) R.pb = P.md[1].seq_off[idx] + (st[1].ren_cp >> 16);
             R.out = E.out[dest][mt] + E.block_off[(size_t)blockIdx.x * 8 + stream] + off;
             R.id_len = (uint16_t)shape[mt].id_len;
             R.lenA = (uint16_t)shape[mt].lenA;
@@ -639,34 +688,124 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
     __syncthreads();
 
     // ---- phase 2 ----
-    const bool revcomp = P.revcomp != 0;
+    bool id_mismatch = false;
+    uint32_t id0_len = 0, id0_v0 = 0, id0_v1 = 0;  // id of mate 1 of the current pair, as held by this lane
     for (int q = 0; q < 32; q++) {
         const int slot = wid * 32 + q;
         if (base + slot >= P.n) break;
         for (int mt = 0; mt < n_mates; mt++) {
             const EmitRec& R = recs[mt][slot];
+            const MateDev& md = P.md[mt];
             const uint32_t seq_len = (uint32_t)R.b - (uint32_t)R.a;
-            const uint32_t e_name = 1 + R.id_len;
-            const uint32_t e_umi = e_name + R.umi_len;
-            const uint32_t e_seq = e_umi + 1 + seq_len;
-            const uint32_t e_qual = e_seq + 3 + seq_len;
-            const uint32_t total = e_qual + 1;
+            const uint32_t e_umi = 1u + R.id_len + R.umi_len;
             uint8_t* __restrict__ out = R.out;
-            for (uint32_t p0 = lane; p0 < total; p0 += 32 * EMIT_UNROLL) {
-                uint8_t ch[EMIT_UNROLL];
+            if (revcomp) {
+                EmitSrc S;
+                S.nm = md.name + R.nm;
+                S.sq = md.seq + R.sq;
+                S.ql = md.qual + R.ql;
+                S.pa = (poolA ? poolA : md.seq) + R.pa;
+                S.pb = (poolB ? poolB : md.seq) + R.pb;
+                const uint32_t e_name = 1u + R.id_len, e_seq = e_umi + 1 + seq_len, e_qual = e_seq + 3 + seq_len, total = e_qual + 1;
+                for (uint32_t p0 = lane; p0 < total; p0 += 32 * EMIT_UNROLL) {
+                    uint8_t ch[EMIT_UNROLL];
 #pragma unroll
-                for (int u = 0; u < EMIT_UNROLL; u++) {
-                    const uint32_t p = p0 + 32 * u;
-                    ch[u] = p < total ? emit_byte(R, p, e_name, e_umi, e_seq, e_qual, revcomp) : (uint8_t)0;
-                }
+                    for (int u = 0; u < EMIT_UNROLL; u++) {
+                        const uint32_t p = p0 + 32 * u;
+                        ch[u] = p < total ? emit_byte(R, S, p, e_name, e_umi, e_seq, e_qual, true) : (uint8_t)0;
+                    }
 #pragma unroll
-                for (int u = 0; u < EMIT_UNROLL; u++) {
-                    const uint32_t p = p0 + 32 * u;
-                    if (p < total) out[p] = ch[u];
+                    for (int u = 0; u < EMIT_UNROLL; u++) {
+                        const uint32_t p = p0 + 32 * u;
+                        if (p < total) out[p] = ch[u];
+                    }
                 }
+                continue;
+            }
+            // bases to out + e_umi + 1, qualities to out + e_umi + 1 + seq_len + 3; word k of a segment goes to the
+            // k-th 4-byte boundary at or behind its first byte
+            const uint32_t id_len = R.id_len, la = R.lenA, lab = la + R.lenB;
+            const uint32_t e_name = 1u + id_len, e_seq = e_umi + 1 + seq_len, e_qual = e_seq + 3 + seq_len;
+            const uint8_t* __restrict__ nm = md.name + R.nm;
+            const uint8_t* __restrict__ sq = md.seq + R.sq + R.a;
+            const uint8_t* __restrict__ ql = md.qual + R.ql + R.a;
+            const uint8_t* __restrict__ pa = (poolA ? poolA : md.seq) + R.pa;
+            const uint8_t* __restrict__ pb = (poolB ? poolB : md.seq) + R.pb;
+            uint8_t* const d_seq = out + e_umi + 1;
+            uint8_t* const d_qual = d_seq + seq_len + 3;
+            uint32_t h_s, nw_s, h_q, nw_q;
+            word_split(d_seq, seq_len, h_s, nw_s);
+            word_split(d_qual, seq_len, h_q, nw_q);
+            // ---- loads ----
+            // lanes 0..15: segment edges (4 groups of up to 3 bytes); lanes 16..22: the seven separator bytes
+            // (selects only: a chain of `lane ==` branches became a divergent jump table)
+            uint32_t misc_pos = 0xFFFFFFFFu;
+            uint32_t misc_val;
+            {
+                const uint32_t t = (uint32_t)lane - 16u;  // separator index for lanes 16..22
+                uint32_t sp = e_seq + (t - 3u);            // t = 3, 4, 5: "\n+\n"
+                sp = t == 0 ? 0u : sp;
+                sp = t == 1 ? e_name : sp;
+                sp = t == 2 ? e_umi : sp;
+                sp = t == 6 ? e_qual : sp;
+                const bool sep_ok = t < 7u && !(t == 1 && R.umi_len == 0);
+                misc_val = (uint32_t)(0x0A0A2B0A0A5F40ull >> (8u * (t & 7u))) & 0xFFu;  // "@_\n\n+\n\n"
+                const uint32_t g = (uint32_t)lane >> 2, x = (uint32_t)lane & 3u;
+                const bool is_q = (g & 2u) != 0, is_tail = (g & 1u) != 0;
+                const uint32_t h = is_q ? h_q : h_s, nw = is_q ? nw_q : nw_s;
+                const uint32_t o = is_tail ? h + 4u * nw + x : x;  // offset inside the segment
+                const uint32_t lim = is_tail ? seq_len : h;
+                const bool edge_ok = lane < 16 && x < 3 && o < lim;
+                if (edge_ok) misc_val = (is_q ? ql : sq)[o];
+                const uint32_t ep = (is_q ? e_seq + 3 : e_umi + 1) + o;
+                misc_pos = edge_ok ? ep : (sep_ok ? sp : 0xFFFFFFFFu);
+            }
+            const uint32_t idv0 = (uint32_t)lane < id_len ? nm[lane] : 0u;
+            const uint32_t idv1 = (uint32_t)lane + 32u < id_len ? nm[lane + 32] : 0u;
+            uint32_t umiv = 0;
+            if ((uint32_t)lane < lab) umiv = (uint32_t)lane < la ? pa[lane] : pb[lane - la];
+            const uintptr_t sa_s = (uintptr_t)(sq + h_s), sa_q = (uintptr_t)(ql + h_q);
+            const uint32_t* __restrict__ al_s = reinterpret_cast<const uint32_t*>(sa_s & ~(uintptr_t)3);
+            const uint32_t* __restrict__ al_q = reinterpret_cast<const uint32_t*>(sa_q & ~(uintptr_t)3);
+            const uint32_t sh_s = (uint32_t)(sa_s & 3u) * 8u, sh_q = (uint32_t)(sa_q & 3u) * 8u;
+            uint32_t* __restrict__ o_s = reinterpret_cast<uint32_t*>(d_seq + h_s);
+            uint32_t* __restrict__ o_q = reinterpret_cast<uint32_t*>(d_qual + h_q);
+            const uint32_t k1 = lane, k2 = k1 + 32;
+            uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+            if (k1 < nw_s) { a0 = al_s[k1]; a1 = al_s[k1 + 1]; }
+            if (k2 < nw_s) { b0 = al_s[k2]; b1 = al_s[k2 + 1]; }
+            if (k1 < nw_q) { c0 = al_q[k1]; c1 = al_q[k1 + 1]; }
+            if (k2 < nw_q) { d0 = al_q[k2]; d1 = al_q[k2 + 1]; }
+            if (P.check_ids) {  // PairedEndRenamer: the ids of the two mates must be identical
+                if (mt == 0) {
+                    id0_len = id_len;
+                    id0_v0 = idv0;
+                    id0_v1 = idv1;
+                } else {
+                    id_mismatch |= id0_len != id_len || id0_v0 != idv0 || id0_v1 != idv1;
+                    const uint8_t* __restrict__ n0 = P.md[0].name + recs[0][slot].nm;
+                    for (uint32_t x = 64 + lane; x < id_len; x += 32) id_mismatch |= n0[x] != nm[x];
+                }
+            }
+            // ---- stores ----
+            if (misc_pos != 0xFFFFFFFFu) out[misc_pos] = (uint8_t)misc_val;
+            if ((uint32_t)lane < id_len) out[1 + lane] = (uint8_t)idv0;
+            if ((uint32_t)lane + 32u < id_len) out[33 + lane] = (uint8_t)idv1;
+            if ((uint32_t)lane < lab) out[e_name + 1 + lane] = (uint8_t)umiv;
+            if (k1 < nw_s) o_s[k1] = __funnelshift_r(a0, a1, sh_s);
+            if (k2 < nw_s) o_s[k2] = __funnelshift_r(b0, b1, sh_s);
+            if (k1 < nw_q) o_q[k1] = __funnelshift_r(c0, c1, sh_q);
+            if (k2 < nw_q) o_q[k2] = __funnelshift_r(d0, d1, sh_q);
+            // rare tails: ids > 64 bytes, UMI parts > 32 bytes, reads > 256 bases
+            for (uint32_t x = 64 + lane; x < id_len; x += 32) out[1 + x] = nm[x];
+            for (uint32_t x = 32 + lane; x < lab; x += 32) out[e_name + 1 + x] = x < la ? pa[x] : pb[x - la];
+            for (uint32_t k = 64 + lane; k < max(nw_s, nw_q); k += 32) {
+                if (k < nw_s) o_s[k] = __funnelshift_r(al_s[k], al_s[k + 1], sh_s);
+                if (k < nw_q) o_q[k] = __funnelshift_r(al_q[k], al_q[k + 1], sh_q);
             }
         }
     }
+    if (__any_sync(0xffffffffu, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
 }
 
 // Integer-issue microbenchmark: 8 independent dependency chains per thread.
@@ -698,7 +837,7 @@ __global__ void __launch_bounds__(256) k_int_peak(int iters, unsigned int* sink)
 
 template <int M>
 cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t stream) {
-    const dim3 grid((n_items + 127) / 128), block(128);
+    const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
     if constexpr (M == 100) {  // the poly-A / poly-T adapters of run.py:389-404
         if (p.homopolymer) {
             k_align<M, true><<<grid, block, 0, stream>>>(p);
@@ -725,7 +864,7 @@ cudaError_t csq_launch_align(const AlignParams& p, uint32_t n_items, cudaStream_
         CSQ_CASE(33) CSQ_CASE(34) CSQ_CASE(100)
 #undef CSQ_CASE
         default: {
-            const dim3 grid((n_items + 127) / 128), block(128);
+            const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
             k_align<0, false><<<grid, block, 0, stream>>>(p);
             return cudaGetLastError();
         }

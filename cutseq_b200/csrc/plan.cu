@@ -75,7 +75,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
     DevBuf seq[2], qual[2], seq_off[2], seq_len[2], name[2], name_off[2], state[2], matches[2];
-    DevBuf dest, rec_len, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
+    DevBuf dest, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
     DevBuf list, list_count;  // prefilter survivors (indices) and their number
     unsigned long long* totals_host = nullptr;  // pinned: 12 totals + error flag
     uint32_t n = 0;
@@ -325,14 +325,13 @@ int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
     }
     int rc;
     if ((rc = s.dest.ensure((size_t)n + 16))) return rc;
-    if ((rc = s.rec_len.ensure((size_t)n * 8 + 16))) return rc;
     if ((rc = s.block_tot.ensure((size_t)nblk * 32 + 32))) return rc;
     if ((rc = s.block_cnt.ensure((size_t)nblk * 16 + 16))) return rc;
     if ((rc = s.block_off.ensure((size_t)nblk * 64 + 64))) return rc;
     if ((rc = s.totals.ensure(16 * 8))) return rc;
     if (!(plan->flags & CSQ_PLAN_NO_PREFILTER)) {
-        if ((rc = s.list.ensure((size_t)n * 4 + 16))) return rc;
-        if ((rc = s.list_count.ensure(16))) return rc;
+        if ((rc = s.list.ensure((size_t)n * CSQ_PF_BINS * 6 + 64))) return rc;
+        if ((rc = s.list_count.ensure(4 * CSQ_PF_BINS + 16))) return rc;
     }
     return 0;
 }
@@ -366,7 +365,6 @@ PairParams pair_params(csq_plan* plan, Slot& s) {
     pp.check_ids = (plan->n_mates == 2 && plan->prog[0].has_rename) ? 1 : 0;
     pp.revcomp = plan->prog[0].revcomp ? 1 : 0;
     pp.dest = (uint8_t*)s.dest.p;
-    pp.rec_len = (uint32_t*)s.rec_len.p;
     pp.block_tot = (uint32_t*)s.block_tot.p;
     pp.block_cnt = (uint32_t*)s.block_cnt.p;
     pp.counters = plan->counters;
@@ -394,7 +392,7 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
                              : nullptr;
             if (!(plan->flags & CSQ_PLAN_NO_PREFILTER) && n) {
                 // reject-only bit-parallel filter; the exact DP then runs on the compacted survivors
-                CUDA_TRY(cudaMemsetAsync(s.list_count.p, 0, 4, st));
+                CUDA_TRY(cudaMemsetAsync(s.list_count.p, 0, 4 * CSQ_PF_BINS, st));
                 CUDA_TRY(csq_launch_prefilter(ap, (uint32_t*)s.list.p, (uint32_t*)s.list_count.p, st));
                 plan->launches += 1;
                 if (kt) kt->mark(sg.pf_name);
@@ -452,8 +450,8 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     return 0;
 }
 
-int check_device_error(Slot& s) {
-    int flag = *(int*)(s.totals_host + 12);
+int check_device_error(Slot& s, int word = 12) {
+    int flag = *(int*)(s.totals_host + word);
     if (flag == CSQ_ERR_PAIRING) return fail(CSQ_ERR_PAIRING, "Input read IDs not identical in a pair");
     if (flag) return fail(flag, "device reported error %d", flag);
     return 0;
@@ -550,7 +548,7 @@ void csq_plan_destroy(csq_plan* plan) {
             for (int d = 0; d < CSQ_N_DEST; d++) s.out[d][m].release();
         }
         s.list.release(); s.list_count.release();
-        s.dest.release(); s.rec_len.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
+        s.dest.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
         for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.totals_host) cudaFreeHost(s.totals_host);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -612,8 +610,11 @@ int csq_wait(csq_plan* plan, int slot) {
             csq_text_out& t = out->text[d][m];
             if (t.bytes) CUDA_TRY(cudaMemcpyAsync(t.data, s.out[d][m].p, t.bytes, cudaMemcpyDeviceToHost, s.stream));
         }
+    // k_emit compares the mate ids (PairedEndRenamer) while it copies them: fetch the flag again
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 13, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev[5], s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if ((rc = check_device_error(s, 13))) return rc;
     float h2d = 0, front = 0, emit = 0, d2h = 0;
     cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]);
     cudaEventElapsedTime(&front, s.ev[1], s.ev[2]);
@@ -653,7 +654,9 @@ int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
     if ((rc = check_device_error(s))) return rc;
     if ((rc = size_outputs(s))) return rc;
     if ((rc = enqueue_emit(plan, s, nullptr, s.stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 13, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if ((rc = check_device_error(s, 13))) return rc;
     if (iters == 1) {  // the sizing pass already did the work once
         if (ms_per_iter) *ms_per_iter = 0.f;
         return 0;
@@ -697,6 +700,9 @@ int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, floa
         if ((rc = check_device_error(s))) return rc;
         if ((rc = size_outputs(s))) return rc;
         if ((rc = enqueue_emit(plan, s, nullptr, st))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s.totals_host + 13, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = check_device_error(s, 13))) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     KernelTimer kt;

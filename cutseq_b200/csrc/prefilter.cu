@@ -21,7 +21,40 @@
 
 namespace {
 
-template <int NW>
+// Survivors go to one of CSQ_PF_BINS lists (bin = class of the number of DP columns the exact pass will walk, so
+// that the 32 reads of a k_align warp have similar trip counts); list b occupies list[b * n .. b * n + count[b]).
+__device__ __forceinline__ void append_survivor(const AlignParams& P, uint32_t* __restrict__ list, uint32_t* __restrict__ list_count,
+                                                bool pass, uint32_t idx, int bin, uint32_t j0, int lane) {
+    uint16_t* __restrict__ list_j0 = reinterpret_cast<uint16_t*>(list + (size_t)CSQ_PF_BINS * P.n);
+#pragma unroll
+    for (int b = 0; b < CSQ_PF_BINS; b++) {
+        const unsigned int ballot = __ballot_sync(0xffffffffu, pass && bin == b);
+        if (!ballot) continue;
+        const int leader = __ffs(ballot) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(list_count + b, (unsigned int)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass && bin == b) {
+            const size_t pos = (size_t)b * P.n + base + __popc(ballot & ((1u << lane) - 1u));
+            list[pos] = idx;
+            list_j0[pos] = (uint16_t)j0;
+        }
+    }
+}
+
+// The read characters are fetched with aligned 128-bit loads (16 columns per load; the few characters in
+// front of the first 16-byte boundary bytewise): one thread walks 150 columns with ~10 load instructions
+// instead of 150 single-byte ones, which is what bounded the first version (L1 request rate).
+//
+// Template switches, all of them about instruction count per column (the kernel is issue bound):
+//   REV    the reversed walk of RightmostFrontAdapter
+//   SIR    adapter start is free (REFERENCE_START): row m can be acceptable in the first columns with a short
+//          aligned length, so the per-column test is the full one.  Without it cost[m][j] >= m - j, and the
+//          test is relaxed to  min_j cost[m][j] <= thr[m]  (thr is monotone, so this is still necessary for
+//          acceptance) - one VIMNMX per column instead of a compare-and-branch.
+//   SMALL  m <= 21: cost[m][j] is tracked scaled by 2^(m-1), i.e. the row-m bits of the horizontal delta
+//          vectors are added / subtracted where they stand (cost <= m + n < 1024 still fits 32 bits).
+template <int NW, bool REV, bool SIR, bool SMALL>
 __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ AlignParams P, uint32_t* __restrict__ list,
                                                    uint32_t* __restrict__ list_count) {
     __shared__ uint32_t lut[256 * NW];
@@ -36,6 +69,8 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
     const bool valid = idx < P.n;
     bool pass = false;
     unsigned int cells = 0;
+    int bin = 0;
+    uint32_t j0 = 0xFFFFu;  // first DP column of the exact pass; 0xFFFF: the aligner's own min_n
     if (valid) {
         ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
         for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
@@ -43,7 +78,7 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
 
         const int m = P.m, k = P.k;
         const int a = st.a, b = st.b, n = b - a;
-        const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
+        const bool siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
         int max_n = n, min_n = 0;
         if (!siq) max_n = min(n, m + k);
         if (!eiq) min_n = max(0, n - m - k);
@@ -53,40 +88,123 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
         uint32_t Pv[NW], Mv[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            Pv[w] = sir ? 0u : 0xFFFFFFFFu;
+            Pv[w] = SIR ? 0u : 0xFFFFFFFFu;
             Mv[w] = 0u;
         }
-        int score = sir ? 0 : m;             // cost[m][min_n]   (min_n == 0 whenever sir, see csq_adapter_kind)
-        const int hin0 = siq ? 0 : 1;        // row 0: cost stays 0 (free read prefix) or grows by 1 per column
         const int top = (m - 1) & 31;
-        const uint8_t* s = P.md.seq + P.md.seq_off[idx];
-        const int step = P.reversed ? -1 : 1;
-        const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
-        for (int j = min_n + 1; j <= max_n; j++, p += step) {
-            const uint32_t c = *p;
-            int hin = hin0;
+        const uint32_t topmask = 1u << top;
+        const int unit = SMALL ? (int)topmask : 1;  // one error in the units of `score`
+        int score = SIR ? 0 : m * unit;             // cost[m][min_n]   (min_n == 0 whenever SIR, see csq_adapter_kind)
+        int smin = 0x7FFFFFFF;                      // !SIR: minimum of cost[m][j] over the columns
+        const uint32_t hpos0 = siq ? 0u : 1u;       // row 0: cost stays 0 (free read prefix) or grows by 1 per column
+        const int min_overlap = P.min_overlap;
+        const int kk = k * unit;
+        int j = min_n;
+        // Column window for the exact pass (BACK flags only, see k_align): fc = number of columns done before the
+        // chunk in which cost[m][j] first dropped to thr[m] (no row-m cell can be acceptable before that)
+        const bool window = !SIR && P.flags == 14;
+        const int T = (int)P.thr[m] * unit;
+        int fc = -1, jc = min_n;
+        auto mark = [&](int cols) {
+            if (window && fc < 0 && smin <= T) fc = jc;
+            jc += cols;
+        };
+        auto column = [&](uint32_t c) {
+            uint32_t hpos = hpos0, hneg = 0u;
 #pragma unroll
             for (int w = 0; w < NW; w++) {
                 uint32_t Eq = lut[c * NW + w];
-                const uint32_t hneg = hin < 0 ? 1u : 0u, hpos = hin > 0 ? 1u : 0u;
                 const uint32_t Xv = Eq | Mv[w];
-                Eq |= hneg;
+                if (w > 0) Eq |= hneg;
                 const uint32_t Xh = (((Eq & Pv[w]) + Pv[w]) ^ Pv[w]) | Eq;
                 uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
                 uint32_t Mh = Pv[w] & Xh;
-                const int bit = (w == NW - 1) ? top : 31;
-                hin = (int)((Ph >> bit) & 1u) - (int)((Mh >> bit) & 1u);  // horizontal delta leaving this word
+                if (w == NW - 1) {  // horizontal delta of row m
+                    if (SMALL) {
+                        score += (int)(Ph & topmask) - (int)(Mh & topmask);
+                    } else {
+                        score += (int)((Ph >> top) & 1u) - (int)((Mh >> top) & 1u);
+                    }
+                }
+                const uint32_t cp = Ph >> 31, cn = Mh >> 31;  // horizontal delta leaving this word
                 Ph = (Ph << 1) | hpos;
                 Mh = (Mh << 1) | hneg;
+                hpos = cp;
+                hneg = cn;
                 Pv[w] = Mh | ~(Xv | Ph);
                 Mv[w] = Ph & Xv;
             }
-            score += hin;
-            if (eiq && score <= k) {
-                const int L = min(m, j + score);
-                if (L >= P.min_overlap && score <= (int)P.thr[L]) pass = true;
+            if (SIR) {
+                j++;
+                if (eiq && score <= kk) {
+                    const int sc = SMALL ? (score >> top) : score;
+                    const int L = min(m, j + sc);
+                    if (L >= min_overlap && sc <= (int)P.thr[L]) pass = true;
+                }
+            } else {
+                smin = min(smin, score);
+            }
+        };
+        // characters of columns min_n+1 .. max_n: s[a+min_n .. a+max_n) ascending, or, for the reversed walk
+        // of RightmostFrontAdapter, s[b-max_n .. b-min_n) descending
+        const uint8_t* s = P.md.seq + P.md.seq_off[idx];
+        int rem = max_n - min_n;
+        if (!REV) {
+            const uint8_t* p = s + a + min_n;
+            int head = min(rem, (int)((16u - (uint32_t)(uintptr_t)p) & 15u));
+            rem -= head;
+            const int head0 = head;
+            for (; head > 0; head--) column(*p++);
+            mark(head0);
+            // software pipelined: the next 16 characters are in flight while these 16 columns are computed
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (rem > 0) v = *reinterpret_cast<const uint4*>(p);  // the pools carry 16 bytes of slack
+            for (; rem >= 16; rem -= 16) {
+                p += 16;
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                if (rem > 16) v = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+                for (int i = 0; i < 16; i++) column((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                mark(16);
+            }
+            if (rem > 0) {
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 15; i++) {
+                    if (i >= rem) break;
+                    column((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                }
+                mark(rem);
+            }
+        } else {
+            const uint8_t* p = s + b - min_n;  // one past the next character
+            int head = min(rem, (int)((uint32_t)(uintptr_t)p & 15u));
+            rem -= head;
+            const int head0 = head;
+            for (; head > 0; head--) column(*--p);
+            mark(head0);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (rem > 0) v = *reinterpret_cast<const uint4*>(p - 16);  // may start below the read, never below the pool
+            for (; rem >= 16; rem -= 16) {
+                p -= 16;
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                if (rem > 16) v = *reinterpret_cast<const uint4*>(p - 16);
+#pragma unroll
+                for (int i = 15; i >= 0; i--) column((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                mark(16);
+            }
+            if (rem > 0) {
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 15; i > 0; i--) {
+                    if (15 - i >= rem) break;
+                    column((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+                }
+                mark(rem);
             }
         }
+        mark(0);
+        if (!SIR && eiq && max_n > min_n && smin <= T) pass = true;
         if (!pass && max_n == n) {
             const int first_i = eir ? 0 : m;
             int d = siq ? 0 : max_n;  // cost[0][max_n]
@@ -103,7 +221,7 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
                 d += (int)((pv >> bt) & 1u) - (int)((mv >> bt) & 1u);
                 if (i >= first_i && d <= k) {
                     const int L = min(i, span + d);
-                    if (L >= P.min_overlap && d <= (int)P.thr[L]) pass = true;
+                    if (L >= min_overlap && d <= (int)P.thr[L]) pass = true;
                 }
             }
         }
@@ -112,18 +230,43 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
             r.found = r.ref_start = r.ref_stop = r.query_start = r.query_stop = r.score = r.errors = r.reserved = 0;
             P.matches[idx] = r;
         }
+        if (pass && window) {
+            // every cell Aligner.locate can accept lies in a column >= min(fc + 1, n); its value depends only on
+            // columns >= that - (m + 3k + 2)  (k_align, "column window")
+            const int jn = fc >= 0 ? fc : n;
+            const int w0 = max(min_n, jn - (m + 3 * k + 3));
+            j0 = (uint32_t)w0;
+            const int cols = max_n - w0;
+            bin = cols > 112 ? 0 : cols > 80 ? 1 : cols > 48 ? 2 : 3;  // longest first
+        }
     }
     // nominal DP cells of the launch (GCUPS numerator) and warp-aggregated append of the survivors
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
     const int lane = threadIdx.x & 31;
     if (lane == 0 && cells) atomicAdd(P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS), (unsigned long long)cells);
-    const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
-    if (ballot) {
-        const int leader = __ffs(ballot) - 1;
-        unsigned int base = 0;
-        if (lane == leader) base = atomicAdd(list_count, (unsigned int)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (pass) list[base + __popc(ballot & ((1u << lane) - 1u))] = idx;
+    append_survivor(P, list, list_count, pass, idx, bin, j0, lane);
+}
+
+template <int NW, bool REV, bool SIR>
+void launch_pf(const AlignParams& p, uint32_t* list, uint32_t* list_count, dim3 grid, dim3 block, cudaStream_t stream) {
+    if constexpr (NW == 1) {
+        if (p.m <= 21) {
+            k_prefilter<NW, REV, SIR, true><<<grid, block, 0, stream>>>(p, list, list_count);
+            return;
+        }
+    }
+    k_prefilter<NW, REV, SIR, false><<<grid, block, 0, stream>>>(p, list, list_count);
+}
+
+template <int NW>
+void launch_pf_nw(const AlignParams& p, uint32_t* list, uint32_t* list_count, dim3 grid, dim3 block, cudaStream_t stream) {
+    const bool sir = (p.flags & 1) != 0;
+    if (p.reversed) {
+        if (sir) launch_pf<NW, true, true>(p, list, list_count, grid, block, stream);
+        else launch_pf<NW, true, false>(p, list, list_count, grid, block, stream);
+    } else {
+        if (sir) launch_pf<NW, false, true>(p, list, list_count, grid, block, stream);
+        else launch_pf<NW, false, false>(p, list, list_count, grid, block, stream);
     }
 }
 
@@ -171,14 +314,7 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
     const int lane = threadIdx.x & 31;
     if (lane == 0 && cells) atomicAdd(P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS), (unsigned long long)cells);
-    const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
-    if (ballot) {
-        const int leader = __ffs(ballot) - 1;
-        unsigned int base = 0;
-        if (lane == leader) base = atomicAdd(list_count, (unsigned int)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (pass) list[base + __popc(ballot & ((1u << lane) - 1u))] = idx;
-    }
+    append_survivor(P, list, list_count, pass, idx, 0, 0xFFFFu, lane);
 }
 
 }  // namespace
@@ -190,12 +326,11 @@ cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t*
         k_prefilter_homo<<<grid, block, 0, stream>>>(p, list, list_count);
         return cudaGetLastError();
     }
-    const int nw = (p.m + 31) / 32;
-    switch (nw) {
-        case 1: k_prefilter<1><<<grid, block, 0, stream>>>(p, list, list_count); break;
-        case 2: k_prefilter<2><<<grid, block, 0, stream>>>(p, list, list_count); break;
-        case 3: k_prefilter<3><<<grid, block, 0, stream>>>(p, list, list_count); break;
-        default: k_prefilter<4><<<grid, block, 0, stream>>>(p, list, list_count); break;
+    switch ((p.m + 31) / 32) {
+        case 1: launch_pf_nw<1>(p, list, list_count, grid, block, stream); break;
+        case 2: launch_pf_nw<2>(p, list, list_count, grid, block, stream); break;
+        case 3: launch_pf_nw<3>(p, list, list_count, grid, block, stream); break;
+        default: launch_pf_nw<4>(p, list, list_count, grid, block, stream); break;
     }
     return cudaGetLastError();
 }

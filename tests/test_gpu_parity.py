@@ -88,6 +88,51 @@ def test_locate_homopolymer_and_low_complexity(kind):
         check_locate(op, reads)
 
 
+@pytest.mark.parametrize("kind", [A.AD_BACK, A.AD_RIGHTMOST_FRONT])
+def test_locate_column_window_long_reads(kind):
+    """The exact pass starts at a column chosen by the prefilter (BACK flags): long reads with several, partly
+    damaged adapter copies far apart, near the ends and back to back (adapter dimers) must give cutadapt's match."""
+    rng = random.Random(4242 + kind)
+    for m, rate, mo in [(20, 0.2, 3), (20, 0.2, 10), (12, 0.25, 3), (31, 0.2, 5), (33, 0.2, 3), (57, 0.12, 3)]:
+        adapter = "".join(rng.choice("ACGT") for _ in range(m))
+        reads = []
+        for i in range(500):
+            n = rng.choice([120, 151, 250, 300, 450, 600, 800])
+            q = [rng.choice("ACGT") for _ in range(n)]
+            copies = rng.choice([0, 1, 1, 2, 2, 3])
+            anchor = rng.randint(0, n - 1)
+            for c in range(copies):
+                piece = list(adapter)
+                if rng.random() < 0.3:
+                    cut = rng.randint(1, m)
+                    piece = piece[:cut] if rng.random() < 0.5 else piece[m - cut:]
+                for _ in range(rng.choice([0, 0, 1, 2, 3, 4, 6])):
+                    if not piece:
+                        break
+                    pos = rng.randrange(len(piece))
+                    t = rng.random()
+                    if t < 0.5:
+                        piece[pos] = rng.choice("ACGT")
+                    elif t < 0.75:
+                        del piece[pos]
+                    else:
+                        piece.insert(pos, rng.choice("ACGT"))
+                where = rng.random()
+                if where < 0.2:
+                    pos = 0
+                elif where < 0.45:
+                    pos = max(0, n - len(piece) + rng.choice([0, 0, 1, 3]))
+                elif where < 0.7:
+                    pos = min(n - 1, anchor + c * (m + rng.choice([0, 0, 1, 2, 5])))  # dimers / near-by copies
+                else:
+                    pos = rng.randint(0, n - 1)
+                q[pos : pos + len(piece)] = piece
+            s = "".join(q)[:n]
+            reads.append((f"w{i}", s, "I" * len(s)))
+        op = Op(A.OP_ALIGN, adapter_kind=kind, adapter=adapter, min_overlap=mo, max_error_rate=rate)
+        check_locate(op, reads)
+
+
 def test_locate_two_letter_alphabet_ties():
     # low-complexity sequence space maximises cost ties, i.e. exercises the tie-breaking rules
     rng = random.Random(5)
