@@ -88,6 +88,14 @@ class csq_batch_in(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mates", C.c_uint32), ("mate", csq_mate_in * 2)]
 
 
+class csq_text_in(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+class csq_batch_text(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_mates", C.c_uint32), ("first_record", C.c_uint64), ("mate", csq_text_in * 2)]
+
+
 class csq_text_out(C.Structure):
     _fields_ = [("data", C.c_void_p), ("capacity", C.c_uint64), ("bytes", C.c_uint64), ("records", C.c_uint64)]
 

@@ -35,13 +35,29 @@ struct __align__(16) ReadState {
 static_assert(sizeof(ReadState) == 32, "ReadState must stay 32 bytes");
 
 struct MateDev {  // device pointers of one mate of one slot
+    // record i: bases seq[seq_off[i] .. +seq_len[i]), qualities qual[qual_off[i] .. +seq_len[i]),
+    // header name[name_off[i] .. name_end[i]).
+    // SoA batches: qual_off == seq_off and name_end == name_off + 1 (the same arrays);
+    // text batches: seq == qual == name == the FASTQ text, all five arrays written by k_records (parse.cu).
     const uint8_t* seq;
     const uint8_t* qual;
     const uint32_t* seq_off;
+    const uint32_t* qual_off;
     const uint32_t* seq_len;
     const uint8_t* name;
     const uint32_t* name_off;
+    const uint32_t* name_end;
     ReadState* state;
+};
+
+struct ParseParams {  // FASTQ text of one mate -> record index (parse.cu)
+    const uint8_t* text;
+    uint64_t bytes;
+    uint32_t n;             // records the host counted (4 n line ends)
+    uint32_t* nl;           // [4 n] byte offsets of the line ends, 16-byte aligned
+    uint32_t* nl_total;     // [1] line ends found
+    uint32_t *seq_off, *qual_off, *seq_len, *name_off, *name_end;
+    unsigned long long* perr;  // smallest (record << 3 | kind) of a malformed record, ~0 when clean
 };
 
 struct AlignParams {
@@ -117,6 +133,8 @@ cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream);
 cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
                             unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream);
 cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream);
+cudaError_t csq_launch_parse(const ParseParams& p, uint32_t* tile_cnt, cudaStream_t stream);
+uint32_t csq_parse_tiles(uint64_t bytes);
 cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t* list_count, cudaStream_t stream);
 bool csq_align_has_exact_kernel(int m);
 cudaError_t csq_launch_int_peak(int variant, int iters, unsigned int* sink, int blocks, int threads, cudaStream_t stream);

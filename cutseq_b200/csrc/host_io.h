@@ -52,6 +52,35 @@ struct MateParser {
     int next(uint32_t max_reads, MateSoA& out);
 };
 
+// ---- text batches (text_reader.cpp) ----
+uint64_t count_newlines(const uint8_t* p, size_t n);
+uint64_t after_kth_newline(const uint8_t* p, size_t n, uint64_t k);  // offset one past the k-th '\n', UINT64_MAX if fewer
+
+struct RawSource {  // decompressed byte stream of a plain or gzip (multi-member) file, read into caller memory
+    int fd = -1;
+    bool gz = false, file_eof = false, stream_end = false;
+    void* zs = nullptr;
+    std::vector<uint8_t> inbuf;
+    size_t in_pos = 0, in_len = 0;
+    std::string name;
+    ~RawSource();
+    int open(const char* path);
+    long read(uint8_t* dst, size_t n);
+    long fill();
+    void close();
+};
+
+struct MateTextReader {  // cuts the byte stream of one mate into batches of whole records
+    RawSource src;
+    std::vector<uint8_t> carry;  // bytes behind the last cut
+    size_t carry_pos = 0;
+    bool eof = false;
+    uint64_t records_done = 0;
+    size_t hint_bytes = 0;       // size of the previous batch: the next buffer is reserved in one go
+    int open(const char* path);
+    int next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads);
+};
+
 int parse_records(const uint8_t* text, size_t n_bytes, bool at_eof, uint32_t max_reads, MateSoA& out, size_t* consumed,
                   uint64_t* line_no, const char* fname);
 

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishPa
         ReadState st = P.first ? fresh_state(len0) : load_state(P.md.state + idx);
         for (int q = 0; q < P.n_post; q++) apply_scalar(P.post[q], st);
         if (P.has_qtrim) {
-            const uint8_t* ql = P.md.qual + P.md.seq_off[idx];
+            const uint8_t* ql = P.md.qual + P.md.qual_off[idx];
             const int a = st.a, n = (int)st.b - (int)st.a;
             int start = 0, stop = n, s = 0, mx = 0;
             for (int i = 0; i < n; i++) {
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishPa
         }
         // header: SuffixRemover ops in order, then the id of Renamer.parse_name
         const uint8_t* nm = P.md.name + P.md.name_off[idx];
-        int nl = (int)(P.md.name_off[idx + 1] - P.md.name_off[idx]);
+        int nl = (int)(P.md.name_end[idx] - P.md.name_off[idx]);
         for (int q = 0; q < P.n_suffix; q++) {
             const int sl = P.suffix_len[q];
             if (nl >= sl) {
@@ -669,7 +669,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
             EmitRec R;
             R.nm = md.name_off[idx] + own.id_start;
             R.sq = md.seq_off[idx];
-            R.ql = md.seq_off[idx];
+            R.ql = md.qual_off[idx];
             R.pa = R.pb = 0;
             if (P.rename_parts & CSQ_REN_OWN_PREFIX) R.pa = R.sq + (own.ren_cp >> 16);
             if (P.rename_parts & CSQ_REN_OWN_SUFFIX) R.pb = R.sq + (own.ren_cs >> 16);

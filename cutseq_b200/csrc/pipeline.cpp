@@ -1,5 +1,6 @@
-// Whole-file driver (csq_run_files): reader thread -> per-GPU worker threads (two slots each,
-// double-buffered csq_submit / csq_wait) -> ordered writer thread (parallel gzip members).
+// Whole-file driver (csq_run_files): reader thread (raw FASTQ bytes, cut at record boundaries;
+// the device parses them) -> per-GPU worker threads (two slots each, double-buffered
+// csq_submit_text / csq_wait) -> ordered writer thread (parallel gzip members).
 // The B200 analogue of cutadapt's reader / worker / ordered-writer runner behind
 // runner.run(pipeline, Progress(), outfiles) in reference run.py:436-473 / 753-794: batches are
 // contiguous record ranges, they are dealt to the GPUs in order and written back in input order.
@@ -21,8 +22,10 @@
 #include "host_io.h"
 
 void csq_set_error(const char* msg);
-struct csq_reader;
-int csq_reader_next_into(csq_reader* r, csqio::MateSoA* soa, uint32_t max_reads, csq_batch_in* in, double* seconds);
+struct csq_text_reader;
+int csq_text_reader_next_into(csq_text_reader* r, csqio::PinnedBuf* bufs, uint32_t max_reads, csq_batch_text* in);
+extern "C" int csq_text_reader_open(const char* path1, const char* path2, csq_text_reader** out);
+extern "C" void csq_text_reader_close(csq_text_reader* r);
 
 namespace {
 
@@ -65,8 +68,8 @@ class Queue {
 
 struct Job {
     long index = -1;
-    csqio::MateSoA soa[2];
-    csq_batch_in in;
+    csqio::PinnedBuf text[2];
+    csq_batch_text in;
     csqio::PinnedBuf outbuf[CSQ_N_DEST][2];
     csq_batch_out out;
     int slot = 0;
@@ -100,7 +103,7 @@ bool size_job_outputs(Job& j, bool first_try) {
     const int n_mates = (int)j.in.n_mates;
     for (int m = 0; m < 2; m++) {
         uint64_t full = 64;
-        if (m < n_mates) full = j.in.mate[m].name_bytes + 2 * j.in.mate[m].seq_bytes + 80ull * j.in.n_reads + 4096;
+        if (m < n_mates) full = j.in.mate[m].bytes + 64ull * j.in.n_reads + 4096;  // renaming can only shorten a record, bar "_" + UMI
         for (int d = 0; d < CSQ_N_DEST; d++) {
             uint64_t want = first_try ? (d == CSQ_DEST_TRIMMED ? full : full / 8 + 4096) : j.out.text[d][m].bytes + 4096;
             if (m >= n_mates) want = 64;
@@ -144,8 +147,8 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             return rc;
         }
     }
-    csq_reader* reader = nullptr;
-    int rc = csq_reader_open(files->in[0], files->in[1], &reader);
+    csq_text_reader* reader = nullptr;
+    int rc = csq_text_reader_open(files->in[0], files->in[1], &reader);
     if (rc) {
         destroy_plans();
         return rc;
@@ -158,7 +161,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                 if (rc) csq_set_error(csqio::io_error());
             }
     if (rc) {
-        csq_reader_close(reader);
+        csq_text_reader_close(reader);
         destroy_plans();
         return rc;
     }
@@ -181,7 +184,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         Job* j = nullptr;
         while (!sh.stop && free_q.pop(j)) {
             const auto t0 = Clock::now();
-            int r = csq_reader_next_into(reader, j->soa, batch_reads, &j->in, nullptr);
+            int r = csq_text_reader_next_into(reader, j->text, batch_reads, &j->in);
             t_read += seconds_since(t0);
             if (r) {
                 sh.fail(r, csq_last_error());
@@ -234,7 +237,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                 }
                 j->slot = next_slot;
                 next_slot ^= 1;
-                int r = csq_submit(plan, j->slot, &j->in, &j->out);
+                int r = csq_submit_text(plan, j->slot, &j->in, &j->out);
                 if (r) {
                     sh.fail(r, csq_last_error());
                     break;
@@ -346,7 +349,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         timing->write_deflate = t_write;
         timing->total = seconds_since(t_start);
     }
-    csq_reader_close(reader);
+    csq_text_reader_close(reader);
     destroy_plans();
     if (sh.err_code) {
         csq_set_error(sh.err_msg.c_str());

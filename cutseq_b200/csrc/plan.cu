@@ -77,7 +77,12 @@ struct Slot {
     DevBuf seq[2], qual[2], seq_off[2], seq_len[2], name[2], name_off[2], state[2], matches[2];
     DevBuf dest, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
     DevBuf list, list_count;  // prefilter survivors (indices) and their number
-    unsigned long long* totals_host = nullptr;  // pinned: 12 totals + error flag
+    // text batches (csq_submit_text): the FASTQ bytes as they came, and the record index k_records builds
+    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16
+    uint64_t text_bytes[2] = {0, 0};
+    uint64_t first_record = 0;
+    bool text_mode = false;
+    unsigned long long* totals_host = nullptr;  // pinned: 12 totals + 2 error flags + 2 parse-error keys
     uint32_t n = 0;
     int n_mates = 0;
     csq_batch_out* pending = nullptr;
@@ -269,15 +274,25 @@ int check_device(int device) {
     return 0;
 }
 
+constexpr size_t TEXT_FRONT_PAD = 64;  // readable bytes in front of the text (reversed 128-bit walks start below a read)
+
 MateDev mate_dev(Slot& s, int m) {
     MateDev d;
-    d.seq = (const uint8_t*)s.seq[m].p;
-    d.qual = (const uint8_t*)s.qual[m].p;
     d.seq_off = (const uint32_t*)s.seq_off[m].p;
     d.seq_len = (const uint32_t*)s.seq_len[m].p;
-    d.name = (const uint8_t*)s.name[m].p;
     d.name_off = (const uint32_t*)s.name_off[m].p;
     d.state = (ReadState*)s.state[m].p;
+    if (s.text_mode) {
+        d.seq = d.qual = d.name = (const uint8_t*)s.text[m].p + TEXT_FRONT_PAD;
+        d.qual_off = (const uint32_t*)s.qual_off[m].p;
+        d.name_end = (const uint32_t*)s.name_end[m].p;
+    } else {
+        d.seq = (const uint8_t*)s.seq[m].p;
+        d.qual = (const uint8_t*)s.qual[m].p;
+        d.name = (const uint8_t*)s.name[m].p;
+        d.qual_off = d.seq_off;
+        d.name_end = d.name_off + 1;
+    }
     return d;
 }
 
@@ -296,12 +311,61 @@ int validate_batch(const csq_plan* plan, const csq_batch_in* in) {
     return 0;
 }
 
+int ensure_common(csq_plan* plan, Slot& s, uint32_t n) {
+    const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
+    int rc;
+    if ((rc = s.dest.ensure((size_t)n + 16))) return rc;
+    if ((rc = s.block_tot.ensure((size_t)nblk * 32 + 32))) return rc;
+    if ((rc = s.block_cnt.ensure((size_t)nblk * 16 + 16))) return rc;
+    if ((rc = s.block_off.ensure((size_t)nblk * 64 + 64))) return rc;
+    if ((rc = s.totals.ensure(16 * 8))) return rc;
+    if (!(plan->flags & CSQ_PLAN_NO_PREFILTER)) {
+        if ((rc = s.list.ensure((size_t)n * CSQ_PF_BINS * 6 + 64))) return rc;
+        if ((rc = s.list_count.ensure(4 * CSQ_PF_BINS + 16))) return rc;
+    }
+    return 0;
+}
+
+// FASTQ text of a batch -> device, as it is; the record index is built by the parse kernels in enqueue_front
+int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
+    const uint32_t n = in->n_reads;
+    s.n = n;
+    s.n_mates = plan->n_mates;
+    s.front_done = false;
+    s.text_mode = true;
+    s.first_record = in->first_record;
+    int rc;
+    for (int m = 0; m < plan->n_mates; m++) {
+        const uint64_t bytes = in->mate[m].bytes;
+        s.text_bytes[m] = bytes;
+        const size_t padded = (size_t)((bytes + 63) & ~(uint64_t)63);
+        if ((rc = s.text[m].ensure(TEXT_FRONT_PAD + padded + 128))) return rc;
+        if ((rc = s.seq_off[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.qual_off[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.name_off[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.name_end[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
+        if ((rc = s.tiles[m].ensure(((size_t)csq_parse_tiles(bytes) + 4) * 4))) return rc;
+        if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
+        if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
+            if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
+        uint8_t* base = (uint8_t*)s.text[m].p;
+        CUDA_TRY(cudaMemsetAsync(base, 0, TEXT_FRONT_PAD, s.stream));
+        // zero padding behind the text: never a line end, and readable by the 128-bit walks
+        CUDA_TRY(cudaMemsetAsync(base + TEXT_FRONT_PAD + (bytes & ~(uint64_t)63), 0, padded - (bytes & ~(uint64_t)63) + 128, s.stream));
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(base + TEXT_FRONT_PAD, in->mate[m].text, bytes, cudaMemcpyHostToDevice, s.stream));
+    }
+    if ((rc = s.parse_misc.ensure(64))) return rc;
+    return ensure_common(plan, s, n);
+}
+
 int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
     const uint32_t n = in->n_reads;
     s.n = n;
     s.n_mates = plan->n_mates;
     s.front_done = false;
-    const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
+    s.text_mode = false;
     for (int m = 0; m < plan->n_mates; m++) {
         const csq_mate_in& mi = in->mate[m];
         int rc;
@@ -323,17 +387,7 @@ int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
             CUDA_TRY(cudaMemcpyAsync(s.name_off[m].p, mi.name_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
         }
     }
-    int rc;
-    if ((rc = s.dest.ensure((size_t)n + 16))) return rc;
-    if ((rc = s.block_tot.ensure((size_t)nblk * 32 + 32))) return rc;
-    if ((rc = s.block_cnt.ensure((size_t)nblk * 16 + 16))) return rc;
-    if ((rc = s.block_off.ensure((size_t)nblk * 64 + 64))) return rc;
-    if ((rc = s.totals.ensure(16 * 8))) return rc;
-    if (!(plan->flags & CSQ_PLAN_NO_PREFILTER)) {
-        if ((rc = s.list.ensure((size_t)n * CSQ_PF_BINS * 6 + 64))) return rc;
-        if ((rc = s.list_count.ensure(4 * CSQ_PF_BINS + 16))) return rc;
-    }
-    return 0;
+    return ensure_common(plan, s, n);
 }
 
 struct KernelTimer {  // optional per-kernel CUDA-event timing (resident mode, last iteration)
@@ -377,6 +431,28 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     const uint32_t n = s.n;
     const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
     if (kt) kt->mark("begin");
+    if (s.text_mode) {
+        // FASTQ text -> record index (parse.cu); nl_total[m] at parse_misc + 4 m, perr[m] at parse_misc + 16 + 8 m
+        CUDA_TRY(cudaMemsetAsync((uint8_t*)s.parse_misc.p + 16, 0xFF, 16, st));
+        for (int m = 0; m < plan->n_mates; m++) {
+            ParseParams pp;
+            pp.text = (const uint8_t*)s.text[m].p + TEXT_FRONT_PAD;
+            pp.bytes = s.text_bytes[m];
+            pp.n = n;
+            pp.nl = (uint32_t*)s.nl[m].p;
+            pp.nl_total = (uint32_t*)s.parse_misc.p + m;
+            pp.seq_off = (uint32_t*)s.seq_off[m].p;
+            pp.qual_off = (uint32_t*)s.qual_off[m].p;
+            pp.seq_len = (uint32_t*)s.seq_len[m].p;
+            pp.name_off = (uint32_t*)s.name_off[m].p;
+            pp.name_end = (uint32_t*)s.name_end[m].p;
+            pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
+            CUDA_TRY(csq_launch_parse(pp, (uint32_t*)s.tiles[m].p, st));
+            plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
+            if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
+        }
+        CUDA_TRY(cudaMemcpyAsync(s.totals_host + 14, (uint8_t*)s.parse_misc.p + 16, 16, cudaMemcpyDeviceToHost, st));
+    }
     for (int m = 0; m < plan->n_mates; m++) {
         MateProgram& mp = plan->prog[m];
         for (Segment& sg : mp.segs) {
@@ -450,7 +526,29 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     return 0;
 }
 
+// FASTQ format errors found by k_records, worded like dnaio's FastqFormatError
+int check_parse_error(Slot& s) {
+    if (!s.text_mode) return 0;
+    for (int m = 0; m < s.n_mates; m++) {
+        const unsigned long long key = s.totals_host[14 + m];
+        if (key == ~0ULL) continue;
+        const unsigned long long rec = key >> 3, line = 4 * (s.first_record + rec);
+        switch ((int)(key & 7)) {
+            case 1: return fail(CSQ_ERR_FORMAT, "input file %d: line %llu is expected to start with '@'", m + 1, line + 1);
+            case 2: return fail(CSQ_ERR_FORMAT, "input file %d: line %llu is expected to start with '+'", m + 1, line + 3);
+            case 3: return fail(CSQ_ERR_FORMAT, "input file %d: length of sequence and qualities differ (record at line %llu)", m + 1, line + 1);
+            case 4: return fail(CSQ_ERR_LIMIT, "input file %d: read at line %llu exceeds the supported %d bases", m + 1, line + 1, CSQ_MAX_READ_LEN);
+            default: return fail(CSQ_ERR_FORMAT, "input file %d: the batch does not hold %u whole FASTQ records (4 lines each)", m + 1, s.n);
+        }
+    }
+    return 0;
+}
+
 int check_device_error(Slot& s, int word = 12) {
+    if (word == 12) {
+        int rc = check_parse_error(s);
+        if (rc) return rc;
+    }
     int flag = *(int*)(s.totals_host + word);
     if (flag == CSQ_ERR_PAIRING) return fail(CSQ_ERR_PAIRING, "Input read IDs not identical in a pair");
     if (flag) return fail(flag, "device reported error %d", flag);
@@ -547,7 +645,10 @@ void csq_plan_destroy(csq_plan* plan) {
             s.name[m].release(); s.name_off[m].release(); s.state[m].release(); s.matches[m].release();
             for (int d = 0; d < CSQ_N_DEST; d++) s.out[d][m].release();
         }
-        s.list.release(); s.list_count.release();
+        s.list.release(); s.list_count.release(); s.parse_misc.release();
+        for (int m = 0; m < 2; m++) {
+            s.text[m].release(); s.qual_off[m].release(); s.name_end[m].release(); s.nl[m].release(); s.tiles[m].release();
+        }
         s.dest.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
         for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.totals_host) cudaFreeHost(s.totals_host);
@@ -571,6 +672,44 @@ int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* 
     if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
     s.pending = out;
+    return 0;
+}
+
+static int validate_text(const csq_plan* plan, const csq_batch_text* in) {
+    if (!in) return fail(CSQ_ERR_INVALID, "null batch");
+    if ((int)in->n_mates != plan->n_mates) return fail(CSQ_ERR_INVALID, "batch has %u mates, plan has %d", in->n_mates, plan->n_mates);
+    for (int m = 0; m < plan->n_mates; m++) {
+        if (in->mate[m].bytes && !in->mate[m].text) return fail(CSQ_ERR_INVALID, "mate %d: null text", m + 1);
+        if (in->mate[m].bytes >= (1ull << 32) - 4096) return fail(CSQ_ERR_LIMIT, "batch text must stay below 4 GiB");
+    }
+    if ((uint64_t)in->n_reads * 4 >= (1ull << 32)) return fail(CSQ_ERR_LIMIT, "too many records in one batch");
+    return 0;
+}
+
+int csq_submit_text(csq_plan* plan, int slot, const csq_batch_text* in, csq_batch_out* out) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || !out) return fail(CSQ_ERR_INVALID, "bad plan/slot/out");
+    int rc = validate_text(plan, in);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (s.pending) return fail(CSQ_ERR_INVALID, "slot %d still has a batch in flight (call csq_wait)", slot);
+    CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
+    if ((rc = upload_text(plan, s, in))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
+    s.pending = out;
+    return 0;
+}
+
+int csq_upload_text(csq_plan* plan, int slot, const csq_batch_text* in) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS) return fail(CSQ_ERR_INVALID, "bad plan/slot");
+    int rc = validate_text(plan, in);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if ((rc = upload_text(plan, s, in))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
     return 0;
 }
 

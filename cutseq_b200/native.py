@@ -39,6 +39,8 @@ def lib():
     L.csq_plan_destroy.argtypes = [vp]
     L.csq_plan_destroy.restype = None
     L.csq_submit.argtypes = [vp, i32, C.POINTER(A.csq_batch_in), C.POINTER(A.csq_batch_out)]
+    L.csq_submit_text.argtypes = [vp, i32, C.POINTER(A.csq_batch_text), C.POINTER(A.csq_batch_out)]
+    L.csq_upload_text.argtypes = [vp, i32, C.POINTER(A.csq_batch_text)]
     L.csq_wait.argtypes = [vp, i32]
     L.csq_slot_times.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.csq_upload.argtypes = [vp, i32, C.POINTER(A.csq_batch_in)]
@@ -62,6 +64,15 @@ def lib():
         L.csq_reader_close.restype = None
         L.csq_parse_fastq_mem.argtypes = [vp, C.c_uint64, u32, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64, vp,
                                           C.POINTER(u32), u64p, u64p]
+        L.csq_text_reader_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+        L.csq_text_reader_next.argtypes = [vp, i32, u32, C.POINTER(A.csq_batch_text)]
+        L.csq_text_reader_close.argtypes = [vp]
+        L.csq_text_reader_close.restype = None
+        L.csq_count_newlines.argtypes = [vp, C.c_uint64]
+        L.csq_count_newlines.restype = C.c_uint64
+        L.csq_after_kth_newline.argtypes = [vp, C.c_uint64, C.c_uint64]
+        L.csq_after_kth_newline.restype = C.c_uint64
+        L.csq_format_fastq.argtypes = [C.POINTER(A.csq_mate_in), u32, vp, C.c_uint64, u64p]
     if hasattr(L, "csq_synth_batch"):
         L.csq_synth_batch.argtypes = [C.POINTER(A.csq_synth), C.c_uint64, u32, i32, C.POINTER(A.csq_batch_in)]
         L.csq_synth_free.restype = None
@@ -119,6 +130,29 @@ class Plan:
     # ---- batch execution with host buffers (the end-to-end path) ----
     def submit(self, slot: int, batch: A.csq_batch_in, out: A.csq_batch_out):
         check(lib().csq_submit(self._h, slot, C.byref(batch), C.byref(out)))
+
+    def submit_text(self, slot: int, batch: A.csq_batch_text, out: A.csq_batch_out):
+        check(lib().csq_submit_text(self._h, slot, C.byref(batch), C.byref(out)))
+
+    def upload_text(self, slot: int, batch: A.csq_batch_text):
+        check(lib().csq_upload_text(self._h, slot, C.byref(batch)))
+
+    def run_text(self, texts, n_reads: int, capacity: int | None = None, slot: int = 0, first_record: int = 0):
+        """FASTQ text per mate (bytes) through csq_submit_text + csq_wait. -> text[d][m] bytes, records[d][m]"""
+        tb = TextBatch(texts, n_reads, first_record)
+        if capacity is None:
+            capacity = max(len(t) for t in texts) + 64 * n_reads + 4096
+        out = A.csq_batch_out()
+        bufs = [[np.empty(capacity, dtype=np.uint8) for _ in range(2)] for _ in range(A.CSQ_N_DEST)]
+        for d in range(A.CSQ_N_DEST):
+            for m in range(2):
+                out.text[d][m].data = bufs[d][m].ctypes.data
+                out.text[d][m].capacity = capacity
+        self.submit_text(slot, tb.c, out)
+        self.wait(slot)
+        text = [[bufs[d][m][: out.text[d][m].bytes].tobytes() for m in range(2)] for d in range(A.CSQ_N_DEST)]
+        records = [[int(out.text[d][m].records) for m in range(2)] for d in range(A.CSQ_N_DEST)]
+        return text, records
 
     def wait(self, slot: int):
         check(lib().csq_wait(self._h, slot))
@@ -197,6 +231,69 @@ class Plan:
         c = A.csq_counters()
         check(lib().csq_stats(self._h, C.byref(c)))
         return c
+
+
+class TextBatch:
+    """csq_batch_text over Python-owned buffers (bytes / numpy uint8 arrays / torch pinned tensors via .data_ptr())."""
+
+    def __init__(self, texts, n_reads: int, first_record: int = 0):
+        self.keep = []
+        self.c = A.csq_batch_text()
+        self.c.n_reads = n_reads
+        self.c.n_mates = len(texts)
+        self.c.first_record = first_record
+        for m, t in enumerate(texts):
+            if hasattr(t, "data_ptr"):
+                ptr, size = t.data_ptr(), t.numel()
+            else:
+                arr = np.frombuffer(t, dtype=np.uint8) if not isinstance(t, np.ndarray) else t
+                ptr, size = arr.ctypes.data, arr.size
+                t = arr
+            self.keep.append(t)
+            self.c.mate[m].text = ptr
+            self.c.mate[m].bytes = size
+
+
+class TextReader:
+    """csq_text_reader: batches of raw FASTQ text cut at record boundaries (host side of the file driver)."""
+
+    def __init__(self, path1, path2=None):
+        self._h = C.c_void_p()
+        check(lib().csq_text_reader_open(os.fsencode(path1), os.fsencode(path2) if path2 else None, C.byref(self._h)))
+
+    def next(self, max_reads: int, buffer: int = 0):
+        """-> (n_reads, [bytes per mate], first_record); n_reads == 0 at the end of the input."""
+        b = A.csq_batch_text()
+        check(lib().csq_text_reader_next(self._h, buffer, max_reads, C.byref(b)))
+        texts = [C.string_at(b.mate[m].text, b.mate[m].bytes) if b.mate[m].bytes else b"" for m in range(b.n_mates)]
+        return b.n_reads, texts, b.first_record
+
+    def close(self):
+        if self._h:
+            lib().csq_text_reader_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def format_fastq(batch: A.csq_batch_in, mate: int, out=None):
+    """FASTQ text of one mate of a SoA batch (``csq_format_fastq``). -> numpy uint8 array (or fills `out`)."""
+    need = C.c_uint64()
+    mi = batch.mate[mate]
+    lib().csq_format_fastq(C.byref(mi), batch.n_reads, None, 0, C.byref(need)) if batch.n_reads == 0 else None
+    if out is None:
+        # size: names + 2 * bases + 6 per record
+        noff = np.ctypeslib.as_array(C.cast(mi.name_off, C.POINTER(C.c_uint32)), (batch.n_reads + 1,))
+        slen = np.ctypeslib.as_array(C.cast(mi.seq_len, C.POINTER(C.c_uint32)), (max(batch.n_reads, 1),))[: batch.n_reads]
+        size = int(noff[batch.n_reads] - noff[0]) + 2 * int(slen.sum(dtype=np.uint64)) + 6 * batch.n_reads
+        out = np.empty(max(size, 1), dtype=np.uint8)
+    ptr, cap = (out.data_ptr(), out.numel()) if hasattr(out, "data_ptr") else (out.ctypes.data, out.size)
+    check(lib().csq_format_fastq(C.byref(mi), batch.n_reads, ptr, cap, C.byref(need)))
+    return out[: need.value]
 
 
 def locate_batch(op, mate_in: A.csq_mate_in, n_reads: int, device: int = 0, flags: int = 0):

@@ -153,6 +153,24 @@ typedef struct csq_batch_in {
     csq_mate_in mate[2];
 } csq_batch_in;
 
+/* Batch in, text form: the FASTQ bytes of the batch as they stand in the file (after
+ * decompression), whole records only - n_reads records of 4 lines per mate, the last line
+ * ended by '\n'. The device builds the record index itself (dnaio's checks: '@' and '+'
+ * line starts, equal sequence and quality lengths, "\r\n" line ends accepted); a malformed
+ * batch makes csq_wait fail with CSQ_ERR_FORMAT. This is what the whole-file driver uses:
+ * the host only cuts the byte stream at record boundaries (csq_count_newlines). */
+typedef struct csq_text_in {
+    const uint8_t* text;
+    uint64_t bytes;
+} csq_text_in;
+
+typedef struct csq_batch_text {
+    uint32_t n_reads;          /* records per mate in this batch                       */
+    uint32_t n_mates;          /* 1 or 2                                               */
+    uint64_t first_record;     /* index of the batch's first record in the file (error texts) */
+    csq_text_in mate[2];
+} csq_batch_text;
+
 /* Batch out: FASTQ text ("@name\nseq\n+\nqual\n" per record, input order) per
  * destination and mate, written into caller-owned buffers. */
 typedef struct csq_text_out {
@@ -217,6 +235,7 @@ void csq_plan_destroy(csq_plan* plan);
  * text and copies it back into `out`; wait blocks until that is complete. */
 #define CSQ_N_SLOTS 8
 int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* out);
+int csq_submit_text(csq_plan* plan, int slot, const csq_batch_text* in, csq_batch_out* out);
 int csq_wait(csq_plan* plan, int slot);
 /* Device time of the last completed submit on this slot, in ms, by CUDA events on the
  * slot's stream: total (H2D + kernels + D2H) and kernels only. */
@@ -225,6 +244,7 @@ int csq_slot_times(csq_plan* plan, int slot, float* total_ms, float* kernel_ms);
 /* Resident mode (measurement): upload once, run the kernels `iters` times on data that
  * stays in HBM; ms_per_iter is measured with CUDA events on the slot's stream. */
 int csq_upload(csq_plan* plan, int slot, const csq_batch_in* in);
+int csq_upload_text(csq_plan* plan, int slot, const csq_batch_text* in);
 int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter);
 /* The same over several uploaded slots: after an untimed sizing pass per slot, `steps` steps run
  * back to back on one stream, step i on slots[i % n_slots]; total_ms is the CUDA-event time of
@@ -266,6 +286,22 @@ int csq_parse_fastq_mem(const uint8_t* text, uint64_t n_bytes, uint32_t max_read
                         uint8_t* seq, uint8_t* qual, uint64_t seq_cap, uint32_t* seq_off,
                         uint32_t* seq_len, uint8_t* name, uint64_t name_cap, uint32_t* name_off,
                         uint32_t* n_reads, uint64_t* seq_bytes, uint64_t* consumed);
+
+/* Reader for text batches: opens 1 or 2 FASTQ files (plain, or gzip incl. concatenated members,
+ * by magic bytes) and returns max_reads whole records per mate as raw text in library-owned
+ * pinned buffers (valid until the next call with the same buffer index). No parsing happens
+ * on the host: the stream is cut after 4 * max_reads line ends. in->n_reads == 0 at the end. */
+typedef struct csq_text_reader csq_text_reader;
+int csq_text_reader_open(const char* path1, const char* path2, csq_text_reader** out);
+int csq_text_reader_next(csq_text_reader* r, int buffer, uint32_t max_reads, csq_batch_text* in);
+void csq_text_reader_close(csq_text_reader* r);
+/* Text-batch helpers (host, SIMD): number of '\n' in [text, text + n_bytes); and the offset
+ * one past the k-th '\n' (k >= 1), or UINT64_MAX when there are fewer. */
+uint64_t csq_count_newlines(const uint8_t* text, uint64_t n_bytes);
+uint64_t csq_after_kth_newline(const uint8_t* text, uint64_t n_bytes, uint64_t k);
+/* SoA batch -> FASTQ text of one mate ("@name\nseq\n+\nqual\n"), for tests and benchmarks. */
+int csq_format_fastq(const csq_mate_in* mate, uint32_t n_reads, uint8_t* out, uint64_t capacity,
+                     uint64_t* bytes);
 
 /* Whole-file driver: read -> (double-buffered) GPU chain -> ordered write. Output paths
  * may be NULL (destination discarded); a ".gz" suffix selects gzip output. */

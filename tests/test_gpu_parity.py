@@ -297,3 +297,73 @@ def test_synthetic_configs_against_oracle():
                     assert text[d][m] == want["text"][d][m], (config, argv, flags, d, m)
             assert list(stats.dp_cells[0]) == list(want["counters"].dp_cells[0])
             assert stats.written == want["counters"].written and stats.untrimmed == want["counters"].untrimmed
+
+
+# ---- text batches: raw FASTQ bytes in, the device builds the record index (parse.cu) ----
+def test_text_batches_equal_soa_batches():
+    cases = [
+        (2, ["-A", "TAKARAV3", "--trim-polyA"], 2),
+        (3, ["-a", "ACACGACGCTCTTCCGATCT(ATCACG)NNNNNNNNXXX<XXX(CGTGAT)AGATCGGAAGAGCACACGTC", "--ensure-inline-barcode"], 2),
+        (4, ["-A", "SMALLRNA"], 1),
+    ]
+    for config, argv, n_mates in cases:
+        prog = helpers.program_for(argv, n_mates)
+        for n in (1, 255, 20011):
+            batch = native.synth_batch(config, n, first_index=99, buffer=5)
+            texts = [native.format_fastq(batch, m).tobytes() for m in range(n_mates)]
+            with native.Plan(prog, 0, 0) as plan:
+                want, want_records = plan.run_batch(batch)
+                got, got_records = plan.run_text(texts, n, slot=1)
+                assert got == want and got_records == want_records, (config, n)
+                crlf = [t.replace(b"\n", b"\r\n") for t in texts]
+                got, got_records = plan.run_text(crlf, n, slot=2)
+                assert got == want and got_records == want_records, (config, n, "crlf")
+
+
+def test_text_batch_odd_records():
+    """'+' line repeating the name, empty reads, a read at the length limit, lower-case bases, header with tabs."""
+    prog = helpers.program_for(["-A", "SMALLRNA"], 1)
+    recs = [
+        ("r1 x", "ACGTACGTACGTACGTACGTACGTAGATCGGAAGAGCACACGTC", True),
+        ("r2\ty", "", False),
+        ("r3", "A" * A.CSQ_MAX_READ_LEN, False),
+        ("r4/1", "acgtacgtnnacgtacgtacgtacgtagatcggaagagcacacgtc", True),
+        ("r5.1 z", "ACGTTTGACCATGACCATGACGATTTACGACGATATTACGAGT", False),
+    ]
+    text = b""
+    for name, seq, plus_name in recs:
+        text += f"@{name}\n{seq}\n+{name if plus_name else ''}\n{'I' * len(seq)}\n".encode()
+    want = oracle_text(prog, [text])
+    with native.Plan(prog, 0, 0) as plan:
+        got, _ = plan.run_text([text], len(recs))
+    assert got[0][0] == want[0][0] and got[1][0] == want[1][0]
+
+
+def oracle_text(prog, texts):
+    """Oracle over FASTQ text: host parser (csq_parse_fastq_mem semantics, Python) -> SoA -> oracle.run_batch."""
+    mates = []
+    for t in texts:
+        lines = t.split(b"\n")
+        mates.append([(lines[i][1:].rstrip(b"\r").decode(), lines[i + 1].rstrip(b"\r").decode(), lines[i + 3].rstrip(b"\r").decode())
+                      for i in range(0, len(lines) - 1, 4)])
+    batch, keep = oracle.make_batch(*mates)
+    return oracle.run_batch(prog, batch, n_threads=2)["text"]
+
+
+@pytest.mark.parametrize("bad,code,needle", [
+    (b"@r1\nACGT\n+\nIIII\nr2\nACGT\n+\nIIII\n", A.ERR_FORMAT, "line 5 is expected to start with '@'"),
+    (b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n-\nIIII\n", A.ERR_FORMAT, "line 7 is expected to start with '+'"),
+    (b"@r1\nACGT\n+\nIII\n@r2\nACGT\n+\nIIII\n", A.ERR_FORMAT, "length of sequence and qualities differ (record at line 1)"),
+    (b"@r1\nACGT\n+\nIIII\n@r2\n" + b"A" * 900 + b"\n+\n" + b"I" * 900 + b"\n", A.ERR_LIMIT, "line 5"),
+    (b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n+\n", A.ERR_FORMAT, "whole FASTQ records"),
+])
+def test_text_batch_format_errors(bad, code, needle):
+    prog = helpers.program_for(["-A", "SMALLRNA"], 1)
+    with native.Plan(prog, 0, 0) as plan:
+        with pytest.raises(native.NativeError) as e:
+            plan.run_text([bad], 2, capacity=8192)
+        assert e.value.code == code and needle in str(e.value), str(e.value)
+        # the plan stays usable
+        good = b"@r1\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+        got, records = plan.run_text([good], 1, capacity=8192)
+        assert got[0][0] == good and records[0][0] == 1

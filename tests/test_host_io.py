@@ -3,6 +3,7 @@
 import ctypes as C
 import gzip
 import os
+import random
 
 import numpy as np
 import pytest
@@ -165,3 +166,103 @@ def test_no_gpu_means_loud_failure():
     with pytest.raises(native.NativeError) as e:
         native.Plan(prog)
     assert e.value.code == A.ERR_NO_DEVICE
+
+
+# ---- text batches: the reader only cuts the byte stream at record boundaries (text_reader.cpp) ----
+def _records(n, read_len=30, crlf=False, seed=5):
+    rng = random.Random(seed)
+    eol = "\r\n" if crlf else "\n"
+    out = []
+    for i in range(n):
+        L = rng.randint(0, read_len)
+        seq = "".join(rng.choice("ACGTN") for _ in range(L))
+        qual = "".join(rng.choice("#-9I") for _ in range(L))
+        out.append(f"@r{i} c{i}{eol}{seq}{eol}+{eol}{qual}{eol}")
+    return out
+
+
+def test_newline_helpers():
+    L = native.lib()
+    rng = random.Random(1)
+    for n in (0, 1, 63, 64, 65, 4096, 4097, 100001):
+        buf = np.frombuffer(bytes(rng.choice(b"ACGT\n\n") for _ in range(n)), dtype=np.uint8) if n else np.zeros(1, np.uint8)
+        raw = buf.tobytes()[:n]
+        assert L.csq_count_newlines(buf.ctypes.data, n) == raw.count(b"\n")
+        for k in (1, 2, raw.count(b"\n"), raw.count(b"\n") + 1):
+            pos, want = -1, 2 ** 64 - 1
+            for _ in range(k):
+                pos = raw.find(b"\n", pos + 1)
+                if pos < 0:
+                    break
+            else:
+                want = pos + 1
+            if k >= 1:
+                assert L.csq_after_kth_newline(buf.ctypes.data, n, k) == want, (n, k)
+
+
+@pytest.mark.parametrize("gz", [False, True], ids=["plain", "gzip"])
+@pytest.mark.parametrize("tail", ["", "nofinal", "blank", "blank_crlf"])
+def test_text_reader_cuts_whole_records(tmp_path, gz, tail):
+    recs1, recs2 = _records(1000, seed=1), _records(1000, seed=2, crlf=(tail == "blank_crlf"))
+    t1, t2 = "".join(recs1), "".join(recs2)
+    if tail == "nofinal":
+        t1 = t1[:-1]
+    elif tail == "blank":
+        t1 += "\n\n"
+    elif tail == "blank_crlf":
+        t2 += "\r\n"
+    p1, p2 = tmp_path / ("a.fq" + (".gz" if gz else "")), tmp_path / ("b.fq" + (".gz" if gz else ""))
+    if gz:  # two concatenated members: one valid gzip file
+        half = len(t1) // 2
+        p1.write_bytes(gzip.compress(t1[:half].encode()) + gzip.compress(t1[half:].encode()))
+        p2.write_bytes(gzip.compress(t2.encode()))
+    else:
+        p1.write_bytes(t1.encode())
+        p2.write_bytes(t2.encode())
+    for batch in (1, 7, 256, 5000):
+        got1, got2, total, first = b"", b"", 0, 0
+        with native.TextReader(str(p1), str(p2)) as r:
+            while True:
+                n, texts, first_record = r.next(batch)
+                if n == 0:
+                    break
+                assert first_record == total and n <= batch
+                assert texts[0].count(b"\n") == 4 * n and texts[1].count(b"\n") == 4 * n
+                got1 += texts[0]
+                got2 += texts[1]
+                total += n
+        assert total == 1000
+        assert got1 == "".join(recs1).encode() and got2 == "".join(recs2).encode()
+
+
+def test_text_reader_errors(tmp_path):
+    (tmp_path / "short.fq").write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nAC\n")
+    with native.TextReader(str(tmp_path / "short.fq")) as r:
+        with pytest.raises(native.NativeError) as e:
+            r.next(100)
+        assert e.value.code == A.ERR_FORMAT and "prematurely" in str(e.value)
+    (tmp_path / "a.fq").write_bytes("".join(_records(10)).encode())
+    (tmp_path / "b.fq").write_bytes("".join(_records(9)).encode())
+    with native.TextReader(str(tmp_path / "a.fq"), str(tmp_path / "b.fq")) as r:
+        with pytest.raises(native.NativeError) as e:
+            r.next(100)
+        assert e.value.code == A.ERR_FORMAT
+    (tmp_path / "trunc.fq.gz").write_bytes(gzip.compress("".join(_records(500)).encode())[:-20])
+    with native.TextReader(str(tmp_path / "trunc.fq.gz")) as r:
+        with pytest.raises(native.NativeError) as e:
+            r.next(1000)
+        assert e.value.code == A.ERR_IO
+    (tmp_path / "empty.fq").write_bytes(b"")
+    with native.TextReader(str(tmp_path / "empty.fq")) as r:
+        assert r.next(10)[0] == 0
+
+
+def test_format_fastq_round_trips_through_the_parser():
+    batch = native.synth_batch(3, 500, first_index=7, buffer=4)
+    for m in range(2):
+        text = native.format_fastq(batch, m)
+        assert text.tobytes().count(b"\n") == 4 * 500
+        rec = parse_mem(text.tobytes())
+        mi = batch.mate[m]
+        noff = np.ctypeslib.as_array(C.cast(mi.name_off, C.POINTER(C.c_uint32)), (501,))
+        assert rec[0][0][0] == C.string_at(mi.name, int(noff[1])).decode()
