@@ -8,8 +8,10 @@
 One "step" = one pass of the whole hot path (all ALIGN ops, cuts, quality trim, filters, FASTQ
 emission) over one batch of synthetic 2x150 read pairs (config 2: `-A TAKARAV3 --trim-polyA`).
 `value` is kernel throughput with the batches resident in HBM (CUDA events around exactly K steps,
-max over ranks); `e2e` is the same chain through csq_submit/csq_wait with pinned HOST buffers,
+max over ranks); `e2e` is the same chain through csq_submit_text/csq_wait with pinned HOST buffers,
 host->device and device->host copies inside the timed region.  Prints ONE JSON line (rank 0).
+Input form: --input text (default; raw FASTQ bytes, the device builds the record index - what the
+file driver does) or --input soa (host-parsed packed struct-of-arrays batches).
 """
 
 from __future__ import annotations
@@ -148,6 +150,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
+    ap.add_argument("--input", default="text", choices=["text", "soa"], help="batch form handed to the library")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -186,12 +189,34 @@ def main():
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
     batches = []
+    text_mode = args.input == "text"
     for b in range(B):
         batch = native.synth_batch(2, P, first_index=(rank * B + b) * P, buffer=min(b, 2))
-        plan.upload(b, batch)
-        if b < 2:
-            batches.append(batch)
+        if text_mode:  # the FASTQ bytes of the batch, as a file would hold them, in pinned host memory
+            texts = []
+            for m in range(2):
+                mi = batch.mate[m]
+                buf = torch.empty(int(mi.name_bytes) + 2 * int(mi.seq_bytes) + 6 * P + 64, dtype=torch.uint8, pin_memory=True)
+                n_bytes = native.format_fastq(batch, m, out=buf).numel()
+                texts.append(buf[:n_bytes])
+            tb = native.TextBatch(texts, P, first_record=(rank * B + b) * P)
+            plan.upload_text(b, tb.c)
+            if b < 2:
+                batches.append(tb)
+        else:
+            plan.upload(b, batch)
+            if b < 2:
+                batches.append(batch)
     slots = list(range(B))
+
+    def in_bytes(bt):
+        return int(sum(bt.c.mate[m].bytes for m in range(2))) if text_mode else h2d_bytes(bt)
+
+    def submit(slot, bt, out):
+        if text_mode:
+            plan.submit_text(slot, bt.c, out)
+        else:
+            plan.submit(slot, bt, out)
 
     # ---- kernel throughput, inputs resident in HBM ----
     if args.warmup > 0:
@@ -226,7 +251,7 @@ def main():
     e2e = None
     clocks = sampler.stop(t0, t1)
     if not args.no_e2e:
-        cap = int(max(b.mate[0].name_bytes for b in batches) + 2 * batches[0].mate[0].seq_bytes + 32 * P + 4096)
+        cap = int(in_bytes(batches[0]) // 2 + 64 * P + 4096)
         outs, keep = [], []
         n_e2e = 3 if B + 2 < A.CSQ_N_SLOTS else 2  # batches in flight: keeps the H2D engine busy while a D2H drains
         for s in range(n_e2e):
@@ -247,7 +272,7 @@ def main():
             submitted = 0
             for i in range(k):
                 while submitted < k and submitted < i + n_e2e:
-                    plan.submit(e2e_slots[submitted % n_e2e], batches[submitted % len(batches)], outs[submitted % n_e2e])
+                    submit(e2e_slots[submitted % n_e2e], batches[submitted % len(batches)], outs[submitted % n_e2e])
                     submitted += 1
                 plan.wait(e2e_slots[i % n_e2e])
                 o = outs[i % n_e2e]
@@ -262,7 +287,7 @@ def main():
         w1 = time.perf_counter()
         barrier()
         e2e_s = max_over_ranks(w1 - w0)
-        e2e = {"value": world * args.steps * P / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(batches[0]),
+        e2e = {"value": world * args.steps * P / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes(batches[0]),
                "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_s / args.steps * 1e3,
                "timing": f"wall clock between device-synchronised points, {n_e2e} batches in flight through csq_submit/csq_wait, max over ranks"}
 
@@ -302,8 +327,8 @@ def main():
             hbm_peak, hbm_src = json.load(f)["hbm_gbs"], "measured"
     except Exception:
         pass
-    d2h_per_step = e2e["d2h_bytes_per_step"] if e2e else int(0.72 * h2d_bytes(batches[0]))
-    emit_bytes = h2d_bytes(batches[0]) + d2h_per_step  # SoA read once + FASTQ text written once (~1.3 KB / pair)
+    d2h_per_step = e2e["d2h_bytes_per_step"] if e2e else int(0.72 * in_bytes(batches[0]))
+    emit_bytes = in_bytes(batches[0]) + d2h_per_step  # input read once + FASTQ text written once (~1.3 KB / pair)
     emit_ms = sum(kms for name, kms in ktimes if name == "k_emit")
     roofline_dp = None
     dom_dp = max(per_kernel, key=lambda r: r["ms"]) if per_kernel else None
@@ -318,7 +343,7 @@ def main():
         }
     roofline_hbm = {"bound": "hbm", "kernel": "k_emit", "achieved": (emit_bytes / (emit_ms * 1e-3) / 1e9) if emit_ms else None,
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "traffic": None,
-                    "how": "algorithmic bytes per launch (input SoA read once + FASTQ text written once) / CUDA-event duration"}
+                    "how": "algorithmic bytes per launch (input records read once + FASTQ text written once) / CUDA-event duration"}
     if roofline_hbm["achieved"]:
         roofline_hbm["frac"] = roofline_hbm["achieved"] / hbm_peak
     # the dominant kernel of the step decides which of the two is THE roofline line
@@ -337,7 +362,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; {B} resident batches x {P} pairs per GPU "
                                f"(= {B * P} pairs), step = one batch; consecutive steps use different batches "
-                               f"({h2d_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed)",
+                               f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
+                               f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
                    "prefilter": not args.no_prefilter},
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,

@@ -130,7 +130,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         return CSQ_ERR_INVALID;
     }
     const int n_dev = files->n_devices > 0 ? files->n_devices : 1;
-    const uint32_t batch_reads = files->batch_reads ? files->batch_reads : (1u << 19);
+    const uint32_t batch_reads = files->batch_reads ? files->batch_reads : (1u << 17);
     const int n_threads = files->n_threads > 0 ? files->n_threads : 4;
 
     // plans first: fails loudly when there is no usable GPU
@@ -301,14 +301,38 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     for (int t = 1; t < nt; t++) pool.emplace_back(compress);
                     compress();
                     for (auto& th : pool) th.join();
-                    for (Task& k : tasks) {
-                        int r = k.rc;
-                        if (!r) r = outs[k.d][k.m].gzip ? outs[k.d][k.m].write_raw(k.z.data(), k.z.size()) : outs[k.d][k.m].write_raw(k.src, k.n);
-                        if (r) {
-                            sh.fail(r, csqio::io_error());
-                            break;
+                    // the files are independent: one writing thread per output file, its tasks in order
+                    std::vector<std::thread> wpool;
+                    std::mutex werr_m;
+                    auto write_file = [&](int d, int m) {
+                        for (Task& k : tasks) {
+                            if (k.d != d || k.m != m) continue;
+                            int r = k.rc;
+                            if (!r) r = outs[d][m].gzip ? outs[d][m].write_raw(k.z.data(), k.z.size()) : outs[d][m].write_raw(k.src, k.n);
+                            if (r) {
+                                std::lock_guard<std::mutex> g(werr_m);
+                                sh.fail(r, csqio::io_error());
+                                return;
+                            }
                         }
-                    }
+                    };
+                    bool first_file = true;
+                    int fd0 = -1, fm0 = -1;
+                    for (int d = 0; d < CSQ_N_DEST; d++)
+                        for (int m = 0; m < n_mates; m++) {
+                            bool any = false;
+                            for (Task& k : tasks) any = any || (k.d == d && k.m == m);
+                            if (!any) continue;
+                            if (first_file) {
+                                first_file = false;
+                                fd0 = d;
+                                fm0 = m;
+                            } else {
+                                wpool.emplace_back(write_file, d, m);
+                            }
+                        }
+                    if (fd0 >= 0) write_file(fd0, fm0);
+                    for (auto& th : wpool) th.join();
                     t_write += seconds_since(t0);
                 }
                 free_q.push(w);

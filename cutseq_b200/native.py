@@ -284,7 +284,6 @@ def format_fastq(batch: A.csq_batch_in, mate: int, out=None):
     """FASTQ text of one mate of a SoA batch (``csq_format_fastq``). -> numpy uint8 array (or fills `out`)."""
     need = C.c_uint64()
     mi = batch.mate[mate]
-    lib().csq_format_fastq(C.byref(mi), batch.n_reads, None, 0, C.byref(need)) if batch.n_reads == 0 else None
     if out is None:
         # size: names + 2 * bases + 6 per record
         noff = np.ctypeslib.as_array(C.cast(mi.name_off, C.POINTER(C.c_uint32)), (batch.n_reads + 1,))

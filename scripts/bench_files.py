@@ -21,36 +21,30 @@ sys.path.insert(0, ROOT)
 
 
 def write_fastq_from_batch(batch, paths, compress):
-    """Serialise a synthetic SoA batch to FASTQ files (numpy, vectorised enough for a few M records)."""
-    import numpy as np
+    """Serialise a synthetic SoA batch to FASTQ files (csq_format_fastq); .gz = one gzip member per file, level 1."""
+    import subprocess
 
+    from cutseq_b200 import native
+
+    procs = []
     for m, path in enumerate(paths):
-        mi = batch.mate[m]
-        n = batch.n_reads
-        seq = np.ctypeslib.as_array(C.cast(mi.seq, C.POINTER(C.c_uint8)), (mi.seq_bytes,))
-        qual = np.ctypeslib.as_array(C.cast(mi.qual, C.POINTER(C.c_uint8)), (mi.seq_bytes,))
-        name = C.string_at(mi.name, mi.name_bytes)
-        noff = np.ctypeslib.as_array(C.cast(mi.name_off, C.POINTER(C.c_uint32)), (n + 1,))
-        soff = np.ctypeslib.as_array(C.cast(mi.seq_off, C.POINTER(C.c_uint32)), (n,))
-        slen = np.ctypeslib.as_array(C.cast(mi.seq_len, C.POINTER(C.c_uint32)), (n,))
-        opener = (lambda p: gzip.open(p, "wb", compresslevel=1)) if compress else (lambda p: open(p, "wb"))
-        with opener(path) as f:
-            chunk = []
-            for i in range(n):
-                o, l = int(soff[i]), int(slen[i])
-                chunk.append(b"@" + name[noff[i]:noff[i + 1]] + b"\n" + seq[o:o + l].tobytes() + b"\n+\n" + qual[o:o + l].tobytes() + b"\n")
-                if len(chunk) == 20000:
-                    f.write(b"".join(chunk))
-                    chunk = []
-            f.write(b"".join(chunk))
+        text = native.format_fastq(batch, m)
+        plain = path[:-3] if compress else path
+        with open(plain, "wb") as f:
+            f.write(memoryview(text))
+        if compress:
+            procs.append(subprocess.Popen(["gzip", "-1", "-f", plain]))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("gzip failed")
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--pairs", type=int, default=1_000_000)
+    ap.add_argument("--pairs", type=int, default=4_000_000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--threads", type=int, default=8)
-    ap.add_argument("--batch-reads", type=int, default=1 << 19)
+    ap.add_argument("--batch-reads", type=int, default=0)
     ap.add_argument("--out", default=None)
     ap.add_argument("--tmp", default=None)
     args = ap.parse_args()
