@@ -410,26 +410,6 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishPa
     }
 }
 
-struct RecordShape {
-    uint32_t id_len, umi_len, seq_len, total;
-    uint32_t lenA, lenB;
-};
-
-__device__ __forceinline__ RecordShape record_shape(const PairParams& P, const ReadState& own, const ReadState& r1,
-                                                    const ReadState& r2) {
-    RecordShape rs;
-    rs.id_len = (uint32_t)own.id_end - (uint32_t)own.id_start;
-    rs.lenA = rs.lenB = 0;
-    if (P.rename_parts & CSQ_REN_OWN_PREFIX) rs.lenA = own.ren_cp & 0xFFFFu;
-    if (P.rename_parts & CSQ_REN_OWN_SUFFIX) rs.lenB = own.ren_cs & 0xFFFFu;
-    if (P.rename_parts & CSQ_REN_R1_PREFIX) rs.lenA = r1.ren_cp & 0xFFFFu;
-    if (P.rename_parts & CSQ_REN_R2_PREFIX) rs.lenB = r2.ren_cp & 0xFFFFu;
-    rs.umi_len = (P.rename_parts ? 1u : 0u) + rs.lenA + rs.lenB;
-    rs.seq_len = (uint32_t)own.b - (uint32_t)own.a;
-    rs.total = 1 + rs.id_len + rs.umi_len + 1 + rs.seq_len + 3 + rs.seq_len + 1;
-    return rs;
-}
-
 // Filters + sink of run.py:446-471 / 763-792 and the byte size of every record.
 // Thread per pair; the per-CTA stream totals are warp-reduced (REDUX) before they touch shared memory.
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_pair(const __grid_constant__ PairParams P) {
@@ -549,16 +529,6 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t nblk, const uint32_t* __
         }
         __syncthreads();
     }
-}
-
-__device__ __forceinline__ uint8_t complement_base(uint8_t c) {
-    // dnaio reverse_complement table: ACGTUMRWSYKVHDBN -> TGCAAKYWSRMBDHVN (case kept), others unchanged
-    const char* from = "ACGTUMRWSYKVHDBNacgtumrwsykvhdbn";
-    const char* to = "TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn";
-#pragma unroll
-    for (int i = 0; i < 32; i++)
-        if (c == (uint8_t)from[i]) return (uint8_t)to[i];
-    return c;
 }
 
 // FASTQ text, "@name\nseq\n+\nqual\n" (dnaio), streams in input order.
@@ -889,7 +859,7 @@ cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint
     return cudaGetLastError();
 }
 
-cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream) {
+cudaError_t csq_launch_emit_warp(const EmitParams& p, cudaStream_t stream) {
     if (p.pp.n == 0) return cudaSuccess;
     k_emit<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
     return cudaGetLastError();

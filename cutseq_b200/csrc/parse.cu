@@ -4,15 +4,16 @@
 // records, cut at a record boundary by counting line ends - and these kernels do what dnaio's FASTQ
 // parser (_core.pyx, behind cutadapt's InputPaths in reference run.py:434, 751) does on the CPU:
 //
-//   k_nl_count     line ends per 16 KiB tile of the text
+//   k_nl_count     reads the text once: a line-end bit mask per 16-byte chunk, line ends per 16 KiB tile
 //   k_tile_scan    exclusive scan of the tile counts (one CTA)
-//   k_nl_index     byte position of every line end, in order:  nl[r] = offset of the r-th '\n'
+//   k_nl_index     from the masks: byte position of every line end, in order, nl[r] = offset of the r-th '\n'
 //   k_records      record i = lines 4i .. 4i+3: '@' / '+' checks, '\r' stripping, equal sequence / quality
 //                  lengths, the read-length limit; writes name / sequence / quality offsets and lengths
 //
 // The trimming kernels then work on the text where it lies (seq == qual == name pool == the text buffer);
-// nothing is copied into a packed layout.  Every byte of the text is read twice here (count, index), at HBM
-// speed; bound: HBM.  A malformed record is reported as the smallest (record, kind) key through `perr`.
+// nothing is copied into a packed layout.  Bound: HBM - the text is read once (plus 1/8 of it written and read
+// back as masks, 16 bytes of line-end offsets per record written, and the six boundary bytes of each record
+// looked at by k_records).  A malformed record is reported as the smallest (record, kind) key through `perr`.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,39 +22,35 @@
 namespace {
 
 constexpr int TILE_THREADS = 256;
-constexpr int BYTES_PER_THREAD = 64;
-constexpr int TILE_BYTES = TILE_THREADS * BYTES_PER_THREAD;  // 16 KiB
+constexpr int TILE_BYTES = 16384;               // 1024 chunks of 16 bytes; thread t owns the 64 bytes at 64 t
+constexpr int TILE_CHUNKS = TILE_BYTES / 16;
 
-__device__ __forceinline__ uint32_t nl_mask4(uint32_t w) {
-    // 0x80 in every byte lane that equals '\n'
-    return __vcmpeq4(w, 0x0A0A0A0Au) & 0x80808080u;
+// bit i set <=> byte i of the 16-byte chunk is '\n'
+__device__ __forceinline__ uint32_t nl_mask16(uint4 v) {
+    auto nib = [](uint32_t w) {
+        const uint32_t x = (__vcmpeq4(w, 0x0A0A0A0Au) >> 7) & 0x01010101u;  // bits 0, 8, 16, 24
+        return ((x * 0x00204081u) >> 21) & 0xFu;                             // gathered into bits 0..3
+    };
+    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
 }
 
-// The text buffer is 16-byte aligned and padded with zero bytes up to a multiple of 64, so whole
-// uint4 loads never leave the allocation and padding never counts as a line end.
-__device__ __forceinline__ void load_span(const uint8_t* __restrict__ text, uint64_t off, uint64_t bytes, uint4 v[4]) {
-    const uint4* p = reinterpret_cast<const uint4*>(text + off);
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = (off + 16u * i < bytes) ? p[i] : make_uint4(0, 0, 0, 0);
-}
-
-__device__ __forceinline__ uint32_t count_span(const uint4 v[4]) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        c += __popc(nl_mask4(v[i].x)) + __popc(nl_mask4(v[i].y)) + __popc(nl_mask4(v[i].z)) + __popc(nl_mask4(v[i].w));
-    return c;
-}
-
+// Pass 1: the text is read ONCE, fully coalesced (chunk c of the tile by thread c % 256); what survives is a
+// 16-bit line-end mask per chunk (1/8 of the text) and the number of line ends per tile.
+// The text buffer is 16-byte aligned and zero padded, so whole chunks never leave the allocation and padding
+// never counts as a line end.
 __global__ void __launch_bounds__(TILE_THREADS) k_nl_count(const uint8_t* __restrict__ text, uint64_t bytes,
-                                                           uint32_t* __restrict__ tile_cnt) {
+                                                           uint16_t* __restrict__ masks, uint32_t* __restrict__ tile_cnt) {
     __shared__ uint32_t wsum[TILE_THREADS / 32];
-    const uint64_t off = (uint64_t)blockIdx.x * TILE_BYTES + (uint64_t)threadIdx.x * BYTES_PER_THREAD;
+    const uint64_t tile_off = (uint64_t)blockIdx.x * TILE_BYTES;
     uint32_t c = 0;
-    if (off < bytes) {
-        uint4 v[4];
-        load_span(text, off, bytes, v);
-        c = count_span(v);
+#pragma unroll
+    for (int i = 0; i < TILE_CHUNKS / TILE_THREADS; i++) {
+        const uint32_t chunk = i * TILE_THREADS + threadIdx.x;
+        const uint64_t off = tile_off + 16ull * chunk;
+        uint32_t m = 0;
+        if (off < bytes) m = nl_mask16(*reinterpret_cast<const uint4*>(text + off));
+        masks[(size_t)blockIdx.x * TILE_CHUNKS + chunk] = (uint16_t)m;
+        c += __popc(m);
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
@@ -101,21 +98,14 @@ __global__ void __launch_bounds__(1024) k_tile_scan(uint32_t n_tiles, uint32_t* 
     if (threadIdx.x == 0) total[0] = carry;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS) k_nl_index(const uint8_t* __restrict__ text, uint64_t bytes,
-                                                           const uint32_t* __restrict__ tile_base, uint32_t* __restrict__ nl,
-                                                           uint32_t nl_cap) {
+// Pass 2 reads only the masks: thread t of a tile owns the 64 bytes at 64 t (four masks = one 64-bit word),
+// ranks its line ends by a CTA-wide scan and writes their byte offsets, nl[r] = offset of the r-th '\n'.
+__global__ void __launch_bounds__(TILE_THREADS) k_nl_index(const uint16_t* __restrict__ masks, const uint32_t* __restrict__ tile_base,
+                                                           uint32_t* __restrict__ nl, uint32_t nl_cap) {
     __shared__ uint32_t wsum[TILE_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint64_t off = (uint64_t)blockIdx.x * TILE_BYTES + (uint64_t)threadIdx.x * BYTES_PER_THREAD;
-    uint4 v[4];
-    uint32_t c = 0;
-    if (off < bytes) {
-        load_span(text, off, bytes, v);
-        c = count_span(v);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = make_uint4(0, 0, 0, 0);
-    }
+    unsigned long long m = reinterpret_cast<const unsigned long long*>(masks + (size_t)blockIdx.x * TILE_CHUNKS)[threadIdx.x];
+    const uint32_t c = __popcll(m);
     uint32_t x = c;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -125,18 +115,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_nl_index(const uint8_t* __rest
     __syncthreads();
     uint32_t r = tile_base[blockIdx.x] + (x - c);
     for (int w = 0; w < wid; w++) r += wsum[w];
-    if (c == 0) return;
-    const uint32_t words[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
-                                v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        uint32_t msk = nl_mask4(words[q]);
-        while (msk) {
-            const int bit = __ffs(msk) - 1;  // 7, 15, 23 or 31
-            msk &= msk - 1;
-            if (r < nl_cap) nl[r] = (uint32_t)(off + 4u * q + (uint32_t)(bit >> 3));
-            r++;
-        }
+    const uint32_t off = blockIdx.x * (uint32_t)TILE_BYTES + threadIdx.x * 64u;
+    while (m) {
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        if (r < nl_cap) nl[r] = off + (uint32_t)bit;
+        r++;
     }
 }
 
@@ -192,12 +176,12 @@ __global__ void __launch_bounds__(256) k_records(const ParseParams P) {
 
 uint32_t csq_parse_tiles(uint64_t bytes) { return (uint32_t)((bytes + TILE_BYTES - 1) / TILE_BYTES); }
 
-cudaError_t csq_launch_parse(const ParseParams& p, uint32_t* tile_cnt, cudaStream_t stream) {
+cudaError_t csq_launch_parse(const ParseParams& p, uint32_t* tile_cnt, uint16_t* masks, cudaStream_t stream) {
     const uint32_t tiles = csq_parse_tiles(p.bytes);
     if (tiles) {
-        k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, tile_cnt);
+        k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, masks, tile_cnt);
         k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_cnt, p.nl_total);
-        k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, tile_cnt, p.nl, 4u * p.n);
+        k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(masks, tile_cnt, p.nl, 4u * p.n);
     } else {
         cudaError_t e = cudaMemsetAsync(p.nl_total, 0, 4, stream);
         if (e != cudaSuccess) return e;

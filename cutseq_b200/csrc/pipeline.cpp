@@ -6,6 +6,7 @@
 // contiguous record ranges, they are dealt to the GPUs in order and written back in input order.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -124,6 +125,10 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         return CSQ_ERR_INVALID;
     }
     const auto t_start = Clock::now();
+    const bool trace = getenv("CSQ_TRACE") != nullptr;  // phase timestamps on stderr
+    auto stamp = [&](const char* what) {
+        if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  %s\n", seconds_since(t_start), what);
+    };
     const int n_mates = files->in[1] ? 2 : 1;
     if ((n_mates == 2) != (n2 > 0)) {
         csq_set_error("number of input files does not match the program (paired vs single-end)");
@@ -147,6 +152,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             return rc;
         }
     }
+    stamp("plans created");
     csq_text_reader* reader = nullptr;
     int rc = csq_text_reader_open(files->in[0], files->in[1], &reader);
     if (rc) {
@@ -195,9 +201,11 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                 break;
             }
             j->index = index++;
+            if (j->index < 6) stamp("batch read");
             ready_q.push(j);
         }
         n_batches = index;
+        stamp("reader done");
         ready_q.close();
     });
 
@@ -242,6 +250,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     sh.fail(r, csq_last_error());
                     break;
                 }
+                if (j->index < 6) stamp("batch submitted");
                 inflight.push_back(j);
                 if (inflight.size() == 2 && !finish_one()) break;
             }
@@ -334,6 +343,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     if (fd0 >= 0) write_file(fd0, fm0);
                     for (auto& th : wpool) th.join();
                     t_write += seconds_since(t0);
+                    if (w->index < 6) stamp("batch written");
                 }
                 free_q.push(w);
             }
@@ -342,8 +352,10 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
 
     reader_thread.join();
     for (auto& w : workers) w.join();
+    stamp("workers done");
     done_q.close();
     writer_thread.join();
+    stamp("writer done");
     free_q.close();
 
     for (int d = 0; d < CSQ_N_DEST; d++)
@@ -375,6 +387,8 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     }
     csq_text_reader_close(reader);
     destroy_plans();
+    jobs.clear();
+    stamp("teardown done");
     if (sh.err_code) {
         csq_set_error(sh.err_msg.c_str());
         return sh.err_code;

@@ -78,7 +78,7 @@ struct Slot {
     DevBuf dest, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
     DevBuf list, list_count;  // prefilter survivors (indices) and their number
     // text batches (csq_submit_text): the FASTQ bytes as they came, and the record index k_records builds
-    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16
+    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16
     uint64_t text_bytes[2] = {0, 0};
     uint64_t first_record = 0;
     bool text_mode = false;
@@ -274,7 +274,9 @@ int check_device(int device) {
     return 0;
 }
 
-constexpr size_t TEXT_FRONT_PAD = 64;  // readable bytes in front of the text (reversed 128-bit walks start below a read)
+// readable bytes in front of and behind every device pool: the 16-byte fetches of k_emit_rec / k_prefilter may
+// start up to 15 bytes below a piece and end up to 19 bytes behind it
+constexpr size_t TEXT_FRONT_PAD = 64, POOL_PAD = 64;
 
 MateDev mate_dev(Slot& s, int m) {
     MateDev d;
@@ -287,9 +289,9 @@ MateDev mate_dev(Slot& s, int m) {
         d.qual_off = (const uint32_t*)s.qual_off[m].p;
         d.name_end = (const uint32_t*)s.name_end[m].p;
     } else {
-        d.seq = (const uint8_t*)s.seq[m].p;
-        d.qual = (const uint8_t*)s.qual[m].p;
-        d.name = (const uint8_t*)s.name[m].p;
+        d.seq = (const uint8_t*)s.seq[m].p + POOL_PAD;
+        d.qual = (const uint8_t*)s.qual[m].p + POOL_PAD;
+        d.name = (const uint8_t*)s.name[m].p + POOL_PAD;
         d.qual_off = d.seq_off;
         d.name_end = d.name_off + 1;
     }
@@ -347,6 +349,7 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
         if ((rc = s.name_end[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
         if ((rc = s.tiles[m].ensure(((size_t)csq_parse_tiles(bytes) + 4) * 4))) return rc;
+        if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;  // 16 bits per 16-byte chunk
         if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
         if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
             if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
@@ -369,21 +372,21 @@ int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
     for (int m = 0; m < plan->n_mates; m++) {
         const csq_mate_in& mi = in->mate[m];
         int rc;
-        if ((rc = s.seq[m].ensure(mi.seq_bytes + 16))) return rc;
-        if ((rc = s.qual[m].ensure(mi.seq_bytes + 16))) return rc;
+        if ((rc = s.seq[m].ensure(mi.seq_bytes + 2 * POOL_PAD))) return rc;
+        if ((rc = s.qual[m].ensure(mi.seq_bytes + 2 * POOL_PAD))) return rc;
         if ((rc = s.seq_off[m].ensure((size_t)n * 4 + 4))) return rc;
         if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 4))) return rc;
-        if ((rc = s.name[m].ensure(mi.name_bytes + 16))) return rc;
+        if ((rc = s.name[m].ensure(mi.name_bytes + 2 * POOL_PAD))) return rc;
         if ((rc = s.name_off[m].ensure(((size_t)n + 1) * 4))) return rc;
         if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
         if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
             if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
         if (n) {
-            CUDA_TRY(cudaMemcpyAsync(s.seq[m].p, mi.seq, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
-            CUDA_TRY(cudaMemcpyAsync(s.qual[m].p, mi.qual, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync((uint8_t*)s.seq[m].p + POOL_PAD, mi.seq, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync((uint8_t*)s.qual[m].p + POOL_PAD, mi.qual, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
             CUDA_TRY(cudaMemcpyAsync(s.seq_off[m].p, mi.seq_off, (size_t)n * 4, cudaMemcpyHostToDevice, s.stream));
             CUDA_TRY(cudaMemcpyAsync(s.seq_len[m].p, mi.seq_len, (size_t)n * 4, cudaMemcpyHostToDevice, s.stream));
-            CUDA_TRY(cudaMemcpyAsync(s.name[m].p, mi.name, mi.name_bytes, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync((uint8_t*)s.name[m].p + POOL_PAD, mi.name, mi.name_bytes, cudaMemcpyHostToDevice, s.stream));
             CUDA_TRY(cudaMemcpyAsync(s.name_off[m].p, mi.name_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
         }
     }
@@ -447,7 +450,7 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
             pp.name_off = (uint32_t*)s.name_off[m].p;
             pp.name_end = (uint32_t*)s.name_end[m].p;
             pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
-            CUDA_TRY(csq_launch_parse(pp, (uint32_t*)s.tiles[m].p, st));
+            CUDA_TRY(csq_launch_parse(pp, (uint32_t*)s.tiles[m].p, (uint16_t*)s.masks[m].p, st));
             plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
             if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
         }
@@ -520,7 +523,7 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     ep.block_off = (const unsigned long long*)s.block_off.p;
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < 2; m++) ep.out[d][m] = (uint8_t*)s.out[d][m].p;
-    CUDA_TRY(csq_launch_emit(ep, st));
+    CUDA_TRY((plan->flags & CSQ_PLAN_EMIT_WARP) ? csq_launch_emit_warp(ep, st) : csq_launch_emit(ep, st));
     plan->launches += s.n ? 1 : 0;
     if (kt) kt->mark("k_emit");
     return 0;
@@ -647,7 +650,7 @@ void csq_plan_destroy(csq_plan* plan) {
         }
         s.list.release(); s.list_count.release(); s.parse_misc.release();
         for (int m = 0; m < 2; m++) {
-            s.text[m].release(); s.qual_off[m].release(); s.name_end[m].release(); s.nl[m].release(); s.tiles[m].release();
+            s.text[m].release(); s.qual_off[m].release(); s.name_end[m].release(); s.nl[m].release(); s.tiles[m].release(); s.masks[m].release();
         }
         s.dest.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
         for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);

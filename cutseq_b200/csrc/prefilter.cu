@@ -42,9 +42,8 @@ __device__ __forceinline__ void append_survivor(const AlignParams& P, uint32_t* 
     }
 }
 
-// The read characters are fetched with aligned 128-bit loads (16 columns per load; the few characters in
-// front of the first 16-byte boundary bytewise): one thread walks 150 columns with ~10 load instructions
-// instead of 150 single-byte ones, which is what bounded the first version (L1 request rate).
+// The read characters are fetched 16 columns at a time (fetch16): one thread walks 150 columns with ~10 fetches
+// instead of 150 single-byte loads, which is what bounded the first version (L1 request rate).
 //
 // Template switches, all of them about instruction count per column (the kernel is issue bound):
 //   REV    the reversed walk of RightmostFrontAdapter
@@ -146,23 +145,21 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
             }
         };
         // characters of columns min_n+1 .. max_n: s[a+min_n .. a+max_n) ascending, or, for the reversed walk
-        // of RightmostFrontAdapter, s[b-max_n .. b-min_n) descending
+        // of RightmostFrontAdapter, s[b-max_n .. b-min_n) descending.  16 columns per fetch from an arbitrary
+        // byte address (fetch16: five aligned 32-bit loads + four funnel shifts), so that all lanes of a warp
+        // walk the same number of chunks whatever the alignment of their reads (records in a FASTQ text batch
+        // start anywhere); the next chunk is in flight while these 16 columns are computed.  The fetch may touch
+        // up to 19 bytes outside the read: every device pool is padded (plan.cu).
         const uint8_t* s = P.md.seq + P.md.seq_off[idx];
         int rem = max_n - min_n;
         if (!REV) {
             const uint8_t* p = s + a + min_n;
-            int head = min(rem, (int)((16u - (uint32_t)(uintptr_t)p) & 15u));
-            rem -= head;
-            const int head0 = head;
-            for (; head > 0; head--) column(*p++);
-            mark(head0);
-            // software pipelined: the next 16 characters are in flight while these 16 columns are computed
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (rem > 0) v = *reinterpret_cast<const uint4*>(p);  // the pools carry 16 bytes of slack
+            if (rem > 0) v = fetch16(p);
             for (; rem >= 16; rem -= 16) {
                 p += 16;
                 const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                if (rem > 16) v = *reinterpret_cast<const uint4*>(p);
+                if (rem > 16) v = fetch16(p);
 #pragma unroll
                 for (int i = 0; i < 16; i++) column((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
                 mark(16);
@@ -178,17 +175,12 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
             }
         } else {
             const uint8_t* p = s + b - min_n;  // one past the next character
-            int head = min(rem, (int)((uint32_t)(uintptr_t)p & 15u));
-            rem -= head;
-            const int head0 = head;
-            for (; head > 0; head--) column(*--p);
-            mark(head0);
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (rem > 0) v = *reinterpret_cast<const uint4*>(p - 16);  // may start below the read, never below the pool
+            if (rem > 0) v = fetch16(p - 16);
             for (; rem >= 16; rem -= 16) {
                 p -= 16;
                 const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                if (rem > 16) v = *reinterpret_cast<const uint4*>(p - 16);
+                if (rem > 16) v = fetch16(p - 16);
 #pragma unroll
                 for (int i = 15; i >= 0; i--) column((w4[i >> 2] >> (8 * (i & 3))) & 0xFFu);
                 mark(16);
