@@ -40,7 +40,7 @@ DEST_TRIMMED, DEST_SHORT, DEST_UNTRIMMED = 0, 1, 2
 
 PLAN_KEEP_MATCHES = 1
 PLAN_NO_PREFILTER = 2
-PLAN_EMIT_WARP = 4
+PLAN_EMIT_REC = 8
 
 
 class csq_op(C.Structure):

@@ -1,7 +1,10 @@
-// k_emit: order-preserving FASTQ text emission ("@name\nseq\n+\nqual\n", dnaio's fastq_bytes), the sink
-// behind PairedEndSink / SingleEndSink and the two filters of reference run.py:446-471 / 763-792.
+// Order-preserving FASTQ text emission ("@name\nseq\n+\nqual\n", dnaio's fastq_bytes), the sink behind
+// PairedEndSink / SingleEndSink and the two filters of reference run.py:446-471 / 763-792.
+// k_emit_rec (CSQ_PLAN_EMIT_REC) is an alternative to the default warp-per-record k_emit of kernels.cu, kept for
+// A/B runs: it needs 4x fewer instructions, but its per-thread access pattern makes it latency / L1-sector bound
+// and it measures 7 % slower (1.26 ms against 1.17 ms per 2 M pairs, profiles/r01_emit_variants.md).
 //
-// One THREAD per pair (both mates).  Phase 1 is a CTA-wide exclusive scan of the record sizes per output
+// k_emit_rec: one THREAD per pair (both mates).  Phase 1 is a CTA-wide exclusive scan of the record sizes per output
 // stream (destination x mate), which places every record; phase 2 streams each record into its place
 // through a 16-byte staging chunk held in registers:
 //
@@ -78,16 +81,44 @@ __device__ __forceinline__ void append_byte(Stage& st, uint32_t c) {
     if (++st.fill == 16) stage_advance(st);
 }
 
+// 16 bytes at byte offset k (0..15) of the 32 bytes (a, b): word select by k >> 2 (a two-level SEL network, no
+// dynamic register indexing), then the funnel shift by k & 3.
+__device__ __forceinline__ uint4 shift32(const uint4 a, const uint4 b, uint32_t k) {
+    const bool q2 = (k & 8u) != 0, q1 = (k & 4u) != 0;
+    const uint32_t sh = (k & 3u) * 8u;
+    const uint32_t t0 = q2 ? a.z : a.x, t1 = q2 ? a.w : a.y, t2 = q2 ? b.x : a.z, t3 = q2 ? b.y : a.w, t4 = q2 ? b.z : b.x,
+                   t5 = q2 ? b.w : b.y;
+    const uint32_t x0 = q1 ? t1 : t0, x1 = q1 ? t2 : t1, x2 = q1 ? t3 : t2, x3 = q1 ? t4 : t3, x4 = q1 ? t5 : t4;
+    return make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                      __funnelshift_r(x3, x4, sh));
+}
+
 // pm[k]: the first k bytes of a chunk
 __device__ __forceinline__ void append_data(Stage& st, const uint8_t* __restrict__ src, uint32_t len, const uint4* __restrict__ pm) {
     while (len) {
-        if (st.fill == 0 && len >= 16) {  // inside one piece, chunk by chunk
-            do {
-                *reinterpret_cast<uint4*>(st.cptr) = fetch16(src);
+        if (st.fill == 0 && len >= 16) {
+            // inside one piece, chunk by chunk: ONE aligned 128-bit load per chunk (read-only path, so the loads
+            // of the next chunks are not ordered behind the stores), the previous load supplies the low bytes
+            const uint32_t k = (uint32_t)(uintptr_t)src & 15u;
+            const uint4* __restrict__ p = reinterpret_cast<const uint4*>((uintptr_t)src & ~(uintptr_t)15);
+            uint4 prev = __ldg(p);
+            while (len >= 32) {
+                const uint4 n1 = __ldg(p + 1), n2 = __ldg(p + 2);
+                reinterpret_cast<uint4*>(st.cptr)[0] = shift32(prev, n1, k);
+                reinterpret_cast<uint4*>(st.cptr)[1] = shift32(n1, n2, k);
+                prev = n2;
+                p += 2;
+                st.cptr += 32;
+                src += 32;
+                len -= 32;
+            }
+            if (len >= 16) {
+                const uint4 n1 = __ldg(p + 1);
+                *reinterpret_cast<uint4*>(st.cptr) = shift32(prev, n1, k);
                 st.cptr += 16;
                 src += 16;
                 len -= 16;
-            } while (len >= 16);
+            }
             continue;
         }
         const uint32_t take = min(16u - st.fill, len);
@@ -226,7 +257,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit_rec(const __grid_consta
 
 }  // namespace
 
-cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream) {
+cudaError_t csq_launch_emit_rec(const EmitParams& p, cudaStream_t stream) {
     if (p.pp.n == 0) return cudaSuccess;
     k_emit_rec<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
     return cudaGetLastError();

@@ -859,7 +859,7 @@ cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint
     return cudaGetLastError();
 }
 
-cudaError_t csq_launch_emit_warp(const EmitParams& p, cudaStream_t stream) {
+cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream) {
     if (p.pp.n == 0) return cudaSuccess;
     k_emit<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
     return cudaGetLastError();

@@ -39,6 +39,46 @@ def write_fastq_from_batch(batch, paths, compress):
             raise RuntimeError("gzip failed")
 
 
+def host_probe(paths):
+    """What the host can do at best on this box: page-cache read of the input files (two threads, reused 4 MiB
+    buffers), line-end counting and memcpy speed - the floor under any host-side FASTQ reader."""
+    import threading
+
+    import numpy as np
+
+    from cutseq_b200 import native
+
+    def read_all(path, out, i):
+        buf = bytearray(4 << 20)
+        n = 0
+        with open(path, "rb", buffering=0) as f:
+            while True:
+                k = f.readinto(buf)
+                if not k:
+                    break
+                n += k
+        out[i] = n
+
+    res = {}
+    sizes = [0] * len(paths)
+    t0 = time.time()
+    ths = [threading.Thread(target=read_all, args=(p, sizes, i)) for i, p in enumerate(paths)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.time() - t0
+    res["page_cache_read_GBps_2_threads"] = sum(sizes) / dt / 1e9
+    a = np.frombuffer(open(paths[0], "rb").read(256 << 20), dtype=np.uint8)
+    t0 = time.time()
+    native.lib().csq_count_newlines(a.ctypes.data, a.size)
+    res["count_newlines_GBps_1_thread"] = a.size / (time.time() - t0) / 1e9
+    b = np.empty_like(a)
+    b[:] = a
+    t0 = time.time()
+    b[:] = a
+    res["memcpy_GBps_1_thread"] = a.size / (time.time() - t0) / 1e9
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=4_000_000)
@@ -68,6 +108,7 @@ def main():
                 t0 = time.time()
                 counters, timing = native.run_files(prog, ins, outs, gpus=args.gpus, threads=args.threads, batch_reads=args.batch_reads)
                 wall = time.time() - t0
+            probe = host_probe(ins) if variant == "plain" else None
             in_bytes = sum(os.path.getsize(p) for p in ins)
             out_bytes = sum(os.path.getsize(p) for v in outs.values() for p in v)
             results.append({
@@ -75,7 +116,7 @@ def main():
                 "pairs_per_s": args.pairs / wall, "wall_s": wall, "input_bytes": in_bytes, "output_bytes": out_bytes,
                 "read_inflate_parse_s": timing.read_inflate, "gpu_h2d_kernels_d2h_s": timing.h2d_kernels_d2h, "gpu_kernels_s": timing.kernels,
                 "deflate_write_s": timing.write_deflate, "total_s": timing.total, "written_pairs": int(counters.written),
-                "fixture_generation_s": gen_s,
+                "fixture_generation_s": gen_s, "host_probe": probe,
                 "note": "stages overlap (reader thread, GPU workers, writer thread): the stage seconds are busy times, not a sum",
             })
             print(json.dumps(results[-1]))
