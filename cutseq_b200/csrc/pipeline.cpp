@@ -108,7 +108,8 @@ bool size_job_outputs(Job& j, bool first_try) {
         for (int d = 0; d < CSQ_N_DEST; d++) {
             uint64_t want = first_try ? (d == CSQ_DEST_TRIMMED ? full : full / 8 + 4096) : j.out.text[d][m].bytes + 4096;
             if (m >= n_mates) want = 64;
-            if (want > j.outbuf[d][m].cap && !j.outbuf[d][m].reserve(want, 0)) return false;
+            // (allocate with 1/8 to spare: a batch a few bytes longer than the last must not cost a new pinned buffer)
+            if (want > j.outbuf[d][m].cap && !j.outbuf[d][m].reserve(want + want / 8, 0)) return false;
             j.out.text[d][m].data = j.outbuf[d][m].p;
             j.out.text[d][m].capacity = j.outbuf[d][m].cap;
         }
@@ -201,7 +202,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                 break;
             }
             j->index = index++;
-            if (j->index < 6) stamp("batch read");
+            if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  batch %ld read in %.1f ms\n", seconds_since(t_start), j->index, seconds_since(t0) * 1e3);
             ready_q.push(j);
         }
         n_batches = index;
@@ -250,7 +251,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     sh.fail(r, csq_last_error());
                     break;
                 }
-                if (j->index < 6) stamp("batch submitted");
+                if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  batch %ld submitted\n", seconds_since(t_start), j->index);
                 inflight.push_back(j);
                 if (inflight.size() == 2 && !finish_one()) break;
             }
@@ -343,7 +344,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     if (fd0 >= 0) write_file(fd0, fm0);
                     for (auto& th : wpool) th.join();
                     t_write += seconds_since(t0);
-                    if (w->index < 6) stamp("batch written");
+                    if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  batch %ld written\n", seconds_since(t_start), w->index);
                 }
                 free_q.push(w);
             }

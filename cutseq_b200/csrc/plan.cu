@@ -41,7 +41,9 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        // cudaFree / cudaMalloc synchronise the device and stall every stream of the plan: grow rarely (x1.25 and
+        // never below 256 KiB, so that the small per-destination buffers do not creep up batch by batch)
+        size_t want = bytes + bytes / 4 + (256u << 10);
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) return fail(CSQ_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
         cap = want;

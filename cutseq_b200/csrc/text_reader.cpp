@@ -196,7 +196,10 @@ int MateTextReader::next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, ui
     *n_reads = 0;
     const size_t avail = carry.size() - carry_pos;
     // pinned memory is expensive to grow: reserve what the previous batch needed (first batch: a guess)
-    if (!buf.reserve((hint_bytes ? hint_bytes + hint_bytes / 16 : (size_t)max_reads * 96) + piece + 64, 0))
+    // (what a batch needs is its own size plus one piece; when that is not there, allocate it with 1/8 to spare, so
+    // that batches a few bytes longer than the previous one do not trigger another - doubling - allocation)
+    const size_t need = (hint_bytes ? hint_bytes : (size_t)max_reads * 96) + piece + 64;
+    if (buf.cap < need && !buf.reserve(need + need / 8, 0))
         return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
     if (avail) {
         const uint8_t* c = carry.data() + carry_pos;
