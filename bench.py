@@ -347,6 +347,13 @@ def main():
                     "how": "algorithmic bytes per launch (input records read once + FASTQ text written once) / CUDA-event duration"}
     if roofline_hbm["achieved"]:
         roofline_hbm["frac"] = roofline_hbm["achieved"] / hbm_peak
+    try:  # DRAM bytes of one launch from the committed ncu capture (per pair, scaled to this batch size)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)["k_emit"]
+        roofline_hbm["traffic"] = tr["dram_bytes_per_pair"] * P
+        roofline_hbm["traffic_source"] = tr["source"]
+    except Exception:
+        pass
     # the dominant kernel of the step decides which of the two is THE roofline line
     roofline = roofline_hbm if (emit_ms and (not dom_dp or emit_ms >= dom_dp["ms"])) else roofline_dp
 

@@ -136,7 +136,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         return CSQ_ERR_INVALID;
     }
     const int n_dev = files->n_devices > 0 ? files->n_devices : 1;
-    const uint32_t batch_reads = files->batch_reads ? files->batch_reads : (1u << 17);
+    const uint32_t batch_reads = files->batch_reads ? files->batch_reads : (1u << 16);
     const int n_threads = files->n_threads > 0 ? files->n_threads : 4;
 
     // plans first: fails loudly when there is no usable GPU
