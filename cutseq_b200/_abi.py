@@ -41,6 +41,8 @@ DEST_TRIMMED, DEST_SHORT, DEST_UNTRIMMED = 0, 1, 2
 PLAN_KEEP_MATCHES = 1
 PLAN_NO_PREFILTER = 2
 PLAN_EMIT_REC = 8
+PLAN_EMIT_G32 = 16
+PLAN_EMIT_G8 = 32
 
 
 class csq_op(C.Structure):

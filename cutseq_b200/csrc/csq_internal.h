@@ -132,7 +132,7 @@ cudaError_t csq_launch_finish(const FinishParams& p, cudaStream_t stream);
 cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream);
 cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
                             unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream);
-cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream);       // kernels.cu: warp per record (default)
+cudaError_t csq_launch_emit(const EmitParams& p, int lanes_per_record, cudaStream_t stream);  // kernels.cu: 32 / 16 / 8 lanes per record
 cudaError_t csq_launch_emit_rec(const EmitParams& p, cudaStream_t stream);   // emit.cu: thread per pair, 16-byte chunks (CSQ_PLAN_EMIT_REC)
 cudaError_t csq_launch_parse(const ParseParams& p, uint32_t* tile_cnt, uint16_t* masks, cudaStream_t stream);
 uint32_t csq_parse_tiles(uint64_t bytes);

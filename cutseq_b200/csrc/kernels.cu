@@ -325,7 +325,15 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
     store_state(P.md.state + idx, st);
 }
 
-__device__ __forceinline__ bool is_py_space(uint32_t c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
+// bit i set <=> byte i of the 16 is one of Python's str.split() blanks: ' ', 9..13, 28..31
+__device__ __forceinline__ uint32_t space_bits16(uint4 v) {
+    auto nib = [](uint32_t w) {
+        const uint32_t m = __vcmpeq4(w, 0x20202020u) | (__vcmpgeu4(w, 0x09090909u) & __vcmpleu4(w, 0x0D0D0D0Du)) |
+                           (__vcmpgeu4(w, 0x1C1C1C1Cu) & __vcmpleu4(w, 0x1F1F1F1Fu));
+        return (((m & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+    };
+    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+}
 
 // Trailing scalar ops, QualityTrimmer (quality_trim_index of qualtrim.pyx), SuffixRemover on the
 // header and Renamer.parse_name's id.
@@ -336,37 +344,80 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishPa
         const uint32_t len0 = P.md.seq_len[idx];
         ReadState st = P.first ? fresh_state(len0) : load_state(P.md.state + idx);
         for (int q = 0; q < P.n_post; q++) apply_scalar(P.post[q], st);
+        // header fetches are issued before the quality scan so that both latencies overlap
+        const uint8_t* nm = P.md.name + P.md.name_off[idx];
+        int nl = (int)(P.md.name_end[idx] - P.md.name_off[idx]);
+        const uint4 nm0 = fetch16(nm);
         if (P.has_qtrim) {
+            // quality_trim_index (qualtrim.pyx): running sums from either end, stop at the first negative sum.
+            // Nearly every read stops within a few bases: the 16 qualities at either end are fetched at once
+            // (two fetch16, issued together), the rare longer scans continue bytewise.
             const uint8_t* ql = P.md.qual + P.md.qual_off[idx];
             const int a = st.a, n = (int)st.b - (int)st.a;
-            int start = 0, stop = n, s = 0, mx = 0;
-            for (int i = 0; i < n; i++) {
-                s += P.cutoff_front - ((int)ql[a + i] - P.qbase);
-                if (s < 0) break;
-                if (s > mx) {
-                    mx = s;
-                    start = i + 1;
+            int start = 0, stop = n;
+            if (n > 0) {
+                const uint4 vf = fetch16(ql + a), vb = fetch16(ql + a + n - 16);
+                const uint32_t wf[4] = {vf.x, vf.y, vf.z, vf.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+                int s = 0, mx = 0, i = 0;
+                bool open = true;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if (open && j < n) {
+                        s += P.cutoff_front - ((int)((wf[j >> 2] >> (8 * (j & 3))) & 0xFFu) - P.qbase);
+                        if (s < 0) {
+                            open = false;
+                        } else {
+                            if (s > mx) {
+                                mx = s;
+                                start = j + 1;
+                            }
+                            i = j + 1;
+                        }
+                    }
                 }
-            }
-            mx = 0;
-            s = 0;
-            for (int i = n - 1; i >= 0; i--) {
-                s += P.cutoff_back - ((int)ql[a + i] - P.qbase);
-                if (s < 0) break;
-                if (s > mx) {
-                    mx = s;
-                    stop = i;
+                for (; open && i < n; i++) {
+                    s += P.cutoff_front - ((int)ql[a + i] - P.qbase);
+                    if (s < 0) break;
+                    if (s > mx) {
+                        mx = s;
+                        start = i + 1;
+                    }
+                }
+                s = 0;
+                mx = 0;
+                open = true;
+                i = n - 1;
+#pragma unroll
+                for (int j = 15; j >= 0; j--) {  // byte j of vb is quality n - 16 + j
+                    if (open && n - 16 + j >= 0) {
+                        s += P.cutoff_back - ((int)((wb[j >> 2] >> (8 * (j & 3))) & 0xFFu) - P.qbase);
+                        if (s < 0) {
+                            open = false;
+                        } else {
+                            if (s > mx) {
+                                mx = s;
+                                stop = n - 16 + j;
+                            }
+                            i = n - 17 + j;
+                        }
+                    }
+                }
+                for (; open && i >= 0; i--) {
+                    s += P.cutoff_back - ((int)ql[a + i] - P.qbase);
+                    if (s < 0) break;
+                    if (s > mx) {
+                        mx = s;
+                        stop = i;
+                    }
                 }
             }
             if (start >= stop) start = stop = 0;
             st.qtrim = (uint32_t)(n - (stop - start));
-            st.b = (uint16_t)(a + stop);
-            st.a = (uint16_t)(a + start);
+            st.b = (uint16_t)(st.a + stop);
+            st.a = (uint16_t)(st.a + start);
             qsum = st.qtrim;
         }
         // header: SuffixRemover ops in order, then the id of Renamer.parse_name
-        const uint8_t* nm = P.md.name + P.md.name_off[idx];
-        int nl = (int)(P.md.name_end[idx] - P.md.name_off[idx]);
         for (int q = 0; q < P.n_suffix; q++) {
             const int sl = P.suffix_len[q];
             if (nl >= sl) {
@@ -375,12 +426,40 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishPa
                 if (eq) nl -= sl;
             }
         }
-        int p = 0;
-        while (p < nl && is_py_space(nm[p])) p++;
-        const int s0 = p;
-        while (p < nl && !is_py_space(nm[p])) p++;
-        const int e0 = p;
-        while (p < nl && is_py_space(nm[p])) p++;
+        // str.split(maxsplit=1): s0 = first non-blank, e0 = first blank behind it, p = first non-blank behind that;
+        // 16 header bytes per step, Python's whitespace set found with per-byte SIMD compares
+        int s0 = nl, e0 = nl, p = nl, state = 0;
+        for (int c = 0; c < nl && state < 3; c += 16) {
+            const uint4 v = c == 0 ? nm0 : fetch16(nm + c);
+            const uint32_t blank = space_bits16(v);
+            const uint32_t valid = nl - c >= 16 ? 0xFFFFu : ((1u << (nl - c)) - 1u);
+            uint32_t from = 0xFFFFu;  // positions still to look at in this chunk
+            if (state == 0) {
+                const uint32_t t = ~blank & valid & from;
+                if (t) {
+                    const int b = __ffs(t) - 1;
+                    s0 = c + b;
+                    from = 0xFFFEu << b;
+                    state = 1;
+                }
+            }
+            if (state == 1) {
+                const uint32_t t = blank & valid & from;
+                if (t) {
+                    const int b = __ffs(t) - 1;
+                    e0 = c + b;
+                    from = 0xFFFEu << b;
+                    state = 2;
+                }
+            }
+            if (state == 2) {
+                const uint32_t t = ~blank & valid & from;
+                if (t) {
+                    p = c + (__ffs(t) - 1);
+                    state = 3;
+                }
+            }
+        }
         if (P.has_rename && e0 > s0 && p < nl) {
             st.id_start = (uint16_t)s0;
             st.id_end = (uint16_t)e0;
@@ -587,6 +666,7 @@ __device__ __forceinline__ void word_split(const uint8_t* dst, uint32_t len, uin
     nw = (len - head) >> 2;
 }
 
+template <int G>
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__ EmitParams E) {
     const PairParams& P = E.pp;
     __shared__ EmitRec recs[2][CSQ_PAIR_BLOCK];
@@ -658,11 +738,21 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
     __syncthreads();
 
     // ---- phase 2 ----
+    // G lanes per record, 32 / G records side by side in a warp: the bookkeeping of a record (uniform within its
+    // group) is issued once per warp instruction for 32 / G records.  G = 16 halves the instruction count per
+    // record of the warp-per-record form (G = 32), which is bound by instruction issue.
+    constexpr int NG = 32 / G;              // records per warp pass
+    constexpr int UW = G == 32 ? 2 : G == 16 ? 3 : 5;  // unrolled word iterations: UW * G words of 4 bytes
+    constexpr int UI = 64 / G > 4 ? 4 : (G == 32 ? 2 : 2);  // unrolled id iterations: UI * G bytes
+    constexpr int MR = (23 + G - 1) / G;    // rounds over the 16 edge slots + 7 separators
+    const uint32_t sl = (uint32_t)lane % G, grp = (uint32_t)lane / G;
     bool id_mismatch = false;
-    uint32_t id0_len = 0, id0_v0 = 0, id0_v1 = 0;  // id of mate 1 of the current pair, as held by this lane
-    for (int q = 0; q < 32; q++) {
-        const int slot = wid * 32 + q;
-        if (base + slot >= P.n) break;
+    uint32_t id0_len = 0, id0_v[UI];        // id of mate 1 of the current pair, as held by this lane
+#pragma unroll
+    for (int u = 0; u < UI; u++) id0_v[u] = 0;
+    for (int q = 0; q < 32 / NG; q++) {
+        const int slot = wid * 32 + q * NG + (int)grp;
+        if (base + slot >= P.n) continue;  // no warp-wide operation below: groups may leave independently
         for (int mt = 0; mt < n_mates; mt++) {
             const EmitRec& R = recs[mt][slot];
             const MateDev& md = P.md[mt];
@@ -677,16 +767,16 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
                 S.pa = (poolA ? poolA : md.seq) + R.pa;
                 S.pb = (poolB ? poolB : md.seq) + R.pb;
                 const uint32_t e_name = 1u + R.id_len, e_seq = e_umi + 1 + seq_len, e_qual = e_seq + 3 + seq_len, total = e_qual + 1;
-                for (uint32_t p0 = lane; p0 < total; p0 += 32 * EMIT_UNROLL) {
+                for (uint32_t p0 = sl; p0 < total; p0 += G * EMIT_UNROLL) {
                     uint8_t ch[EMIT_UNROLL];
 #pragma unroll
                     for (int u = 0; u < EMIT_UNROLL; u++) {
-                        const uint32_t p = p0 + 32 * u;
+                        const uint32_t p = p0 + G * u;
                         ch[u] = p < total ? emit_byte(R, S, p, e_name, e_umi, e_seq, e_qual, true) : (uint8_t)0;
                     }
 #pragma unroll
                     for (int u = 0; u < EMIT_UNROLL; u++) {
-                        const uint32_t p = p0 + 32 * u;
+                        const uint32_t p = p0 + G * u;
                         if (p < total) out[p] = ch[u];
                     }
                 }
@@ -707,69 +797,80 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
             word_split(d_seq, seq_len, h_s, nw_s);
             word_split(d_qual, seq_len, h_q, nw_q);
             // ---- loads ----
-            // lanes 0..15: segment edges (4 groups of up to 3 bytes); lanes 16..22: the seven separator bytes
-            // (selects only: a chain of `lane ==` branches became a divergent jump table)
-            uint32_t misc_pos = 0xFFFFFFFFu;
-            uint32_t misc_val;
-            {
-                const uint32_t t = (uint32_t)lane - 16u;  // separator index for lanes 16..22
+            // single bytes: slots 0..15 = segment edges (4 groups of up to 3 bytes), slots 16..22 = the seven
+            // separator bytes; slot = sl + G * round  (selects only: a chain of `==` branches became a jump table)
+            uint32_t misc_pos[MR], misc_val[MR];
+#pragma unroll
+            for (int r = 0; r < MR; r++) {
+                const uint32_t ms = sl + (uint32_t)(G * r);
+                const uint32_t t = ms - 16u;               // separator index for slots 16..22
                 uint32_t sp = e_seq + (t - 3u);            // t = 3, 4, 5: "\n+\n"
                 sp = t == 0 ? 0u : sp;
                 sp = t == 1 ? e_name : sp;
                 sp = t == 2 ? e_umi : sp;
                 sp = t == 6 ? e_qual : sp;
                 const bool sep_ok = t < 7u && !(t == 1 && R.umi_len == 0);
-                misc_val = (uint32_t)(0x0A0A2B0A0A5F40ull >> (8u * (t & 7u))) & 0xFFu;  // "@_\n\n+\n\n"
-                const uint32_t g = (uint32_t)lane >> 2, x = (uint32_t)lane & 3u;
+                misc_val[r] = (uint32_t)(0x0A0A2B0A0A5F40ull >> (8u * (t & 7u))) & 0xFFu;  // "@_\n\n+\n\n"
+                const uint32_t g = ms >> 2, x = ms & 3u;
                 const bool is_q = (g & 2u) != 0, is_tail = (g & 1u) != 0;
                 const uint32_t h = is_q ? h_q : h_s, nw = is_q ? nw_q : nw_s;
                 const uint32_t o = is_tail ? h + 4u * nw + x : x;  // offset inside the segment
                 const uint32_t lim = is_tail ? seq_len : h;
-                const bool edge_ok = lane < 16 && x < 3 && o < lim;
-                if (edge_ok) misc_val = (is_q ? ql : sq)[o];
+                const bool edge_ok = ms < 16 && x < 3 && o < lim;
+                if (edge_ok) misc_val[r] = (is_q ? ql : sq)[o];
                 const uint32_t ep = (is_q ? e_seq + 3 : e_umi + 1) + o;
-                misc_pos = edge_ok ? ep : (sep_ok ? sp : 0xFFFFFFFFu);
+                misc_pos[r] = edge_ok ? ep : (sep_ok ? sp : 0xFFFFFFFFu);
             }
-            const uint32_t idv0 = (uint32_t)lane < id_len ? nm[lane] : 0u;
-            const uint32_t idv1 = (uint32_t)lane + 32u < id_len ? nm[lane + 32] : 0u;
+            uint32_t idv[UI];
+#pragma unroll
+            for (int u = 0; u < UI; u++) idv[u] = sl + (uint32_t)(G * u) < id_len ? nm[sl + G * u] : 0u;
             uint32_t umiv = 0;
-            if ((uint32_t)lane < lab) umiv = (uint32_t)lane < la ? pa[lane] : pb[lane - la];
+            if (sl < lab) umiv = sl < la ? pa[sl] : pb[sl - la];
             const uintptr_t sa_s = (uintptr_t)(sq + h_s), sa_q = (uintptr_t)(ql + h_q);
             const uint32_t* __restrict__ al_s = reinterpret_cast<const uint32_t*>(sa_s & ~(uintptr_t)3);
             const uint32_t* __restrict__ al_q = reinterpret_cast<const uint32_t*>(sa_q & ~(uintptr_t)3);
             const uint32_t sh_s = (uint32_t)(sa_s & 3u) * 8u, sh_q = (uint32_t)(sa_q & 3u) * 8u;
             uint32_t* __restrict__ o_s = reinterpret_cast<uint32_t*>(d_seq + h_s);
             uint32_t* __restrict__ o_q = reinterpret_cast<uint32_t*>(d_qual + h_q);
-            const uint32_t k1 = lane, k2 = k1 + 32;
-            uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;
-            if (k1 < nw_s) { a0 = al_s[k1]; a1 = al_s[k1 + 1]; }
-            if (k2 < nw_s) { b0 = al_s[k2]; b1 = al_s[k2 + 1]; }
-            if (k1 < nw_q) { c0 = al_q[k1]; c1 = al_q[k1 + 1]; }
-            if (k2 < nw_q) { d0 = al_q[k2]; d1 = al_q[k2 + 1]; }
+            uint32_t ws[UW][2], wq[UW][2];
+#pragma unroll
+            for (int u = 0; u < UW; u++) {
+                const uint32_t k = sl + (uint32_t)(G * u);
+                ws[u][0] = ws[u][1] = wq[u][0] = wq[u][1] = 0;
+                if (k < nw_s) { ws[u][0] = al_s[k]; ws[u][1] = al_s[k + 1]; }
+                if (k < nw_q) { wq[u][0] = al_q[k]; wq[u][1] = al_q[k + 1]; }
+            }
             if (P.check_ids) {  // PairedEndRenamer: the ids of the two mates must be identical
                 if (mt == 0) {
                     id0_len = id_len;
-                    id0_v0 = idv0;
-                    id0_v1 = idv1;
+#pragma unroll
+                    for (int u = 0; u < UI; u++) id0_v[u] = idv[u];
                 } else {
-                    id_mismatch |= id0_len != id_len || id0_v0 != idv0 || id0_v1 != idv1;
+                    id_mismatch |= id0_len != id_len;
+#pragma unroll
+                    for (int u = 0; u < UI; u++) id_mismatch |= id0_v[u] != idv[u];
                     const uint8_t* __restrict__ n0 = P.md[0].name + recs[0][slot].nm;
-                    for (uint32_t x = 64 + lane; x < id_len; x += 32) id_mismatch |= n0[x] != nm[x];
+                    for (uint32_t x = UI * G + sl; x < id_len; x += G) id_mismatch |= n0[x] != nm[x];
                 }
             }
             // ---- stores ----
-            if (misc_pos != 0xFFFFFFFFu) out[misc_pos] = (uint8_t)misc_val;
-            if ((uint32_t)lane < id_len) out[1 + lane] = (uint8_t)idv0;
-            if ((uint32_t)lane + 32u < id_len) out[33 + lane] = (uint8_t)idv1;
-            if ((uint32_t)lane < lab) out[e_name + 1 + lane] = (uint8_t)umiv;
-            if (k1 < nw_s) o_s[k1] = __funnelshift_r(a0, a1, sh_s);
-            if (k2 < nw_s) o_s[k2] = __funnelshift_r(b0, b1, sh_s);
-            if (k1 < nw_q) o_q[k1] = __funnelshift_r(c0, c1, sh_q);
-            if (k2 < nw_q) o_q[k2] = __funnelshift_r(d0, d1, sh_q);
-            // rare tails: ids > 64 bytes, UMI parts > 32 bytes, reads > 256 bases
-            for (uint32_t x = 64 + lane; x < id_len; x += 32) out[1 + x] = nm[x];
-            for (uint32_t x = 32 + lane; x < lab; x += 32) out[e_name + 1 + x] = x < la ? pa[x] : pb[x - la];
-            for (uint32_t k = 64 + lane; k < max(nw_s, nw_q); k += 32) {
+#pragma unroll
+            for (int r = 0; r < MR; r++)
+                if (misc_pos[r] != 0xFFFFFFFFu) out[misc_pos[r]] = (uint8_t)misc_val[r];
+#pragma unroll
+            for (int u = 0; u < UI; u++)
+                if (sl + (uint32_t)(G * u) < id_len) out[1 + sl + G * u] = (uint8_t)idv[u];
+            if (sl < lab) out[e_name + 1 + sl] = (uint8_t)umiv;
+#pragma unroll
+            for (int u = 0; u < UW; u++) {
+                const uint32_t k = sl + (uint32_t)(G * u);
+                if (k < nw_s) o_s[k] = __funnelshift_r(ws[u][0], ws[u][1], sh_s);
+                if (k < nw_q) o_q[k] = __funnelshift_r(wq[u][0], wq[u][1], sh_q);
+            }
+            // rare tails: long ids, long UMI parts, long reads
+            for (uint32_t x = UI * G + sl; x < id_len; x += G) out[1 + x] = nm[x];
+            for (uint32_t x = G + sl; x < lab; x += G) out[e_name + 1 + x] = x < la ? pa[x] : pb[x - la];
+            for (uint32_t k = UW * G + sl; k < max(nw_s, nw_q); k += G) {
                 if (k < nw_s) o_s[k] = __funnelshift_r(al_s[k], al_s[k + 1], sh_s);
                 if (k < nw_q) o_q[k] = __funnelshift_r(al_q[k], al_q[k + 1], sh_q);
             }
@@ -859,9 +960,15 @@ cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint
     return cudaGetLastError();
 }
 
-cudaError_t csq_launch_emit(const EmitParams& p, cudaStream_t stream) {
+cudaError_t csq_launch_emit(const EmitParams& p, int lanes_per_record, cudaStream_t stream) {
     if (p.pp.n == 0) return cudaSuccess;
-    k_emit<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
+    const dim3 grid((p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK), block(CSQ_PAIR_BLOCK);
+    if (lanes_per_record == 32)
+        k_emit<32><<<grid, block, 0, stream>>>(p);
+    else if (lanes_per_record == 8)
+        k_emit<8><<<grid, block, 0, stream>>>(p);
+    else
+        k_emit<16><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -525,7 +525,8 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     ep.block_off = (const unsigned long long*)s.block_off.p;
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < 2; m++) ep.out[d][m] = (uint8_t*)s.out[d][m].p;
-    CUDA_TRY((plan->flags & CSQ_PLAN_EMIT_REC) ? csq_launch_emit_rec(ep, st) : csq_launch_emit(ep, st));
+    CUDA_TRY((plan->flags & CSQ_PLAN_EMIT_REC) ? csq_launch_emit_rec(ep, st)
+                                                : csq_launch_emit(ep, (plan->flags & CSQ_PLAN_EMIT_G32) ? 32 : (plan->flags & CSQ_PLAN_EMIT_G8) ? 8 : 16, st));
     plan->launches += s.n ? 1 : 0;
     if (kt) kt->mark("k_emit");
     return 0;
