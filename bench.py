@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="g16", choices=["g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); g16 (16 lanes per record) is the product default")
+    ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
     ap.add_argument("--input", default="text", choices=["text", "soa"], help="batch form handed to the library")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -185,7 +186,7 @@ def main():
 
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
-    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"g16": 0, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit])
+    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"g16": 0, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0))
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.

@@ -43,6 +43,7 @@ PLAN_NO_PREFILTER = 2
 PLAN_EMIT_REC = 8
 PLAN_EMIT_G32 = 16
 PLAN_EMIT_G8 = 32
+PLAN_ONE_STREAM = 64
 
 
 class csq_op(C.Structure):

@@ -78,7 +78,9 @@ struct Slot {
     cudaEvent_t ev[6] = {};
     DevBuf seq[2], qual[2], seq_off[2], seq_len[2], name[2], name_off[2], state[2], matches[2];
     DevBuf dest, block_tot, block_cnt, block_off, totals, out[CSQ_N_DEST][2];
-    DevBuf list, list_count;  // prefilter survivors (indices) and their number
+    DevBuf list[2], list_count[2];  // per mate: prefilter survivors (indices) and their number
+    cudaStream_t stream2 = nullptr;  // chain of mate 2
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // text batches (csq_submit_text): the FASTQ bytes as they came, and the record index k_records builds
     DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16
     uint64_t text_bytes[2] = {0, 0};
@@ -324,8 +326,10 @@ int ensure_common(csq_plan* plan, Slot& s, uint32_t n) {
     if ((rc = s.block_off.ensure((size_t)nblk * 64 + 64))) return rc;
     if ((rc = s.totals.ensure(16 * 8))) return rc;
     if (!(plan->flags & CSQ_PLAN_NO_PREFILTER)) {
-        if ((rc = s.list.ensure((size_t)n * CSQ_PF_BINS * 6 + 64))) return rc;
-        if ((rc = s.list_count.ensure(4 * CSQ_PF_BINS + 16))) return rc;
+        for (int m = 0; m < plan->n_mates; m++) {
+            if ((rc = s.list[m].ensure((size_t)n * CSQ_PF_BINS * 6 + 64))) return rc;
+            if ((rc = s.list_count[m].ensure(4 * CSQ_PF_BINS + 16))) return rc;
+        }
     }
     return 0;
 }
@@ -431,70 +435,89 @@ PairParams pair_params(csq_plan* plan, Slot& s) {
     return pp;
 }
 
-// align ... scan, then the 12 totals + error flag to pinned host memory
-int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
+// One mate of a batch: parse (text batches), then prefilter / align per ALIGN op, then finish - all on `st`.
+int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t st) {
     const uint32_t n = s.n;
-    const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
-    if (kt) kt->mark("begin");
     if (s.text_mode) {
         // FASTQ text -> record index (parse.cu); nl_total[m] at parse_misc + 4 m, perr[m] at parse_misc + 16 + 8 m
-        CUDA_TRY(cudaMemsetAsync((uint8_t*)s.parse_misc.p + 16, 0xFF, 16, st));
-        for (int m = 0; m < plan->n_mates; m++) {
-            ParseParams pp;
-            pp.text = (const uint8_t*)s.text[m].p + TEXT_FRONT_PAD;
-            pp.bytes = s.text_bytes[m];
-            pp.n = n;
-            pp.nl = (uint32_t*)s.nl[m].p;
-            pp.nl_total = (uint32_t*)s.parse_misc.p + m;
-            pp.seq_off = (uint32_t*)s.seq_off[m].p;
-            pp.qual_off = (uint32_t*)s.qual_off[m].p;
-            pp.seq_len = (uint32_t*)s.seq_len[m].p;
-            pp.name_off = (uint32_t*)s.name_off[m].p;
-            pp.name_end = (uint32_t*)s.name_end[m].p;
-            pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
-            CUDA_TRY(csq_launch_parse(pp, (uint32_t*)s.tiles[m].p, (uint16_t*)s.masks[m].p, st));
-            plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
-            if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
-        }
-        CUDA_TRY(cudaMemcpyAsync(s.totals_host + 14, (uint8_t*)s.parse_misc.p + 16, 16, cudaMemcpyDeviceToHost, st));
+        ParseParams pp;
+        pp.text = (const uint8_t*)s.text[m].p + TEXT_FRONT_PAD;
+        pp.bytes = s.text_bytes[m];
+        pp.n = n;
+        pp.nl = (uint32_t*)s.nl[m].p;
+        pp.nl_total = (uint32_t*)s.parse_misc.p + m;
+        pp.seq_off = (uint32_t*)s.seq_off[m].p;
+        pp.qual_off = (uint32_t*)s.qual_off[m].p;
+        pp.seq_len = (uint32_t*)s.seq_len[m].p;
+        pp.name_off = (uint32_t*)s.name_off[m].p;
+        pp.name_end = (uint32_t*)s.name_end[m].p;
+        pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
+        CUDA_TRY(csq_launch_parse(pp, (uint32_t*)s.tiles[m].p, (uint16_t*)s.masks[m].p, st));
+        plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
+        if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
     }
-    for (int m = 0; m < plan->n_mates; m++) {
-        MateProgram& mp = plan->prog[m];
-        for (Segment& sg : mp.segs) {
-            AlignParams ap = sg.ap;
-            ap.md = mate_dev(s, m);
-            ap.n = n;
-            ap.list = nullptr;
-            ap.list_count = nullptr;
-            ap.count_cells = 1;
-            ap.counters = plan->counters;
-            ap.matches = (plan->flags & CSQ_PLAN_KEEP_MATCHES)
-                             ? (csq_match*)s.matches[m].p + (size_t)mp.align_slot[sg.op_index] * n
-                             : nullptr;
-            if (!(plan->flags & CSQ_PLAN_NO_PREFILTER) && n) {
-                // reject-only bit-parallel filter; the exact DP then runs on the compacted survivors
-                CUDA_TRY(cudaMemsetAsync(s.list_count.p, 0, 4 * CSQ_PF_BINS, st));
-                CUDA_TRY(csq_launch_prefilter(ap, (uint32_t*)s.list.p, (uint32_t*)s.list_count.p, st));
-                plan->launches += 1;
-                if (kt) kt->mark(sg.pf_name);
-                ap.list = (const uint32_t*)s.list.p;
-                ap.list_count = (const uint32_t*)s.list_count.p;
-                ap.first = 0;   // the prefilter initialised the state and ran the scalar ops
-                ap.n_pre = 0;
-                ap.count_cells = 0;
-            }
-            CUDA_TRY(csq_launch_align(ap, n, st));
-            plan->launches += n ? 1 : 0;
-            if (kt) kt->mark(sg.name);
+    MateProgram& mp = plan->prog[m];
+    for (Segment& sg : mp.segs) {
+        AlignParams ap = sg.ap;
+        ap.md = mate_dev(s, m);
+        ap.n = n;
+        ap.list = nullptr;
+        ap.list_count = nullptr;
+        ap.count_cells = 1;
+        ap.counters = plan->counters;
+        ap.matches = (plan->flags & CSQ_PLAN_KEEP_MATCHES)
+                         ? (csq_match*)s.matches[m].p + (size_t)mp.align_slot[sg.op_index] * n
+                         : nullptr;
+        if (!(plan->flags & CSQ_PLAN_NO_PREFILTER) && n) {
+            // reject-only bit-parallel filter; the exact DP then runs on the compacted survivors
+            CUDA_TRY(cudaMemsetAsync(s.list_count[m].p, 0, 4 * CSQ_PF_BINS, st));
+            CUDA_TRY(csq_launch_prefilter(ap, (uint32_t*)s.list[m].p, (uint32_t*)s.list_count[m].p, st));
+            plan->launches += 1;
+            if (kt) kt->mark(sg.pf_name);
+            ap.list = (const uint32_t*)s.list[m].p;
+            ap.list_count = (const uint32_t*)s.list_count[m].p;
+            ap.first = 0;   // the prefilter initialised the state and ran the scalar ops
+            ap.n_pre = 0;
+            ap.count_cells = 0;
         }
-        FinishParams fp = mp.fin;
-        fp.md = mate_dev(s, m);
-        fp.n = n;
-        fp.counters = plan->counters;
-        CUDA_TRY(csq_launch_finish(fp, st));
+        CUDA_TRY(csq_launch_align(ap, n, st));
         plan->launches += n ? 1 : 0;
-        if (kt) kt->mark(m == 0 ? "k_finish.r1" : "k_finish.r2");
+        if (kt) kt->mark(sg.name);
     }
+    FinishParams fp = mp.fin;
+    fp.md = mate_dev(s, m);
+    fp.n = n;
+    fp.counters = plan->counters;
+    CUDA_TRY(csq_launch_finish(fp, st));
+    plan->launches += n ? 1 : 0;
+    if (kt) kt->mark(m == 0 ? "k_finish.r1" : "k_finish.r2");
+    return 0;
+}
+
+// parse ... scan, then the 12 totals + error flags to pinned host memory.
+// The two mates of a pair do not meet before k_pair: with a second stream (`st2`, nullptr = off) the chain of
+// mate 2 runs beside the chain of mate 1, so that the single-CTA scans and the register-bound k_align<100>
+// (2 CTAs per SM) of one mate share the machine with the other mate's kernels.  Per-kernel event timing
+// (`kt`) keeps everything on one stream.
+int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st, cudaStream_t st2 = nullptr) {
+    const uint32_t n = s.n;
+    const uint32_t nblk = (n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK;
+    const bool dual = st2 != nullptr && !kt && plan->n_mates == 2 && n > 0 && !(plan->flags & CSQ_PLAN_ONE_STREAM);
+    int rc;
+    if (kt) kt->mark("begin");
+    if (s.text_mode) CUDA_TRY(cudaMemsetAsync((uint8_t*)s.parse_misc.p + 16, 0xFF, 16, st));
+    if (dual) {
+        CUDA_TRY(cudaEventRecord(s.ev_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(st2, s.ev_fork, 0));
+    }
+    for (int m = 0; m < plan->n_mates; m++)
+        if ((rc = enqueue_mate(plan, s, m, kt, (dual && m == 1) ? st2 : st))) return rc;
+    if (dual) {
+        CUDA_TRY(cudaEventRecord(s.ev_join, st2));
+        CUDA_TRY(cudaStreamWaitEvent(st, s.ev_join, 0));
+    }
+    if (s.text_mode)
+        CUDA_TRY(cudaMemcpyAsync(s.totals_host + 14, (uint8_t*)s.parse_misc.p + 16, 16, cudaMemcpyDeviceToHost, st));
     PairParams pp = pair_params(plan, s);
     CUDA_TRY(csq_launch_pair(pp, st));
     plan->launches += n ? 1 : 0;
@@ -628,6 +651,9 @@ int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, 
     for (int i = 0; i < CSQ_N_SLOTS && e == cudaSuccess; i++) {
         Slot& s = plan->slots[i];
         e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming);
         for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&s.ev[k]);
         if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.totals_host, 16 * 8, cudaHostAllocDefault);
         if (e == cudaSuccess) memset(s.totals_host, 0, 16 * 8);
@@ -651,7 +677,11 @@ void csq_plan_destroy(csq_plan* plan) {
             s.name[m].release(); s.name_off[m].release(); s.state[m].release(); s.matches[m].release();
             for (int d = 0; d < CSQ_N_DEST; d++) s.out[d][m].release();
         }
-        s.list.release(); s.list_count.release(); s.parse_misc.release();
+        s.parse_misc.release();
+        for (int m = 0; m < 2; m++) { s.list[m].release(); s.list_count[m].release(); }
+        if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+        if (s.ev_join) cudaEventDestroy(s.ev_join);
+        if (s.stream2) cudaStreamDestroy(s.stream2);
         for (int m = 0; m < 2; m++) {
             s.text[m].release(); s.qual_off[m].release(); s.name_end[m].release(); s.nl[m].release(); s.tiles[m].release(); s.masks[m].release();
         }
@@ -675,7 +705,7 @@ int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* 
     CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
     if ((rc = upload(plan, s, in))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
-    if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream, s.stream2))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
     s.pending = out;
     return 0;
@@ -702,7 +732,7 @@ int csq_submit_text(csq_plan* plan, int slot, const csq_batch_text* in, csq_batc
     CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
     if ((rc = upload_text(plan, s, in))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
-    if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream, s.stream2))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
     s.pending = out;
     return 0;
@@ -794,7 +824,7 @@ int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
     Slot& s = plan->slots[slot];
     int rc;
     // sizing pass (not timed): totals are needed on the host before the emit buffers exist
-    if ((rc = enqueue_front(plan, s, nullptr, s.stream))) return rc;
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream, s.stream2))) return rc;
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     if ((rc = check_device_error(s))) return rc;
     if ((rc = size_outputs(s))) return rc;
@@ -811,7 +841,7 @@ int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter) {
     CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
     for (int it = 1; it < iters; it++) {
         kt.on = (it == iters - 1);
-        if ((rc = enqueue_front(plan, s, &kt, s.stream))) return rc;
+        if ((rc = enqueue_front(plan, s, kt.on ? &kt : nullptr, s.stream, s.stream2))) return rc;
         if ((rc = enqueue_emit(plan, s, &kt, s.stream))) return rc;
     }
     CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
@@ -840,7 +870,7 @@ int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, floa
     for (int i = 0; i < n_slots; i++) {  // untimed sizing pass: emit buffers must exist
         Slot& s = plan->slots[slots[i]];
         CUDA_TRY(cudaStreamSynchronize(s.stream));
-        if ((rc = enqueue_front(plan, s, nullptr, st))) return rc;
+        if ((rc = enqueue_front(plan, s, nullptr, st, s0.stream2))) return rc;
         CUDA_TRY(cudaStreamSynchronize(st));
         if ((rc = check_device_error(s))) return rc;
         if ((rc = size_outputs(s))) return rc;
@@ -856,7 +886,7 @@ int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, floa
     for (int it = 0; it < steps; it++) {
         Slot& s = plan->slots[slots[it % n_slots]];
         kt.on = (it == steps - 1);
-        if ((rc = enqueue_front(plan, s, &kt, st))) return rc;
+        if ((rc = enqueue_front(plan, s, kt.on ? &kt : nullptr, st, s0.stream2))) return rc;
         if ((rc = enqueue_emit(plan, s, &kt, st))) return rc;
     }
     CUDA_TRY(cudaEventRecord(s0.ev[1], st));
