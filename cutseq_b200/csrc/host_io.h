@@ -56,10 +56,50 @@ struct MateParser {
 uint64_t count_newlines(const uint8_t* p, size_t n);
 uint64_t after_kth_newline(const uint8_t* p, size_t n, uint64_t k);  // offset one past the k-th '\n', UINT64_MAX if fewer
 
+// gzip / DEFLATE decoder (inflate.cpp): whole compressed input in memory, output into the caller's buffer in
+// pieces of any size.
+class Inflater {
+   public:
+    Inflater();
+    ~Inflater();
+    Inflater(const Inflater&) = delete;
+    Inflater& operator=(const Inflater&) = delete;
+    void reset(const uint8_t* data, size_t n);
+    long read(uint8_t* dst, size_t n);  // bytes produced (< n only at the end of the input), -1 on error
+    const char* error() const { return err_ ? err_ : ""; }
+
+   private:
+    struct Tables;
+    enum State { S_HEADER, S_BLOCK, S_STORED, S_HUFFMAN, S_TRAILER, S_DONE, S_ERROR };
+    bool need(int n);
+    uint32_t take(int n);
+    void align_to_byte();
+    bool fail(const char* msg);
+    bool parse_header();
+    bool parse_block_header();
+    uint8_t hist_byte(const uint8_t* base, const uint8_t* out, uint32_t dist) const;
+    uint8_t* run_huffman(uint8_t* base, uint8_t* out, uint8_t* out_end);
+    Tables* t_;
+    const uint8_t *in_ = nullptr, *in_end_ = nullptr;
+    uint64_t bitbuf_ = 0;
+    int bits_ = 0;
+    State state_ = S_HEADER;
+    bool last_block_ = false;
+    uint32_t stored_left_ = 0, pend_len_ = 0, pend_dist_ = 0;
+    uint8_t win_[32768];
+    size_t win_len_ = 0;
+    uint32_t crc_ = 0, isize_ = 0;
+    uint64_t members_ = 0;
+    const char* err_ = nullptr;
+};
+
 struct RawSource {  // decompressed byte stream of a plain or gzip (multi-member) file, read into caller memory
     int fd = -1;
     bool gz = false, file_eof = false, stream_end = false;
-    void* zs = nullptr;
+    void* zs = nullptr;            // zlib stream (CSQ_ZLIB_INFLATE=1: A/B runs against the built-in decoder)
+    Inflater* fast = nullptr;      // built-in decoder over the mmap-ed file
+    const uint8_t* map = nullptr;
+    size_t map_len = 0;
     std::vector<uint8_t> inbuf;
     size_t in_pos = 0, in_len = 0;
     std::string name;

@@ -8,7 +8,10 @@
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -65,6 +68,11 @@ uint64_t after_kth_newline(const uint8_t* p, size_t n, uint64_t k) {
 RawSource::~RawSource() { close(); }
 
 void RawSource::close() {
+    delete fast;
+    fast = nullptr;
+    if (map) munmap((void*)map, map_len);
+    map = nullptr;
+    map_len = 0;
     if (zs) {
         inflateEnd((z_stream*)zs);
         delete (z_stream*)zs;
@@ -101,6 +109,20 @@ int RawSource::open(const char* path) {
     file_eof = stream_end = false;
     if (fill() < 0) return CSQ_ERR_IO;
     gz = in_len >= 2 && inbuf[0] == 0x1f && inbuf[1] == 0x8b;
+    const char* use_zlib = getenv("CSQ_ZLIB_INFLATE");
+    if (gz && !(use_zlib && use_zlib[0] == '1')) {
+        // the built-in decoder sees the whole compressed file at once
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || sb.st_size <= 0) return io_fail(CSQ_ERR_IO, "cannot stat %s: %s", path, strerror(errno));
+        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return io_fail(CSQ_ERR_IO, "cannot map %s: %s", path, strerror(errno));
+        madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+        map = (const uint8_t*)m;
+        map_len = (size_t)sb.st_size;
+        fast = new Inflater();
+        fast->reset(map, map_len);
+        return 0;
+    }
     if (gz) {
         z_stream* z = new z_stream();
         memset(z, 0, sizeof(*z));
@@ -134,6 +156,14 @@ long RawSource::read(uint8_t* dst, size_t n) {
             done += (size_t)got;
         }
         return (long)done;
+    }
+    if (fast) {
+        const long got = fast->read(dst, n);
+        if (got < 0) {
+            io_fail(CSQ_ERR_IO, "%s: %s", name.c_str(), fast->error());
+            return -1;
+        }
+        return got;
     }
     z_stream* z = (z_stream*)zs;
     while (done < n) {
@@ -356,6 +386,38 @@ int csq_text_reader_next(csq_text_reader* r, int buffer, uint32_t max_reads, csq
 }
 
 void csq_text_reader_close(csq_text_reader* r) { delete r; }
+
+// gzip data in memory -> dst, produced in pieces of `piece` bytes (exercises the decoder's resumption points)
+int csq_gunzip_mem(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t piece, uint64_t* out_n) {
+    if (!src || !dst || !out_n || piece == 0) {
+        csq_set_error("bad argument");
+        return CSQ_ERR_INVALID;
+    }
+    Inflater inf;
+    inf.reset(src, (size_t)n);
+    uint64_t total = 0;
+    for (;;) {
+        const uint64_t want = cap - total < piece ? cap - total : piece;
+        if (want == 0) {  // is there more?
+            uint8_t probe;
+            const long g = inf.read(&probe, 1);
+            if (g < 0) break;
+            *out_n = total;
+            if (g == 0) return 0;
+            csq_set_error("output buffer too small");
+            return CSQ_ERR_CAPACITY;
+        }
+        const long got = inf.read(dst + total, (size_t)want);
+        if (got < 0) break;
+        total += (uint64_t)got;
+        if ((uint64_t)got < want) {
+            *out_n = total;
+            return 0;
+        }
+    }
+    csq_set_error(inf.error());
+    return CSQ_ERR_IO;
+}
 
 uint64_t csq_count_newlines(const uint8_t* text, uint64_t n_bytes) { return text ? count_newlines(text, (size_t)n_bytes) : 0; }
 

@@ -72,6 +72,7 @@ def lib():
         L.csq_count_newlines.restype = C.c_uint64
         L.csq_after_kth_newline.argtypes = [vp, C.c_uint64, C.c_uint64]
         L.csq_after_kth_newline.restype = C.c_uint64
+        L.csq_gunzip_mem.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, u64p]
         L.csq_format_fastq.argtypes = [C.POINTER(A.csq_mate_in), u32, vp, C.c_uint64, u64p]
     if hasattr(L, "csq_synth_batch"):
         L.csq_synth_batch.argtypes = [C.POINTER(A.csq_synth), C.c_uint64, u32, i32, C.POINTER(A.csq_batch_in)]

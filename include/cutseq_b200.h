@@ -304,6 +304,8 @@ void csq_text_reader_close(csq_text_reader* r);
  * one past the k-th '\n' (k >= 1), or UINT64_MAX when there are fewer. */
 uint64_t csq_count_newlines(const uint8_t* text, uint64_t n_bytes);
 uint64_t csq_after_kth_newline(const uint8_t* text, uint64_t n_bytes, uint64_t k);
+/* gzip data in memory -> dst, decoded in pieces of `piece` bytes with the library's own inflate (tests). */
+int csq_gunzip_mem(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t piece, uint64_t* out_n);
 /* SoA batch -> FASTQ text of one mate ("@name\nseq\n+\nqual\n"), for tests and benchmarks. */
 int csq_format_fastq(const csq_mate_in* mate, uint32_t n_reads, uint8_t* out, uint64_t capacity,
                      uint64_t* bytes);

@@ -1,0 +1,114 @@
+"""The library's own gzip / DEFLATE decoder (csrc/inflate.cpp, csq_gunzip_mem) against zlib - runs without a GPU.
+
+Every block type (stored, fixed, dynamic), every resumption point of the piece-wise API (pieces of 1 byte to
+1 MiB, i.e. output buffers that end inside a match, right at a block end, ...), concatenated members, header
+flags, small windows, truncation and single-bit corruption."""
+
+import ctypes as C
+import gzip
+import io
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from cutseq_b200 import native
+
+
+def gunzip(data: bytes, piece: int, cap: int):
+    L = native.lib()
+    src = np.frombuffer(data + b"\0" * 16, dtype=np.uint8)
+    dst = np.zeros(max(cap, 1), dtype=np.uint8)
+    n = C.c_uint64()
+    rc = L.csq_gunzip_mem(src.ctypes.data, len(data), dst.ctypes.data, cap, piece, C.byref(n))
+    if rc:
+        raise native.NativeError(rc, L.csq_last_error().decode())
+    return dst[: n.value].tobytes()
+
+
+def gz(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=31):
+    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+def fastq(n, seed=3):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        ln = rng.randint(20, 150)
+        out.append(f"@read{i} {rng.randint(0, 99999)}\n{''.join(rng.choice('ACGT') for _ in range(ln))}\n+\n"
+                   f"{''.join(rng.choice('I9-#') for _ in range(ln))}\n")
+    return "".join(out).encode()
+
+
+CASES = {
+    "empty": b"", "one": b"a", "text": b"hello world\n" * 1000, "random": os.urandom(60000), "fastq": fastq(2000),
+    "zeros": bytes(70000), "period2": b"ab" * 40000, "period3": b"abc" * 30000, "period7": b"abcdefg" * 15000,
+    "bytes": bytes(range(256)) * 200,
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_round_trip_all_block_types_and_piece_sizes(name):
+    data = CASES[name]
+    for level in (0, 1, 6, 9):
+        for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+            comp = gz(data, level, strategy)
+            for piece in (1, 7, 300, 319, 320, 321, 4096, 1 << 20):
+                if piece < 300 and len(data) > 50000 and (level, strategy) != (6, zlib.Z_DEFAULT_STRATEGY):
+                    continue
+                assert gunzip(comp, piece, len(data) + 10) == data, (name, level, strategy, piece)
+
+
+def test_members_header_flags_padding_and_windows():
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="name.txt", mode="wb", fileobj=buf, mtime=0) as f:
+        f.write(b"first member\n" * 100)
+    m2 = gz(fastq(500, seed=4), 1)
+    both = buf.getvalue() + m2 + b"\0" * 50
+    want = b"first member\n" * 100 + gzip.decompress(m2)
+    for piece in (1, 33, 1000, 1 << 20):
+        assert gunzip(both, piece, len(want) + 5) == want
+    big = fastq(12000, seed=5)
+    for wbits in (25, 28, 31):  # 512-byte, 4 KiB and 32 KiB windows
+        assert gunzip(gz(big, 9, wbits=wbits), 5000, len(big) + 1) == big
+
+
+def test_truncation_corruption_and_capacity_are_errors():
+    rng = random.Random(9)
+    data = fastq(2000, seed=6)
+    comp = gz(data, 6)
+    for cut in (5, 12, len(comp) // 2, len(comp) - 9, len(comp) - 1):
+        with pytest.raises(native.NativeError):
+            gunzip(comp[:cut], 1000, 1 << 20)
+    for _ in range(200):
+        b = bytearray(comp)
+        b[rng.randrange(10, len(b))] ^= 1 << rng.randrange(8)
+        with pytest.raises(native.NativeError):
+            gunzip(bytes(b), 1000, 1 << 21)
+    with pytest.raises(native.NativeError):
+        gunzip(comp, 1000, 100)
+    with pytest.raises(native.NativeError):
+        gunzip(b"", 1000, 100)
+    with pytest.raises(native.NativeError):
+        gunzip(b"not gzip at all", 1000, 100)
+
+
+def test_text_reader_built_in_and_zlib_agree(tmp_path, monkeypatch):
+    data = fastq(5000, seed=7)
+    p = tmp_path / "r.fq.gz"
+    p.write_bytes(gz(data[: len(data) // 3], 1) + gz(data[len(data) // 3:], 9))
+    outs = []
+    for use_zlib in ("0", "1"):
+        monkeypatch.setenv("CSQ_ZLIB_INFLATE", use_zlib)
+        got = b""
+        with native.TextReader(str(p)) as r:
+            while True:
+                n, texts, _ = r.next(777)
+                if n == 0:
+                    break
+                got += texts[0]
+        outs.append(got)
+    assert outs[0] == outs[1] == data
