@@ -118,6 +118,47 @@ def cpu_leg(prog, steps, warmup, sample_pairs, first_index=0):
     return steps * sample_pairs / dt, threads, dt / steps
 
 
+def files_leg(prog, pairs):
+    """FASTQ files on disk -> csq_run_files -> trimmed FASTQ files, plain and .gz; host stages reported separately."""
+    import shutil
+    import tempfile
+
+    from cutseq_b200 import native
+    from scripts import bench_files
+
+    tmp = tempfile.mkdtemp()
+    out = {}
+    try:
+        batch = native.synth_batch(2, pairs, first_index=0, buffer=14)
+        for variant in ("plain", "gz"):
+            ext = ".fq.gz" if variant == "gz" else ".fq"
+            ins = [os.path.join(tmp, f"in_R{m}{ext}") for m in (1, 2)]
+            bench_files.write_fastq_from_batch(batch, ins, variant == "gz")
+            outs = {"trimmed": [os.path.join(tmp, f"out_trimmed_R{m}{ext}") for m in (1, 2)],
+                    "short": [os.path.join(tmp, f"out_short_R{m}{ext}") for m in (1, 2)]}
+            best = None
+            for rep in range(2):
+                t0 = time.time()
+                counters, timing = native.run_files(prog, ins, outs, gpus=1, threads=os.cpu_count() or 4)
+                wall = time.time() - t0
+                if best is None or wall < best[0]:
+                    best = (wall, timing)
+            wall, timing = best
+            out[variant] = {"pairs_per_s": pairs / wall, "wall_s": wall, "read_inflate_s": timing.read_inflate,
+                            "gpu_h2d_kernels_d2h_s": timing.h2d_kernels_d2h, "gpu_kernels_s": timing.kernels,
+                            "deflate_write_s": timing.write_deflate, "input_bytes": sum(os.path.getsize(p) for p in ins)}
+            for p in ins + outs["trimmed"] + outs["short"]:
+                if os.path.exists(p):
+                    os.remove(p)
+        out["pairs"] = pairs
+        out["host_threads"] = os.cpu_count()
+        out["note"] = ("whole run incl. plan set-up and pinned allocations (~0.5 s fixed); stage seconds are busy times of "
+                       "overlapping stages; .gz = one gzip member per input file (level 1), own inflate, zlib level-1 members out")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -149,6 +190,8 @@ def main():
     ap.add_argument("--batches", type=int, default=N_BATCHES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
+    ap.add_argument("--file-pairs", type=int, default=2_000_000, help="pairs in the whole-file leg")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="g16", choices=["g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); g16 (16 lanes per record) is the product default")
     ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
@@ -358,6 +401,14 @@ def main():
     # the dominant kernel of the step decides which of the two is THE roofline line
     roofline = roofline_hbm if (emit_ms and (not dom_dp or emit_ms >= dom_dp["ms"])) else roofline_dp
 
+    # ---- whole files: read / inflate, GPU chain, deflate / write (N = 1, rank 0; reported separately) ----
+    files = None
+    if not args.no_files and world == 1:
+        try:
+            files = files_leg(prog, args.file_pairs)
+        except Exception as exc:  # the headline numbers must not die with a full /tmp
+            files = {"error": repr(exc)}
+
     cpu = None
     if not args.no_cpu and world == 1:
         v, threads, step_s = cpu_leg(prog, 3, 1, 100_000)
@@ -377,7 +428,7 @@ def main():
                    "prefilter": not args.no_prefilter},
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
         "roofline": roofline, "roofline_dp": roofline_dp, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
-        "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timed_launches), "clocks": clocks,
+        "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
         "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
     }
     sys.stdout.flush()
