@@ -388,6 +388,13 @@ int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
         if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
             if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
         if (n) {
+            // the padding is read (and masked off) by the 16-byte fetches: keep it defined
+            for (DevBuf* b : {&s.seq[m], &s.qual[m]}) {
+                CUDA_TRY(cudaMemsetAsync(b->p, 0, POOL_PAD, s.stream));
+                CUDA_TRY(cudaMemsetAsync((uint8_t*)b->p + POOL_PAD + mi.seq_bytes, 0, POOL_PAD, s.stream));
+            }
+            CUDA_TRY(cudaMemsetAsync(s.name[m].p, 0, POOL_PAD, s.stream));
+            CUDA_TRY(cudaMemsetAsync((uint8_t*)s.name[m].p + POOL_PAD + mi.name_bytes, 0, POOL_PAD, s.stream));
             CUDA_TRY(cudaMemcpyAsync((uint8_t*)s.seq[m].p + POOL_PAD, mi.seq, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
             CUDA_TRY(cudaMemcpyAsync((uint8_t*)s.qual[m].p + POOL_PAD, mi.qual, mi.seq_bytes, cudaMemcpyHostToDevice, s.stream));
             CUDA_TRY(cudaMemcpyAsync(s.seq_off[m].p, mi.seq_off, (size_t)n * 4, cudaMemcpyHostToDevice, s.stream));
