@@ -193,7 +193,8 @@ def main():
     ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
     ap.add_argument("--file-pairs", type=int, default=2_000_000, help="pairs in the whole-file leg")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
-    ap.add_argument("--emit", default="g16", choices=["g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); g16 (16 lanes per record) is the product default")
+    ap.add_argument("--emit", default="stage", choices=["stage", "g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
+    ap.add_argument("--parse", default="onepass", choices=["onepass", "v1"], help="text-batch parse (A/B runs); onepass (look-back kernel) is the product default")
     ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
     ap.add_argument("--input", default="text", choices=["text", "soa"], help="batch form handed to the library")
     args = ap.parse_args()
@@ -229,7 +230,8 @@ def main():
 
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
-    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"g16": 0, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0))
+    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0)
+                       | (A.PLAN_PARSE_V1 if args.parse == "v1" else 0))
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
@@ -425,7 +427,7 @@ def main():
                                f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
                                f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
-                   "prefilter": not args.no_prefilter},
+                   "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse},
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
         "roofline": roofline, "roofline_dp": roofline_dp, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
         "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,

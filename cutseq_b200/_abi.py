@@ -44,6 +44,8 @@ PLAN_EMIT_REC = 8
 PLAN_EMIT_G32 = 16
 PLAN_EMIT_G8 = 32
 PLAN_ONE_STREAM = 64
+PLAN_PARSE_V1 = 128
+PLAN_EMIT_G16 = 256
 
 
 class csq_op(C.Structure):

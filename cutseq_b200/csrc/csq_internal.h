@@ -54,7 +54,7 @@ struct ParseParams {  // FASTQ text of one mate -> record index (parse.cu)
     const uint8_t* text;
     uint64_t bytes;
     uint32_t n;             // records the host counted (4 n line ends)
-    uint32_t* nl;           // [4 n] byte offsets of the line ends, 16-byte aligned
+    uint32_t* nl;           // four-kernel form: [4 n] byte offsets of the line ends, 16-byte aligned; one-pass form: [n] scratch
     uint32_t* nl_total;     // [1] line ends found
     uint32_t *seq_off, *qual_off, *seq_len, *name_off, *name_end;
     unsigned long long* perr;  // smallest (record << 3 | kind) of a malformed record, ~0 when clean
@@ -133,8 +133,9 @@ cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream);
 cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
                             unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream);
 cudaError_t csq_launch_emit(const EmitParams& p, int lanes_per_record, cudaStream_t stream);  // kernels.cu: 32 / 16 / 8 lanes per record
+cudaError_t csq_launch_emit_stage(const EmitParams& p, cudaStream_t stream); // emit_stage.cu: staged through shared memory (default)
 cudaError_t csq_launch_emit_rec(const EmitParams& p, cudaStream_t stream);   // emit.cu: thread per pair, 16-byte chunks (CSQ_PLAN_EMIT_REC)
-cudaError_t csq_launch_parse(const ParseParams& p, uint32_t* tile_cnt, uint16_t* masks, cudaStream_t stream);
+cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* masks, uint32_t* ticket, bool v1, cudaStream_t stream);
 uint32_t csq_parse_tiles(uint64_t bytes);
 cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t* list_count, cudaStream_t stream);
 bool csq_align_has_exact_kernel(int m);

@@ -1,0 +1,435 @@
+// k_emit_stage: order-preserving FASTQ text emission ("@name\nseq\n+\nqual\n", dnaio's fastq_bytes) staged through
+// shared memory - the default sink behind PairedEndSink / SingleEndSink of reference run.py:446-471 / 763-792.
+//
+// Why: the direct kernels (k_emit<G> in kernels.cu, k_emit_rec in emit.cu) move every record with
+// byte-granular global loads and stores from arbitrary alignments; they spend 125-250 warp instructions per
+// record on position bookkeeping and are bound by instruction issue at 48 % of the HBM copy peak.  Here the
+// global side only ever sees aligned, fully coalesced 16-byte accesses, and the byte shuffling happens in
+// shared memory where a lane can walk its own record:
+//
+//   phase 1 (thread per pair)   as before: destination, record sizes, CTA-wide exclusive scan per output
+//                               stream -> where every record goes.  The descriptors stay in registers.
+//   then each WARP walks its 32 pairs in passes of up to 8 pairs (16 single-end reads) = 16 records x 2 lanes:
+//   load      the source bytes of the pass - in a text batch one contiguous span of the FASTQ text per mate - come
+//             in with 16-byte cp.async copies, lane-strided (LDGSTS, no registers);
+//   reformat  lane (record, role): role 0 writes '@' id ['_' UMI] '\n' bases '\n', role 1 writes '+' '\n' qualities
+//             '\n' into the staging image of the output, 32-bit words built from two aligned shared-memory words
+//             (funnel shift), ~5 instructions per 4 bytes and no bookkeeping in the loop;
+//   flush     the records of a pass that go to the same output stream are contiguous there: the image is laid
+//             out at the same offset modulo 16 as its place in the output and leaves with 16-byte stores,
+//             lane-strided; only the < 16 bytes at either end of a span go bytewise.
+//
+// Every source byte is read once and every output byte written once.  A pass that does not fit the staging
+// buffers is halved; a pair that does not fit alone (reads near the length limit with very long headers) takes
+// a bytewise path.  PairedEndRenamer's id check compares the two staged ids.  The reverse-complementing
+// single-end sink stays with k_emit<16>.
+#include <cuda_pipeline.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "csq_internal.h"
+#include "device_common.cuh"
+
+namespace {
+
+constexpr uint32_t ES_SRC_CAP = 6656;   // source bytes staged per warp and pass
+constexpr uint32_t ES_DST_CAP = 5632;   // output bytes staged per warp and pass
+constexpr uint32_t ES_SLACK = 16;       // readable bytes behind either region (the word loops look one word ahead)
+constexpr uint32_t ES_WARP_BYTES = ES_SRC_CAP + ES_SLACK + ES_DST_CAP + ES_SLACK;
+constexpr uint32_t ES_SRC0 = 0, ES_DST0 = ES_SRC_CAP + ES_SLACK;
+constexpr int ES_WARPS = CSQ_PAIR_BLOCK / 32;
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct StageRec {  // one mate of one pair, held by the lane that owns the pair in phase 1
+    uint32_t nm;   // id bytes: offset into the name pool
+    uint32_t sq;   // original read: offset into the seq pool
+    uint32_t ql;   // ... into the qual pool
+    uint32_t pa, pb;  // UMI parts: offsets into the seq pool of the mate they come from
+    uint32_t ab;   // a | b << 16
+    uint32_t idl;  // id_len | umi_len << 16  (umi_len counts the '_')
+    uint32_t lab;  // lenA | lenB << 16
+    uint32_t off;  // byte offset of the record inside the CTA's part of its output stream
+    uint32_t len;  // bytes of the record
+};
+
+__device__ __forceinline__ StageRec shfl_rec(const StageRec& r, int src) {
+    StageRec o;
+    o.nm = __shfl_sync(FULL, r.nm, src);
+    o.sq = __shfl_sync(FULL, r.sq, src);
+    o.ql = __shfl_sync(FULL, r.ql, src);
+    o.pa = __shfl_sync(FULL, r.pa, src);
+    o.pb = __shfl_sync(FULL, r.pb, src);
+    o.ab = __shfl_sync(FULL, r.ab, src);
+    o.idl = __shfl_sync(FULL, r.idl, src);
+    o.lab = __shfl_sync(FULL, r.lab, src);
+    o.off = __shfl_sync(FULL, r.off, src);
+    o.len = __shfl_sync(FULL, r.len, src);
+    return o;
+}
+
+__device__ __forceinline__ uint32_t lds32(const uint8_t* sm, uint32_t a) { return *reinterpret_cast<const uint32_t*>(sm + a); }
+
+// n bytes from shared offset s to shared offset d, any alignment on both sides.  Looks at most one aligned word
+// (4 bytes) beyond s + n.
+__device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, uint32_t n) {
+    if (n == 0) return;
+    const uint32_t h = min((4u - (d & 3u)) & 3u, n);
+    for (uint32_t i = 0; i < h; i++) sm[d + i] = sm[s + i];
+    s += h;
+    d += h;
+    n -= h;
+    const uint32_t sh = (s & 3u) * 8u;
+    uint32_t sa = s & ~3u;
+    uint32_t w0 = lds32(sm, sa);
+    const uint32_t nw = n >> 2;
+#pragma unroll 4
+    for (uint32_t i = 0; i < nw; i++) {
+        sa += 4;
+        const uint32_t w1 = lds32(sm, sa);
+        *reinterpret_cast<uint32_t*>(sm + d) = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+        d += 4;
+    }
+    s = sa + (sh >> 3);
+    n &= 3u;
+    for (uint32_t i = 0; i < n; i++) sm[d + i] = sm[s + i];
+}
+
+// are the n bytes at shared offsets x and y different?
+__device__ __forceinline__ bool differ_s(const uint8_t* sm, uint32_t x, uint32_t y, uint32_t n) {
+    if (n == 0) return false;
+    const uint32_t xs = (x & 3u) * 8u, ys = (y & 3u) * 8u;
+    uint32_t xa = x & ~3u, ya = y & ~3u;
+    uint32_t x0 = lds32(sm, xa), y0 = lds32(sm, ya);
+    uint32_t diff = 0;
+    for (uint32_t i = 0; i < n; i += 4) {
+        xa += 4;
+        ya += 4;
+        const uint32_t x1 = lds32(sm, xa), y1 = lds32(sm, ya);
+        const uint32_t rem = n - i;
+        const uint32_t mask = rem >= 4 ? 0xFFFFFFFFu : ((1u << (8u * rem)) - 1u);
+        diff |= (__funnelshift_r(x0, x1, xs) ^ __funnelshift_r(y0, y1, ys)) & mask;
+        x0 = x1;
+        y0 = y1;
+    }
+    return diff != 0;
+}
+
+__global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_constant__ EmitParams E) {
+    extern __shared__ __align__(16) uint8_t es_smem[];
+    __shared__ unsigned int wtot[8][ES_WARPS];  // per-stream totals of every warp
+    const PairParams& P = E.pp;
+    const uint32_t base = blockIdx.x * CSQ_PAIR_BLOCK;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool paired = P.n_mates == 2;
+    const int n_mates = paired ? 2 : 1;
+    uint8_t* const sm = es_smem + (uint32_t)wid * ES_WARP_BYTES;
+
+    // ---- phase 1: where does every record go (thread per pair) ----
+    const uint32_t idx = base + threadIdx.x;
+    const bool live = idx < P.n;
+    int dest = 0;
+    uint32_t len[2] = {0, 0}, incl[2] = {0, 0};
+    ReadState st[2];
+    RecordShape shape[2];
+    if (live) {
+        dest = P.dest[idx];
+        st[0] = load_state(P.md[0].state + idx);
+        st[1] = paired ? load_state(P.md[1].state + idx) : st[0];
+        for (int mt = 0; mt < n_mates; mt++) {
+            shape[mt] = record_shape(P, st[mt], st[0], st[1]);
+            len[mt] = shape[mt].total;
+        }
+    }
+    for (int mt = 0; mt < n_mates; mt++)
+        for (int d = 0; d < CSQ_N_DEST; d++) {
+            const uint32_t v = (live && dest == d) ? len[mt] : 0u;
+            uint32_t x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, x, o);
+                if (lane >= o) x += y;
+            }
+            if (live && dest == d) incl[mt] = x;
+            if (lane == 31) wtot[d * 2 + mt][wid] = x;
+        }
+    __syncthreads();
+    StageRec rec[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        StageRec& R = rec[mt];
+        R.nm = R.sq = R.ql = R.pa = R.pb = R.ab = R.idl = R.lab = R.off = R.len = 0;
+        if (live && mt < n_mates) {
+            const int stream = dest * 2 + mt;
+            uint32_t off = incl[mt] - len[mt];
+            for (int w = 0; w < wid; w++) off += wtot[stream][w];
+            const MateDev& md = P.md[mt];
+            const ReadState& own = st[mt];
+            R.nm = md.name_off[idx] + own.id_start;
+            R.sq = md.seq_off[idx];
+            R.ql = md.qual_off[idx];
+            if (P.rename_parts & CSQ_REN_OWN_PREFIX) R.pa = R.sq + (own.ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_OWN_SUFFIX) R.pb = R.sq + (own.ren_cs >> 16);
+            if (P.rename_parts & CSQ_REN_R1_PREFIX) R.pa = P.md[0].seq_off[idx] + (st[0].ren_cp >> 16);
+            if (P.rename_parts & CSQ_REN_R2_PREFIX) R.pb = P.md[1].seq_off[idx] + (st[1].ren_cp >> 16);
+            R.ab = (uint32_t)own.a | ((uint32_t)own.b << 16);
+            R.idl = shape[mt].id_len | (shape[mt].umi_len << 16);
+            R.lab = shape[mt].lenA | (shape[mt].lenB << 16);
+            R.off = off;
+            R.len = len[mt];
+        }
+    }
+    // from here on the warps are on their own (no CTA-wide barrier below)
+    const int n_warp = min(32, (int)P.n - (int)(base + (uint32_t)wid * 32u));
+    if (n_warp <= 0) return;
+
+    // where the CTA's part of every output stream begins
+    uint8_t* gbase[CSQ_N_DEST][2];
+#pragma unroll
+    for (int d = 0; d < CSQ_N_DEST; d++)
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+            gbase[d][mt] = E.out[d][mt] + (mt < n_mates ? E.block_off[(size_t)blockIdx.x * 8 + d * 2 + mt] : 0ull);
+    // pools the UMI parts come from: the mate itself (single-end template) or R1 / R2 (paired template)
+    const uint8_t* const poolA = (P.rename_parts & CSQ_REN_R1_PREFIX) ? P.md[0].seq : nullptr;
+    const uint8_t* const poolB = (P.rename_parts & CSQ_REN_R2_PREFIX) ? P.md[1].seq : nullptr;
+    // a text batch keeps header, bases and qualities of a mate in ONE buffer: one source span per mate and pass
+    const bool one_pool = P.md[0].seq == P.md[0].name && P.md[0].seq == P.md[0].qual;
+    const int n_pools = one_pool ? 1 : 3;
+
+    const int q = lane >> 1, role = lane & 1;
+    const int ppass = paired ? 8 : 16;
+    const int my_mt = paired ? (q & 1) : 0;
+    const int my_pp = paired ? (q >> 1) : q;  // pair of the pass this lane works on
+    bool id_mismatch = false;
+
+    for (int p0 = 0; p0 < n_warp;) {
+        const int src_lane = (p0 + my_pp) & 31;
+        const StageRec r0 = shfl_rec(rec[0], src_lane), r1 = shfl_rec(rec[1], src_lane);
+        const StageRec R = my_mt ? r1 : r0;
+        const int my_dest = __shfl_sync(FULL, dest, src_lane);
+        const uint32_t a = R.ab & 0xFFFFu, b = R.ab >> 16, seq_len = b - a;
+        const uint32_t id_len = R.idl & 0xFFFFu, umi_len = R.idl >> 16;
+        const uint32_t la = R.lab & 0xFFFFu, lab = la + (R.lab >> 16);
+        // source pieces of this record in pool coordinates: name [nm, nm + id_len), bases [sq + a, sq + b),
+        // qualities [ql + a, ql + b); empty pieces take no part in the spans
+        uint32_t plo[3], phi[3];
+        plo[0] = R.nm;
+        phi[0] = R.nm + id_len;
+        plo[1] = R.sq + a;
+        phi[1] = R.sq + b;
+        plo[2] = R.ql + a;
+        phi[2] = R.ql + b;
+        if (one_pool) {
+            uint32_t lo = 0xFFFFFFFFu, hi = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if (phi[k] > plo[k]) {
+                    lo = min(lo, plo[k]);
+                    hi = max(hi, phi[k]);
+                }
+            plo[0] = lo;
+            phi[0] = hi;
+        }
+
+        int g = min(ppass, n_warp - p0);
+        bool valid = false;
+        uint32_t sdelta[3] = {0, 0, 0};   // staged address of pool offset x of my mate: ES_SRC0 + sdelta[pool] + x
+        uint32_t ddelta = 0;              // staged address of my record: ES_DST0 + ddelta + R.off
+        uint32_t sp_lo16[2][3], sp_n16[2][3], sp_base[2][3];  // source spans of the pass: pool offset, 16-byte chunks, staged offset
+        for (;;) {
+            valid = my_pp < g;
+            uint32_t cursor = 0;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    sp_n16[mt][k] = 0;
+                    sp_lo16[mt][k] = sp_base[mt][k] = 0;
+                    if (mt < n_mates && k < n_pools) {
+                        const bool part = valid && role == 0 && my_mt == mt && phi[k] > plo[k];
+                        const uint32_t lo = __reduce_min_sync(FULL, part ? plo[k] : 0xFFFFFFFFu);
+                        const uint32_t hi = __reduce_max_sync(FULL, part ? phi[k] : 0u);
+                        if (hi > lo) {
+                            const uint32_t lo16 = lo & ~15u;
+                            const uint32_t n16 = (hi - lo16 + 15u) >> 4;
+                            sp_lo16[mt][k] = lo16;
+                            sp_n16[mt][k] = n16;
+                            sp_base[mt][k] = cursor;
+                            if (my_mt == mt) sdelta[k] = cursor - lo16;
+                            cursor += n16 << 4;
+                        }
+                    }
+                }
+            // output: the records of one (destination, mate) stream are contiguous there
+            uint32_t dcursor = 0;
+#pragma unroll
+            for (int d = 0; d < CSQ_N_DEST; d++)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const bool part = valid && role == 0 && my_mt == mt && my_dest == d;
+                    const uint32_t mask = __ballot_sync(FULL, part);
+                    if (mask) {
+                        const uint32_t goff = __shfl_sync(FULL, R.off, __ffs((int)mask) - 1);
+                        const uint32_t bytes = __reduce_add_sync(FULL, part ? R.len : 0u);
+                        const uint32_t mis = (uint32_t)(uintptr_t)(gbase[d][mt] + goff) & 15u;
+                        const uint32_t dstart = ((dcursor + 15u) & ~15u) + mis;
+                        dcursor = dstart + bytes;
+                        if (my_mt == mt && my_dest == d) ddelta = dstart - goff;
+                    }
+                }
+            if (cursor <= ES_SRC_CAP && dcursor <= ES_DST_CAP) break;
+            if (g == 1) {
+                g = 0;
+                break;
+            }
+            g >>= 1;
+        }
+
+        if (g == 0) {
+            // ---- the pair at p0 does not fit the staging buffers: bytewise, straight from and to global memory ----
+            const int sl = p0 & 31;
+            const int fd = __shfl_sync(FULL, dest, sl);
+            const uint8_t* idp[2] = {nullptr, nullptr};
+            uint32_t idn[2] = {0, 0};
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                if (mt >= n_mates) continue;
+                const StageRec F = shfl_rec(rec[mt], sl);
+                const MateDev& md = P.md[mt];
+                const uint32_t fa = F.ab & 0xFFFFu, fb = F.ab >> 16, fl = fb - fa, fid = F.idl & 0xFFFFu, fumi = F.idl >> 16;
+                const uint32_t fla = F.lab & 0xFFFFu;
+                const uint8_t* nm = md.name + F.nm;
+                const uint8_t* sq = md.seq + F.sq + fa;
+                const uint8_t* ql = md.qual + F.ql + fa;
+                const uint8_t* pa = (poolA ? poolA : md.seq) + F.pa;
+                const uint8_t* pb = (poolB ? poolB : md.seq) + F.pb;
+                uint8_t* out = (fd == 0 ? gbase[0][mt] : fd == 1 ? gbase[1][mt] : gbase[2][mt]) + F.off;
+                const uint32_t e_name = 1u + fid, e_umi = e_name + fumi, e_seq = e_umi + 1u + fl, e_qual = e_seq + 3u + fl;
+                for (uint32_t p = lane; p < F.len; p += 32) {
+                    uint8_t c;
+                    if (p < e_name) c = p == 0 ? (uint8_t)'@' : nm[p - 1];
+                    else if (p < e_umi) {
+                        const uint32_t x = p - e_name;
+                        c = x == 0 ? (uint8_t)'_' : (x - 1 < fla ? pa[x - 1] : pb[x - 1 - fla]);
+                    } else if (p == e_umi) c = '\n';
+                    else if (p < e_seq) c = sq[p - e_umi - 1];
+                    else if (p < e_seq + 3) c = (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
+                    else if (p < e_qual) c = ql[p - e_seq - 3];
+                    else c = '\n';
+                    out[p] = c;
+                }
+                idp[mt] = nm;
+                idn[mt] = fid;
+            }
+            if (P.check_ids) {
+                id_mismatch |= idn[0] != idn[1];
+                for (uint32_t x = lane; x < min(idn[0], idn[1]); x += 32) id_mismatch |= idp[0][x] != idp[1][x];
+            }
+            p0 += 1;
+            continue;
+        }
+
+        // ---- load: source spans -> shared memory, UMI parts -> their place in the output image ----
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (sp_n16[mt][k] == 0) continue;
+                const MateDev& md = P.md[mt];
+                const uint8_t* pool = k == 0 ? (one_pool ? md.seq : md.name) : k == 1 ? md.seq : md.qual;
+                const uint8_t* src = pool + sp_lo16[mt][k];
+                uint8_t* dst = sm + ES_SRC0 + sp_base[mt][k];
+                for (uint32_t c = lane; c < sp_n16[mt][k]; c += 32) __pipeline_memcpy_async(dst + 16u * c, src + 16u * c, 16);
+            }
+        __pipeline_commit();
+        const uint32_t d0 = ES_DST0 + ddelta + R.off;  // my record in the output image
+        if (valid && role == 0 && lab) {
+            const MateDev& md = P.md[my_mt];
+            const uint8_t* __restrict__ pa = (poolA ? poolA : md.seq) + R.pa;
+            const uint8_t* __restrict__ pb = (poolB ? poolB : md.seq) + R.pb;
+            const uint32_t du = d0 + 1u + id_len + 1u;
+            for (uint32_t x0 = 0; x0 < lab; x0 += 8) {
+                uint8_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t x = x0 + u;
+                    v[u] = x < lab ? (x < la ? pa[x] : pb[x - la]) : (uint8_t)0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (x0 + u < lab) sm[du + x0 + u] = v[u];
+            }
+        }
+        __pipeline_wait_prior(0);
+        __syncwarp();
+
+        // ---- reformat ----
+        const uint32_t sd_name = sdelta[0], sd_seq = one_pool ? sdelta[0] : sdelta[1], sd_qual = one_pool ? sdelta[0] : sdelta[2];
+        const uint32_t s_id = ES_SRC0 + sd_name + R.nm;
+        if (valid) {
+            const uint32_t d_seq = d0 + 1u + id_len + umi_len + 1u;
+            const uint32_t d_qual = d_seq + seq_len + 3u;
+            const uint32_t s_big = ES_SRC0 + (role ? sd_qual + R.ql : sd_seq + R.sq) + a;
+            copy_s2s(sm, s_big, role ? d_qual : d_seq, seq_len);
+            if (role == 0) {
+                sm[d0] = '@';
+                copy_s2s(sm, s_id, d0 + 1u, id_len);
+                if (umi_len) sm[d0 + 1u + id_len] = '_';
+                sm[d_seq - 1u] = '\n';
+                sm[d_seq + seq_len] = '\n';
+            } else {
+                sm[d_qual - 2u] = '+';
+                sm[d_qual - 1u] = '\n';
+                sm[d_qual + seq_len] = '\n';
+            }
+        }
+        if (P.check_ids) {  // PairedEndRenamer: the ids of the two mates must be identical (mate 1 sits two lanes below)
+            const uint32_t o_id = __shfl_sync(FULL, s_id, (lane - 2) & 31), o_len = __shfl_sync(FULL, id_len, (lane - 2) & 31);
+            if (valid && role == 0 && my_mt == 1) id_mismatch |= o_len != id_len || differ_s(sm, s_id, o_id, id_len);
+        }
+        __syncwarp();
+
+        // ---- flush: every (destination, mate) span of the pass, 16 bytes per lane and store ----
+        {
+            uint32_t dcursor = 0;
+#pragma unroll
+            for (int d = 0; d < CSQ_N_DEST; d++)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const bool part = valid && role == 0 && my_mt == mt && my_dest == d;
+                    const uint32_t mask = __ballot_sync(FULL, part);
+                    if (mask) {
+                        const uint32_t goff = __shfl_sync(FULL, R.off, __ffs((int)mask) - 1);
+                        const uint32_t bytes = __reduce_add_sync(FULL, part ? R.len : 0u);
+                        uint8_t* __restrict__ gp = gbase[d][mt] + goff;
+                        const uint32_t mis = (uint32_t)(uintptr_t)gp & 15u;
+                        const uint32_t dstart = ((dcursor + 15u) & ~15u) + mis;
+                        dcursor = dstart + bytes;
+                        const uint8_t* __restrict__ sp = sm + ES_DST0 + dstart;
+                        const uint32_t head = min((16u - mis) & 15u, bytes);
+                        if ((uint32_t)lane < head) gp[lane] = sp[lane];
+                        const uint32_t nvec = (bytes - head) >> 4;
+                        const uint4* __restrict__ sv = reinterpret_cast<const uint4*>(sp + head);
+                        uint4* __restrict__ gv = reinterpret_cast<uint4*>(gp + head);
+                        for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
+                        const uint32_t done = head + (nvec << 4), tail = bytes - done;
+                        if ((uint32_t)lane < tail) gp[done + lane] = sp[done + lane];
+                    }
+                }
+        }
+        __syncwarp();
+        p0 += g;
+    }
+    if (__any_sync(FULL, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
+}
+
+}  // namespace
+
+cudaError_t csq_launch_emit_stage(const EmitParams& p, cudaStream_t stream) {
+    if (p.pp.n == 0) return cudaSuccess;
+    // per device: a function attribute belongs to the current context
+    cudaError_t attr = cudaFuncSetAttribute(k_emit_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ES_WARPS * ES_WARP_BYTES));
+    if (attr != cudaSuccess) return attr;
+    k_emit_stage<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, ES_WARPS * ES_WARP_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}

@@ -82,7 +82,7 @@ struct Slot {
     cudaStream_t stream2 = nullptr;  // chain of mate 2
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // text batches (csq_submit_text): the FASTQ bytes as they came, and the record index k_records builds
-    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16
+    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16 | tile ticket[2] (u32) at +32
     uint64_t text_bytes[2] = {0, 0};
     uint64_t first_record = 0;
     bool text_mode = false;
@@ -353,9 +353,13 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
         if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.name_off[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.name_end[m].ensure((size_t)n * 4 + 16))) return rc;
-        if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
-        if ((rc = s.tiles[m].ensure(((size_t)csq_parse_tiles(bytes) + 4) * 4))) return rc;
-        if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;  // 16 bits per 16-byte chunk
+        if (plan->flags & CSQ_PLAN_PARSE_V1) {
+            if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
+            if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;  // 16 bits per 16-byte chunk
+        } else {
+            if ((rc = s.nl[m].ensure(((size_t)n + 8) * 4))) return rc;  // quality lengths (scratch of the one-pass parse)
+        }
+        if ((rc = s.tiles[m].ensure(((size_t)csq_parse_tiles(bytes) + 4) * 8))) return rc;
         if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
         if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
             if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
@@ -459,8 +463,9 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
         pp.name_off = (uint32_t*)s.name_off[m].p;
         pp.name_end = (uint32_t*)s.name_end[m].p;
         pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
-        CUDA_TRY(csq_launch_parse(pp, (uint32_t*)s.tiles[m].p, (uint16_t*)s.masks[m].p, st));
-        plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
+        const bool v1 = (plan->flags & CSQ_PLAN_PARSE_V1) != 0;
+        CUDA_TRY(csq_launch_parse(pp, s.tiles[m].p, (uint16_t*)s.masks[m].p, (uint32_t*)((uint8_t*)s.parse_misc.p + 32) + m, v1, st));
+        plan->launches += csq_parse_tiles(pp.bytes) ? (v1 ? 4 : 2) : 1;
         if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
     }
     MateProgram& mp = plan->prog[m];
@@ -555,8 +560,13 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     ep.block_off = (const unsigned long long*)s.block_off.p;
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < 2; m++) ep.out[d][m] = (uint8_t*)s.out[d][m].p;
-    CUDA_TRY((plan->flags & CSQ_PLAN_EMIT_REC) ? csq_launch_emit_rec(ep, st)
-                                                : csq_launch_emit(ep, (plan->flags & CSQ_PLAN_EMIT_G32) ? 32 : (plan->flags & CSQ_PLAN_EMIT_G8) ? 8 : 16, st));
+    // default: staged through shared memory; the direct kernels stay for A/B runs and for the reverse-complementing sink
+    if (plan->flags & CSQ_PLAN_EMIT_REC)
+        CUDA_TRY(csq_launch_emit_rec(ep, st));
+    else if ((plan->flags & (CSQ_PLAN_EMIT_G32 | CSQ_PLAN_EMIT_G16 | CSQ_PLAN_EMIT_G8)) || ep.pp.revcomp)
+        CUDA_TRY(csq_launch_emit(ep, (plan->flags & CSQ_PLAN_EMIT_G32) ? 32 : (plan->flags & CSQ_PLAN_EMIT_G8) ? 8 : 16, st));
+    else
+        CUDA_TRY(csq_launch_emit_stage(ep, st));
     plan->launches += s.n ? 1 : 0;
     if (kt) kt->mark("k_emit");
     return 0;
@@ -725,7 +735,8 @@ static int validate_text(const csq_plan* plan, const csq_batch_text* in) {
         if (in->mate[m].bytes && !in->mate[m].text) return fail(CSQ_ERR_INVALID, "mate %d: null text", m + 1);
         if (in->mate[m].bytes >= (1ull << 32) - 4096) return fail(CSQ_ERR_LIMIT, "batch text must stay below 4 GiB");
     }
-    if ((uint64_t)in->n_reads * 4 >= (1ull << 32)) return fail(CSQ_ERR_LIMIT, "too many records in one batch");
+    // the look-back words of the parse kernel count line ends in 30 bits
+    if ((uint64_t)in->n_reads * 4 >= (1ull << 30)) return fail(CSQ_ERR_LIMIT, "too many records in one batch (limit 2^28 - 1)");
     return 0;
 }
 

@@ -220,10 +220,14 @@ typedef struct csq_plan csq_plan;
 #define CSQ_PLAN_KEEP_MATCHES 1u  /* keep per-ALIGN csq_match records (tests, statistics) */
 #define CSQ_PLAN_NO_PREFILTER 2u  /* run the exact DP on every read (no bit-parallel prefilter) */
 #define CSQ_PLAN_ONE_STREAM 64u   /* run the chains of mate 1 and mate 2 on one stream (default: side by side) */
-#define CSQ_PLAN_EMIT_G32 16u     /* k_emit with 32 lanes per record (default: 16), A/B runs */
+#define CSQ_PLAN_EMIT_G16 256u    /* emit FASTQ text with the direct (global -> global) k_emit, 16 lanes per record, instead of
+                                     the default k_emit_stage (staged through shared memory); A/B runs       */
+#define CSQ_PLAN_EMIT_G32 16u     /* ... direct k_emit with 32 lanes per record */
 #define CSQ_PLAN_EMIT_G8 32u      /* ... with 8 lanes per record */
+#define CSQ_PLAN_PARSE_V1 128u   /* text batches: the four-kernel parse (masks + line-end offsets through HBM) instead of
+                                     the one-pass look-back kernel (A/B runs)                                        */
 #define CSQ_PLAN_EMIT_REC 8u      /* emit FASTQ text with the thread-per-pair 16-byte-chunk kernel instead of the
-                                     default warp-per-record one (A/B runs)                            */
+                                     default k_emit_stage (A/B runs)                                     */
 
 /* Library / device */
 int csq_abi_version(void);

@@ -190,7 +190,7 @@ def compare_with_oracle(prog, mates, flags=0):
     return text
 
 
-@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G8], ids=["prefilter", "exact_only", "emit_rec", "emit_g32", "emit_g8"])
+@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8], ids=["prefilter", "exact_only", "emit_rec", "emit_g32", "emit_g16", "emit_g8"])
 @pytest.mark.parametrize("case", helpers.golden_cases(), ids=lambda c: c["case"])
 def test_golden_vectors(case, flags):
     prog = helpers.program_for(case["argv"], case["n_mates"])
@@ -280,7 +280,7 @@ def test_synthetic_configs_against_oracle():
         prog = helpers.program_for(argv, n_mates)
         batch = native.synth_batch(config, 30000, first_index=12345, buffer=3)
         want = oracle.run_batch(prog, batch, n_threads=8)
-        for flags in (0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G8):
+        for flags in (0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8):
             with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES | flags) as plan:
                 text, records = plan.run_batch(batch)
                 stats = plan.stats()
@@ -300,7 +300,12 @@ def test_synthetic_configs_against_oracle():
 
 
 # ---- text batches: raw FASTQ bytes in, the device builds the record index (parse.cu) ----
-def test_text_batches_equal_soa_batches():
+PARSE_FLAGS = [0, A.PLAN_PARSE_V1]
+PARSE_IDS = ["onepass", "parse_v1"]
+
+
+@pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
+def test_text_batches_equal_soa_batches(pflags):
     cases = [
         (2, ["-A", "TAKARAV3", "--trim-polyA"], 2),
         (3, ["-a", "ACACGACGCTCTTCCGATCT(ATCACG)NNNNNNNNXXX<XXX(CGTGAT)AGATCGGAAGAGCACACGTC", "--ensure-inline-barcode"], 2),
@@ -311,7 +316,7 @@ def test_text_batches_equal_soa_batches():
         for n in (1, 255, 20011):
             batch = native.synth_batch(config, n, first_index=99, buffer=5)
             texts = [native.format_fastq(batch, m).tobytes() for m in range(n_mates)]
-            with native.Plan(prog, 0, 0) as plan:
+            with native.Plan(prog, 0, pflags) as plan:
                 want, want_records = plan.run_batch(batch)
                 got, got_records = plan.run_text(texts, n, slot=1)
                 assert got == want and got_records == want_records, (config, n)
@@ -320,7 +325,8 @@ def test_text_batches_equal_soa_batches():
                 assert got == want and got_records == want_records, (config, n, "crlf")
 
 
-def test_text_batch_odd_records():
+@pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
+def test_text_batch_odd_records(pflags):
     """'+' line repeating the name, empty reads, a read at the length limit, lower-case bases, header with tabs."""
     prog = helpers.program_for(["-A", "SMALLRNA"], 1)
     recs = [
@@ -334,9 +340,44 @@ def test_text_batch_odd_records():
     for name, seq, plus_name in recs:
         text += f"@{name}\n{seq}\n+{name if plus_name else ''}\n{'I' * len(seq)}\n".encode()
     want = oracle_text(prog, [text])
-    with native.Plan(prog, 0, 0) as plan:
+    with native.Plan(prog, 0, pflags) as plan:
         got, _ = plan.run_text([text], len(recs))
     assert got[0][0] == want[0][0] and got[1][0] == want[1][0]
+
+
+@pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
+def test_text_batch_lines_longer_than_a_parse_tile(pflags):
+    """Header comments / '+' lines of 20-50 KB: whole 16 KiB parse tiles without a line end, so the start of the
+    open line has to be carried across several tiles by the look-back."""
+    prog = helpers.program_for(["-A", "SMALLRNA"], 1)
+    rng = random.Random(7)
+    text = b""
+    n = 0
+    for i in range(400):
+        seq = "".join(rng.choice("ACGT") for _ in range(rng.randint(0, 120))) + "AGATCGGAAGAGCACACGTC"[: rng.randint(0, 20)]
+        comment = "c" * (rng.choice([20000, 33000, 50000]) if i % 57 == 5 else rng.randint(0, 30))
+        plus = f"r{i} {comment}" if i % 3 == 0 else ""  # the '+' line may repeat the header
+        text += f"@r{i} {comment}\n{seq}\n+{plus}\n{'I' * len(seq)}\n".encode()
+        n += 1
+    want = oracle_text(prog, [text])
+    with native.Plan(prog, 0, pflags) as plan:
+        got, _ = plan.run_text([text], n)
+    assert got[0][0] == want[0][0] and got[1][0] == want[1][0]
+
+
+@pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
+def test_text_batch_many_tiny_records(pflags):
+    """Empty reads: 6-byte lines, ~2 700 line ends per parse tile; plus a wrong record count in both directions."""
+    prog = helpers.program_for(["-A", "SMALLRNA"], 1)
+    n = 50000
+    text = b"".join(b"@%d\n\n+\n\n" % i for i in range(n))
+    with native.Plan(prog, 0, pflags) as plan:
+        got, records = plan.run_text([text], n)
+        assert records[1][0] == n and got[1][0] == text  # all too short, unchanged
+        for wrong in (n - 1, n + 1):
+            with pytest.raises(native.NativeError) as e:
+                plan.run_text([text], wrong)
+            assert e.value.code == A.ERR_FORMAT and "whole FASTQ records" in str(e.value)
 
 
 def oracle_text(prog, texts):
@@ -357,9 +398,10 @@ def oracle_text(prog, texts):
     (b"@r1\nACGT\n+\nIIII\n@r2\n" + b"A" * 900 + b"\n+\n" + b"I" * 900 + b"\n", A.ERR_LIMIT, "line 5"),
     (b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n+\n", A.ERR_FORMAT, "whole FASTQ records"),
 ])
-def test_text_batch_format_errors(bad, code, needle):
+@pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
+def test_text_batch_format_errors(bad, code, needle, pflags):
     prog = helpers.program_for(["-A", "SMALLRNA"], 1)
-    with native.Plan(prog, 0, 0) as plan:
+    with native.Plan(prog, 0, pflags) as plan:
         with pytest.raises(native.NativeError) as e:
             plan.run_text([bad], 2, capacity=8192)
         assert e.value.code == code and needle in str(e.value), str(e.value)
