@@ -189,11 +189,13 @@ def main():
     ap.add_argument("--batch-pairs", type=int, default=BATCH_PAIRS)
     ap.add_argument("--batches", type=int, default=N_BATCHES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
     ap.add_argument("--file-pairs", type=int, default=2_000_000, help="pairs in the whole-file leg")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="stage", choices=["stage", "g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
+    ap.add_argument("--homo", default="two", choices=["two", "v1"], help="poly-A / poly-T exact DP: two columns side by side (default) or one (A/B runs)")
     ap.add_argument("--parse", default="onepass", choices=["onepass", "v1"], help="text-batch parse (A/B runs); onepass (look-back kernel) is the product default")
     ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
     ap.add_argument("--input", default="text", choices=["text", "soa"], help="batch form handed to the library")
@@ -220,6 +222,8 @@ def main():
     torch.cuda.set_device(local_rank)
     build.build()
     native.lib()  # fails loudly when the CUDA library is missing
+    # one process per GPU: this rank's threads and pinned buffers stay on the GPU's NUMA node (-1: nothing to bind to)
+    numa_node = -1 if args.no_numa else native.bind_host_to_device(local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,7 +235,7 @@ def main():
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
     plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0)
-                       | (A.PLAN_PARSE_V1 if args.parse == "v1" else 0))
+                       | (A.PLAN_PARSE_V1 if args.parse == "v1" else 0) | (A.PLAN_HOMO_V1 if args.homo == "v1" else 0))
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
@@ -338,6 +342,7 @@ def main():
                "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_s / args.steps * 1e3,
                "timing": f"wall clock between device-synchronised points, {n_e2e} batches in flight through csq_submit/csq_wait, max over ranks"}
 
+    native.unbind_host()  # the host legs below (files, CPU baseline) use every core of the box
     if rank != 0:
         plan.close()
         group.close()
@@ -427,7 +432,7 @@ def main():
                                f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
                                f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
-                   "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse},
+                   "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse, "homo_dp": args.homo, "numa_node": numa_node},
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
         "roofline": roofline, "roofline_dp": roofline_dp, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
         "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,

@@ -46,6 +46,7 @@ PLAN_EMIT_G8 = 32
 PLAN_ONE_STREAM = 64
 PLAN_PARSE_V1 = 128
 PLAN_EMIT_G16 = 256
+PLAN_HOMO_V1 = 512
 
 
 class csq_op(C.Structure):

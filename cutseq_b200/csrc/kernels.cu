@@ -126,7 +126,7 @@ __device__ __forceinline__ void best_to_match(const Best& best, int m, int n, bo
 }
 
 // Exact DP for a compile-time adapter length M: the column lives in registers W[0..M].
-template <int M, bool HOMO>
+template <int M, int HOMO>
 __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P,
                                          const uint32_t* __restrict__ lut, int j0, csq_match& r) {
     constexpr int NW = (M + 31) / 32;
@@ -206,6 +206,109 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
     best_to_match(best, M, n, P.reversed != 0, r);
 }
 
+// Homopolymer adapter (the poly-A / poly-T 100-mers of run.py:389-404): every row compares against the same
+// base, so a column needs one match/mismatch delta and no match mask.  A thread walks a column top to bottom,
+// each cell waiting for the one above it: a dependent chain of 3 instructions x M cells that a register-bound
+// kernel (M + 1 live cells, 2 CTAs per SM) cannot hide.  Two columns are therefore computed side by side, column
+// j + 1 one row behind column j - two independent chains, same cells, same order of the row-m / last-column
+// rules.  Everything else (init, early stop after k + 1 foreign characters, best-match rules) is dp_exact's.
+template <int M>
+__device__ __forceinline__ void dp_homo(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P, int j0,
+                                        csq_match& r) {
+    const int n = b - a;
+    const int k = P.k;
+    const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
+    int max_n = n, min_n = 0;
+    if (!siq) max_n = min(n, M + k);
+    if (!eiq) min_n = max(0, n - M - k);
+    if (j0 >= 0) min_n = max(min_n, j0);  // column window, see dp_exact
+    uint32_t W[M + 1];
+#pragma unroll
+    for (int i = 0; i <= M; i++) {
+        int cost, origin;
+        init_cell(i, min_n, sir, siq, cost, origin);
+        W[i] = pack_cell(cost, origin);
+    }
+    Best best = {M + n + 1, 0, 0, M, n};
+    const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
+    const int step = P.reversed ? -1 : 1;
+    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    const uint32_t letter = P.letter;
+    int foreign = 0;
+    bool cut_short = false;
+    int j = min_n + 1;
+    while (j <= max_n) {
+        const bool eq0 = ((uint32_t)*p & 0xDFu) == letter;
+        if (!siq) {
+            foreign += eq0 ? 0 : 1;
+            if (foreign > k) {  // no cell of this or any later column can be accepted (see dp_exact)
+                cut_short = true;
+                break;
+            }
+        }
+        const uint32_t d0 = eq0 ? D_MATCH : D_MIS;
+        bool two = j + 1 <= max_n;
+        bool eq1 = false;
+        if (two) {
+            eq1 = ((uint32_t)p[step] & 0xDFu) == letter;
+            if (!siq && foreign + (eq1 ? 0 : 1) > k) two = false;  // the scan stops at column j + 1: finish column j alone
+        }
+        if (two) {
+            if (!siq) foreign += eq1 ? 0 : 1;
+            const uint32_t d1 = eq1 ? D_MATCH : D_MIS;
+            uint32_t wd = W[0];                        // cell (i - 1, j - 1)
+            const uint32_t a0 = wd + row0_delta;       // cell (0, j)
+            const uint32_t b0 = a0 + row0_delta;       // cell (0, j + 1)
+            W[0] = b0;
+            uint32_t am2 = a0, am1 = a0, bm1 = b0;     // cells (i - 2, j), (i - 1, j), (i - 2, j + 1)
+            uint32_t wm_a = 0, wm_b = 0;
+#pragma unroll
+            for (int i = 1; i <= M + 1; i++) {
+                uint32_t ai = 0;
+                if (i <= M) {
+                    const uint32_t wl = W[i];          // cell (i, j - 1)
+                    ai = __vimin3_u32(wd + d0, am1 + D_INS, wl + D_DEL) & PRIO_CLEAR;
+                    wd = wl;
+                    if (i == M) wm_a = ai;
+                }
+                if (i >= 2) {                          // cell (i - 1, j + 1)
+                    const uint32_t bi = __vimin3_u32(am2 + d1, bm1 + D_INS, am1 + D_DEL) & PRIO_CLEAR;
+                    W[i - 1] = bi;
+                    bm1 = bi;
+                    if (i - 1 == M) wm_b = bi;
+                }
+                am2 = am1;
+                am1 = ai;
+            }
+            if (eiq) {
+                row_m_update(wm_a, j, M, n, P, best);
+                row_m_update(wm_b, j + 1, M, n, P, best);
+            }
+            j += 2;
+            p += 2 * step;
+        } else {
+            uint32_t wd = W[0];
+            W[0] += row0_delta;
+#pragma unroll
+            for (int i = 1; i <= M; i++) {
+                const uint32_t wl = W[i];
+                W[i] = __vimin3_u32(wd + d0, W[i - 1] + D_INS, wl + D_DEL) & PRIO_CLEAR;
+                wd = wl;
+            }
+            if (eiq) row_m_update(W[M], j, M, n, P, best);
+            j += 1;
+            p += step;
+        }
+    }
+    if (max_n == n && !cut_short) {
+        const int first_i = eir ? 0 : M;
+#pragma unroll
+        for (int i = M; i >= 0; i--)
+            if (i >= first_i) last_col_update(W[i], i, n, P, best);
+    }
+    best_to_match(best, M, n, P.reversed != 0, r);
+}
+
 // Same recurrence for any m <= CSQ_MAX_ADAPTER with the column in local memory (slow path for
 // adapter lengths without a register-resident instantiation).
 __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P, int j0,
@@ -249,7 +352,9 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
     best_to_match(best, m, n, P.reversed != 0, r);
 }
 
-template <int M, bool HOMO>
+// HOMO: 0 = any adapter, 1 = homopolymer adapter, one column at a time (CSQ_PLAN_HOMO_V1, A/B runs),
+// 2 = homopolymer adapter, two columns side by side (dp_homo)
+template <int M, int HOMO>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
     __shared__ uint32_t lut[(HOMO || M == 0) ? 1 : 256 * NW];
@@ -309,7 +414,9 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
             atomicAdd(dst, (unsigned long long)mine);
         }
     }
-    if constexpr (M > 0)
+    if constexpr (HOMO == 2)
+        dp_homo<M>(s, st.a, st.b, P, j0, r);
+    else if constexpr (M > 0)
         dp_exact<M, HOMO>(s, st.a, st.b, P, lut, j0, r);
     else
         dp_generic(s, st.a, st.b, P, j0, r);
@@ -910,12 +1017,16 @@ template <int M>
 cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t stream) {
     const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
     if constexpr (M == 100) {  // the poly-A / poly-T adapters of run.py:389-404
+        if (p.homopolymer == 2) {
+            k_align<M, 2><<<grid, block, 0, stream>>>(p);
+            return cudaGetLastError();
+        }
         if (p.homopolymer) {
-            k_align<M, true><<<grid, block, 0, stream>>>(p);
+            k_align<M, 1><<<grid, block, 0, stream>>>(p);
             return cudaGetLastError();
         }
     }
-    k_align<M, false><<<grid, block, 0, stream>>>(p);
+    k_align<M, 0><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -936,7 +1047,7 @@ cudaError_t csq_launch_align(const AlignParams& p, uint32_t n_items, cudaStream_
 #undef CSQ_CASE
         default: {
             const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
-            k_align<0, false><<<grid, block, 0, stream>>>(p);
+            k_align<0, 0><<<grid, block, 0, stream>>>(p);
             return cudaGetLastError();
         }
     }

@@ -471,6 +471,7 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
     MateProgram& mp = plan->prog[m];
     for (Segment& sg : mp.segs) {
         AlignParams ap = sg.ap;
+        if (ap.homopolymer && !(plan->flags & CSQ_PLAN_HOMO_V1)) ap.homopolymer = 2;  // two DP columns side by side
         ap.md = mate_dev(s, m);
         ap.n = n;
         ap.list = nullptr;

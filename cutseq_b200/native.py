@@ -54,6 +54,8 @@ def lib():
     L.csq_stats.argtypes = [vp, C.POINTER(A.csq_counters)]
     L.csq_locate_batch.argtypes = [i32, C.POINTER(A.csq_op), C.POINTER(A.csq_mate_in), u32, u32, vp]
     L.csq_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.csq_bind_host_to_device.argtypes = [i32, C.POINTER(C.c_int)]
+    L.csq_unbind_host.argtypes = []
     L.csq_device_count.argtypes = [C.POINTER(i32)]
     if hasattr(L, "csq_run_files"):
         L.csq_run_files.argtypes = [C.POINTER(A.csq_op), i32, C.POINTER(A.csq_op), i32, C.POINTER(A.csq_filters), u32,
@@ -319,6 +321,17 @@ def synth_batch(config: int, n_reads: int, first_index: int = 0, buffer: int = 0
 def check_plain(rc: int):
     if rc != 0:
         raise NativeError(rc, "synthetic generator failed")
+
+
+def bind_host_to_device(device: int = 0) -> int:
+    """Keep this thread, the threads it starts and the memory it pins on the GPU's NUMA node. -> node or -1."""
+    node = C.c_int(-1)
+    check(lib().csq_bind_host_to_device(device, C.byref(node)))
+    return node.value
+
+
+def unbind_host() -> None:
+    check(lib().csq_unbind_host())
 
 
 def int_peak(device: int = 0):

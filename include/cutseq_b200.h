@@ -226,6 +226,7 @@ typedef struct csq_plan csq_plan;
 #define CSQ_PLAN_EMIT_G8 32u      /* ... with 8 lanes per record */
 #define CSQ_PLAN_PARSE_V1 128u   /* text batches: the four-kernel parse (masks + line-end offsets through HBM) instead of
                                      the one-pass look-back kernel (A/B runs)                                        */
+#define CSQ_PLAN_HOMO_V1 512u     /* homopolymer (poly-A / poly-T) exact DP one column at a time instead of two side by side (A/B) */
 #define CSQ_PLAN_EMIT_REC 8u      /* emit FASTQ text with the thread-per-pair 16-byte-chunk kernel instead of the
                                      default k_emit_stage (A/B runs)                                     */
 
@@ -278,6 +279,14 @@ int csq_locate_batch(int device, const csq_op* align_op, const csq_mate_in* read
 /* Integer-issue microbenchmark used as the DP roofline denominator: returns measured
  * 32-bit integer lane-ops per second for (0) ALU-pipe only, (1) ALU+FMA-pipe mix. */
 int csq_int_peak(int device, double* alu_ops_per_s, double* mixed_ops_per_s);
+
+/* One process (or thread) per GPU: restrict the calling thread - and the threads and pinned buffers it creates
+ * afterwards - to the CPUs / memory of the NUMA node the device's PCIe root port belongs to.  *numa_node = the
+ * node, or -1 when nothing was changed (single node, no sysfs entry, cpuset without CPUs of that node).
+ * csq_unbind_host() restores the affinity mask and memory policy saved by the first bind.  The reference has no
+ * counterpart (cutadapt's worker processes are not placed); used by bench.py / dist runs. */
+int csq_bind_host_to_device(int device, int* numa_node);
+int csq_unbind_host(void);
 
 /* ---------------------------------------------------------------------------
  * Host FASTQ side (the step either side of the path: dnaio / xopen in the reference).
