@@ -44,7 +44,7 @@ PLAN_EMIT_REC = 8
 PLAN_EMIT_G32 = 16
 PLAN_EMIT_G8 = 32
 PLAN_ONE_STREAM = 64
-PLAN_PARSE_V1 = 128
+PLAN_PARSE_ONEPASS = 128
 PLAN_EMIT_G16 = 256
 PLAN_HOMO_V1 = 512
 

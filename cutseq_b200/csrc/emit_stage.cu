@@ -69,12 +69,13 @@ __device__ __forceinline__ StageRec shfl_rec(const StageRec& r, int src) {
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t* sm, uint32_t a) { return *reinterpret_cast<const uint32_t*>(sm + a); }
 
-// n bytes from shared offset s to shared offset d, any alignment on both sides.  Looks at most one aligned word
-// (4 bytes) beyond s + n.
+// n bytes from shared offset s to shared offset d, any alignment on both sides.  Looks at most 7 bytes beyond s + n.
 __device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, uint32_t n) {
     if (n == 0) return;
-    const uint32_t h = min((4u - (d & 3u)) & 3u, n);
-    for (uint32_t i = 0; i < h; i++) sm[d + i] = sm[s + i];
+    const uint32_t h = min((4u - (d & 3u)) & 3u, n);  // bytes in front of the first whole output word
+    if (h > 0) sm[d] = sm[s];
+    if (h > 1) sm[d + 1] = sm[s + 1];
+    if (h > 2) sm[d + 2] = sm[s + 2];
     s += h;
     d += h;
     n -= h;
@@ -90,9 +91,13 @@ __device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, ui
         w0 = w1;
         d += 4;
     }
-    s = sa + (sh >> 3);
-    n &= 3u;
-    for (uint32_t i = 0; i < n; i++) sm[d + i] = sm[s + i];
+    n &= 3u;  // bytes behind the last whole word: the low bytes of one more funnel shift
+    if (n) {
+        const uint32_t w = __funnelshift_r(w0, lds32(sm, sa + 4), sh);
+        sm[d] = (uint8_t)w;
+        if (n > 1) sm[d + 1] = (uint8_t)(w >> 8);
+        if (n > 2) sm[d + 2] = (uint8_t)(w >> 16);
+    }
 }
 
 // are the n bytes at shared offsets x and y different?
@@ -115,14 +120,16 @@ __device__ __forceinline__ bool differ_s(const uint8_t* sm, uint32_t x, uint32_t
     return diff != 0;
 }
 
+// PAIRED: two mates per pair; ONE_POOL: text batch (header, bases and qualities of a mate in one buffer)
+template <bool PAIRED, bool ONE_POOL>
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_constant__ EmitParams E) {
     extern __shared__ __align__(16) uint8_t es_smem[];
     __shared__ unsigned int wtot[8][ES_WARPS];  // per-stream totals of every warp
     const PairParams& P = E.pp;
     const uint32_t base = blockIdx.x * CSQ_PAIR_BLOCK;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool paired = P.n_mates == 2;
-    const int n_mates = paired ? 2 : 1;
+    constexpr bool paired = PAIRED;
+    constexpr int n_mates = PAIRED ? 2 : 1;
     uint8_t* const sm = es_smem + (uint32_t)wid * ES_WARP_BYTES;
 
     // ---- phase 1: where does every record go (thread per pair) ----
@@ -193,11 +200,11 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
     const uint8_t* const poolA = (P.rename_parts & CSQ_REN_R1_PREFIX) ? P.md[0].seq : nullptr;
     const uint8_t* const poolB = (P.rename_parts & CSQ_REN_R2_PREFIX) ? P.md[1].seq : nullptr;
     // a text batch keeps header, bases and qualities of a mate in ONE buffer: one source span per mate and pass
-    const bool one_pool = P.md[0].seq == P.md[0].name && P.md[0].seq == P.md[0].qual;
-    const int n_pools = one_pool ? 1 : 3;
+    constexpr bool one_pool = ONE_POOL;
+    constexpr int n_pools = ONE_POOL ? 1 : 3;
 
     const int q = lane >> 1, role = lane & 1;
-    const int ppass = paired ? 8 : 16;
+    constexpr int ppass = PAIRED ? 8 : 16;
     const int my_mt = paired ? (q & 1) : 0;
     const int my_pp = paired ? (q >> 1) : q;  // pair of the pass this lane works on
     bool id_mismatch = false;
@@ -348,16 +355,21 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             const uint8_t* __restrict__ pa = (poolA ? poolA : md.seq) + R.pa;
             const uint8_t* __restrict__ pb = (poolB ? poolB : md.seq) + R.pb;
             const uint32_t du = d0 + 1u + id_len + 1u;
-            for (uint32_t x0 = 0; x0 < lab; x0 += 8) {
-                uint8_t v[8];
+            const uint32_t lb = lab - la;
+#pragma unroll 1
+            for (uint32_t x0 = 0; x0 < max(la, lb); x0 += 8) {
+                uint8_t va[8], vb[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    const uint32_t x = x0 + u;
-                    v[u] = x < lab ? (x < la ? pa[x] : pb[x - la]) : (uint8_t)0;
+                    va[u] = vb[u] = 0;
+                    if (x0 + u < la) va[u] = pa[x0 + u];
+                    if (x0 + u < lb) vb[u] = pb[x0 + u];
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (x0 + u < lab) sm[du + x0 + u] = v[u];
+                for (int u = 0; u < 8; u++) {
+                    if (x0 + u < la) sm[du + x0 + u] = va[u];
+                    if (x0 + u < lb) sm[du + la + x0 + u] = vb[u];
+                }
             }
         }
         __pipeline_wait_prior(0);
@@ -423,13 +435,22 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
     if (__any_sync(FULL, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
 }
 
+template <bool PAIRED, bool ONE_POOL>
+cudaError_t launch_stage(const EmitParams& p, cudaStream_t stream) {
+    // per device: a function attribute belongs to the current context
+    cudaError_t attr = cudaFuncSetAttribute(k_emit_stage<PAIRED, ONE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ES_WARPS * ES_WARP_BYTES));
+    if (attr != cudaSuccess) return attr;
+    k_emit_stage<PAIRED, ONE_POOL><<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, ES_WARPS * ES_WARP_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t csq_launch_emit_stage(const EmitParams& p, cudaStream_t stream) {
     if (p.pp.n == 0) return cudaSuccess;
-    // per device: a function attribute belongs to the current context
-    cudaError_t attr = cudaFuncSetAttribute(k_emit_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ES_WARPS * ES_WARP_BYTES));
-    if (attr != cudaSuccess) return attr;
-    k_emit_stage<<<(p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, ES_WARPS * ES_WARP_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    const PairParams& P = p.pp;
+    const bool paired = P.n_mates == 2;
+    const bool one_pool = P.md[0].seq == P.md[0].name && P.md[0].seq == P.md[0].qual;
+    if (paired) return one_pool ? launch_stage<true, true>(p, stream) : launch_stage<true, false>(p, stream);
+    return one_pool ? launch_stage<false, true>(p, stream) : launch_stage<false, false>(p, stream);
 }

@@ -667,53 +667,76 @@ __global__ void __launch_bounds__(1024) k_scan(uint32_t nblk, const uint32_t* __
                                                const uint32_t* __restrict__ block_cnt,
                                                unsigned long long* __restrict__ block_off,
                                                unsigned long long* __restrict__ totals) {
-    __shared__ unsigned long long warp_sums[32];
-    __shared__ unsigned long long carry;
+    // all 8 streams in one sweep: thread t takes CTA base + t (its 8 totals are one 32-byte row)
+    __shared__ unsigned long long warp_sums[8][32];
+    __shared__ unsigned long long carry[8];
+    __shared__ unsigned long long cnt_sums[4][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int stream = 0; stream < 8; stream++) {
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        for (uint32_t base = 0; base < nblk; base += 1024) {
-            const uint32_t i = base + threadIdx.x;
-            const unsigned long long v = i < nblk ? block_tot[i * 8 + stream] : 0ULL;
-            unsigned long long x = v;
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            if (lane == 31) warp_sums[wid] = x;
-            __syncthreads();
-            if (wid == 0) {
-                unsigned long long ws = warp_sums[lane];
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned long long y = __shfl_up_sync(0xffffffffu, ws, o);
-                    if (lane >= o) ws += y;
-                }
-                warp_sums[lane] = ws;
-            }
-            __syncthreads();
-            const unsigned long long before = carry + (wid ? warp_sums[wid - 1] : 0ULL) + (x - v);
-            if (i < nblk) block_off[i * 8 + stream] = before;
-            __syncthreads();
-            if (threadIdx.x == 1023) carry = before + v;
-            __syncthreads();
+    if (threadIdx.x < 8) carry[threadIdx.x] = 0;
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    __syncthreads();
+    for (uint32_t base = 0; base < nblk; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long v[8], x[8];
+        if (i < nblk) {
+            const uint4 lo = reinterpret_cast<const uint4*>(block_tot)[2 * (size_t)i];
+            const uint4 hi = reinterpret_cast<const uint4*>(block_tot)[2 * (size_t)i + 1];
+            const uint4 c = reinterpret_cast<const uint4*>(block_cnt)[i];
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+            v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            cnt[0] += c.x; cnt[1] += c.y; cnt[2] += c.z; cnt[3] += c.w;
+        } else {
+#pragma unroll
+            for (int s = 0; s < 8; s++) v[s] = 0;
         }
-        if (threadIdx.x == 0) totals[stream] = carry;
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            unsigned long long y = v[s];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long z = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= o) y += z;
+            }
+            x[s] = y;
+            if (lane == 31) warp_sums[s][wid] = y;
+        }
+        __syncthreads();
+        if (wid < 8) {  // warp s scans the 32 warp totals of stream s
+            unsigned long long ws = warp_sums[wid][lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long z = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += z;
+            }
+            warp_sums[wid][lane] = ws;
+        }
+        __syncthreads();
+        unsigned long long before[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) before[s] = carry[s] + (wid ? warp_sums[s][wid - 1] : 0ULL) + (x[s] - v[s]);
+        if (i < nblk) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(block_off + (size_t)i * 8);
+#pragma unroll
+            for (int s = 0; s < 4; s++) dst[s] = make_ulonglong2(before[2 * s], before[2 * s + 1]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+#pragma unroll
+            for (int s = 0; s < 8; s++) carry[s] = before[s] + v[s];
+        }
         __syncthreads();
     }
+    if (threadIdx.x < 8) totals[threadIdx.x] = carry[threadIdx.x];
     // record counts per destination
+#pragma unroll
     for (int d = 0; d < 4; d++) {
-        unsigned long long s = 0;
-        for (uint32_t i = threadIdx.x; i < nblk; i += 1024) s += block_cnt[i * 4 + d];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) warp_sums[wid] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long t = 0;
-            for (int w = 0; w < 32; w++) t += warp_sums[w];
-            totals[8 + d] = t;
-        }
-        __syncthreads();
+        unsigned long long t = cnt[d];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) cnt_sums[d][wid] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 32; w++) t += cnt_sums[threadIdx.x][w];
+        totals[8 + threadIdx.x] = t;
     }
 }
 

@@ -173,10 +173,15 @@ __global__ void __launch_bounds__(256) k_records(const ParseParams P) {
 }
 
 
-// ---- one-pass form (default) -------------------------------------------------------------------------------
+// ---- one-pass form (CSQ_PLAN_PARSE_ONEPASS) -------------------------------------------------------------------------------
 // k_parse_onepass reads the text ONCE and writes the record index directly; nothing else is written or read
 // back (the four-kernel form above moves 1/8 of the text twice as masks, 16 bytes of line-end offsets per record
 // twice, and k_records looks at ~4 sectors of every record again).
+// Measured on B200 (1 M pairs, ncu, profiles/r01_ncu_onepass_stage.csv): 240 us against 187 us for the four
+// kernels - DRAM traffic is 357 MB instead of ~560 MB, but every tile is one latency chain (load -> masks ->
+// scan -> look-back -> walk, three barriers) and 8 resident CTAs x 16 KiB per SM cannot cover it (19 % of the
+// DRAM peak, top stall: barrier).  Kept behind the flag; the next form would be persistent CTAs that prefetch
+// tile i + 1 while tile i is in its look-back.
 //
 // A CTA takes the next 16 KiB tile (ticket counter, so tiles start in order), loads it fully coalesced, leaves the
 // line-end masks in shared memory, and learns what lies in front of its tile - the number of line ends and the
@@ -337,8 +342,8 @@ __global__ void __launch_bounds__(256) k_records_fix(const ParseParams P, const 
 
 uint32_t csq_parse_tiles(uint64_t bytes) { return (uint32_t)((bytes + TILE_BYTES - 1) / TILE_BYTES); }
 
-// v1 = the four-kernel form (CSQ_PLAN_PARSE_V1, A/B runs): `tiles` holds u32 tile counts, `masks` the line-end
-// masks, p.nl the line-end offsets.  Default: `tiles` holds one u64 status word per tile (zeroed here), p.nl is
+// v1 = the four-kernel form (default): `tiles` holds u32 tile counts, `masks` the line-end
+// masks, p.nl the line-end offsets.  One-pass form (CSQ_PLAN_PARSE_ONEPASS): `tiles` holds one u64 status word per tile (zeroed here), p.nl is
 // scratch for the quality lengths (n words), `ticket` one zeroed u32.
 cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* masks, uint32_t* ticket, bool v1, cudaStream_t stream) {
     const uint32_t tiles = csq_parse_tiles(p.bytes);

@@ -353,7 +353,7 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
         if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.name_off[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.name_end[m].ensure((size_t)n * 4 + 16))) return rc;
-        if (plan->flags & CSQ_PLAN_PARSE_V1) {
+        if (!(plan->flags & CSQ_PLAN_PARSE_ONEPASS)) {
             if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
             if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;  // 16 bits per 16-byte chunk
         } else {
@@ -463,7 +463,7 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
         pp.name_off = (uint32_t*)s.name_off[m].p;
         pp.name_end = (uint32_t*)s.name_end[m].p;
         pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
-        const bool v1 = (plan->flags & CSQ_PLAN_PARSE_V1) != 0;
+        const bool v1 = !(plan->flags & CSQ_PLAN_PARSE_ONEPASS);
         CUDA_TRY(csq_launch_parse(pp, s.tiles[m].p, (uint16_t*)s.masks[m].p, (uint32_t*)((uint8_t*)s.parse_misc.p + 32) + m, v1, st));
         plan->launches += csq_parse_tiles(pp.bytes) ? (v1 ? 4 : 2) : 1;
         if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");

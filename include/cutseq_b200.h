@@ -224,8 +224,8 @@ typedef struct csq_plan csq_plan;
                                      the default k_emit_stage (staged through shared memory); A/B runs       */
 #define CSQ_PLAN_EMIT_G32 16u     /* ... direct k_emit with 32 lanes per record */
 #define CSQ_PLAN_EMIT_G8 32u      /* ... with 8 lanes per record */
-#define CSQ_PLAN_PARSE_V1 128u   /* text batches: the four-kernel parse (masks + line-end offsets through HBM) instead of
-                                     the one-pass look-back kernel (A/B runs)                                        */
+#define CSQ_PLAN_PARSE_ONEPASS 128u /* text batches: the one-pass look-back parse kernel instead of the default four-kernel
+                                     form (A/B runs; measured slower: one latency chain per 16 KiB tile)             */
 #define CSQ_PLAN_HOMO_V1 512u     /* homopolymer (poly-A / poly-T) exact DP one column at a time instead of two side by side (A/B) */
 #define CSQ_PLAN_EMIT_REC 8u      /* emit FASTQ text with the thread-per-pair 16-byte-chunk kernel instead of the
                                      default k_emit_stage (A/B runs)                                     */

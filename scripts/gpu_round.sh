@@ -12,15 +12,17 @@ if [ "${2:-tests}" = "tests" ]; then
 fi
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err
 echo "bench exit $?"; head -c 600 $OUT/bench.json; echo
-for v in "--emit g16" "--parse v1" "--emit g16 --parse v1 --one-stream" "--one-stream"; do
+VARIANTS="${VARIANTS:---emit g16;--homo v1;--no-numa}"
+IFS=';' read -ra VS <<< "$VARIANTS"
+for v in "${VS[@]}"; do
   name=$(echo $v | tr -d ' -')
-  timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-files --no-e2e $v > $OUT/bench_$name.json 2> $OUT/bench_$name.err
+  timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-files $v > $OUT/bench_$name.json 2> $OUT/bench_$name.err
   echo "bench $v exit $?"
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu --no-files --no-e2e --batches 2 --batch-pairs 1000000 > $OUT/ncu_launch.log 2>&1
 echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_emit_stage|k_parse_onepass|k_records_fix' -c 6 -o $OUT/new_kernels \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_emit_stage|k_align|k_scan}" -c ${NCU_COUNT:-8} -o $OUT/new_kernels \
   python bench.py --steps 1 --warmup 0 --no-cpu --no-files --no-e2e --batches 1 --batch-pairs 1000000 > $OUT/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT

@@ -300,8 +300,8 @@ def test_synthetic_configs_against_oracle():
 
 
 # ---- text batches: raw FASTQ bytes in, the device builds the record index (parse.cu) ----
-PARSE_FLAGS = [0, A.PLAN_PARSE_V1]
-PARSE_IDS = ["onepass", "parse_v1"]
+PARSE_FLAGS = [0, A.PLAN_PARSE_ONEPASS]
+PARSE_IDS = ["parse_v1", "onepass"]
 
 
 @pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
