@@ -288,14 +288,15 @@ def main():
     ms = max_over_ranks(ms)
     value = world * args.steps * P / (ms * 1e-3)
     # launches of the sizing pass are outside the CUDA-event bracket: count the timed ones only
-    per_step_launches = launches // (args.steps + B) if (args.steps + B) else 0
+    # csq_run_steps = B sizing steps + K timed steps + 1 per-kernel profiling step
+    per_step_launches = launches // (args.steps + B + 1)
     timed_launches = per_step_launches * args.steps
 
     # nominal DP cells (device counters) over the timed + sizing steps -> cells per step
     def cells(c):
         return sum(sum(c.dp_cells[m]) for m in range(2))
 
-    cells_per_step = (cells(c1) - cells(c0)) / (args.steps + B)
+    cells_per_step = (cells(c1) - cells(c0)) / (args.steps + B + 1)
     gcups_whole_chain = cells_per_step / (ms / args.steps * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H timed) ----
@@ -358,7 +359,7 @@ def main():
     for m, ops in enumerate((prog.ops_r1, prog.ops_r2)):
         for t, op in enumerate(ops):
             if op.kind == A.OP_ALIGN:
-                align_cells.append((c1.dp_cells[m][t] - c0.dp_cells[m][t]) / (args.steps + B))
+                align_cells.append((c1.dp_cells[m][t] - c0.dp_cells[m][t]) / (args.steps + B + 1))
     # one entry per ALIGN op: its k_prefilter launch (if any) plus its k_align launch
     align_ops = []
     for name, kms in ktimes:
@@ -428,7 +429,7 @@ def main():
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
         "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; {B} resident batches x {P} pairs per GPU "
-                               f"(= {B * P} pairs), step = one batch; consecutive steps use different batches "
+                               f"(= {B * P} pairs), step = one batch, each on the streams of its own slot (as behind csq_submit; steps on different slots may overlap); consecutive steps use different batches "
                                f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
                                f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
