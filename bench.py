@@ -429,7 +429,7 @@ def main():
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
         "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; {B} resident batches x {P} pairs per GPU "
-                               f"(= {B * P} pairs), step = one batch, each on the streams of its own slot (as behind csq_submit; steps on different slots may overlap); consecutive steps use different batches "
+                               f"(= {B * P} pairs), step = one batch; consecutive steps use different batches "
                                f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
                                f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",

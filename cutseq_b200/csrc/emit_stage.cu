@@ -11,19 +11,20 @@
 //                               stream -> where every record goes.  The descriptors stay in registers.
 //   then each WARP walks its 32 pairs in passes of up to 8 pairs (16 single-end reads) = 16 records x 2 lanes:
 //   load      the source bytes of the pass - in a text batch one contiguous span of the FASTQ text per mate - come
-//             in with 16-byte cp.async copies, lane-strided (LDGSTS, no registers);
+//             in as ONE bulk copy per span (cp.async.bulk global -> shared, TMA engine), issued by one lane and
+//             awaited by the warp on its own mbarrier (expect_tx = bytes of all spans);
 //   reformat  lane (record, role): role 0 writes '@' id ['_' UMI] '\n' bases '\n', role 1 writes '+' '\n' qualities
 //             '\n' into the staging image of the output, 32-bit words built from two aligned shared-memory words
 //             (funnel shift), ~5 instructions per 4 bytes and no bookkeeping in the loop;
 //   flush     the records of a pass that go to the same output stream are contiguous there: the image is laid
-//             out at the same offset modulo 16 as its place in the output and leaves with 16-byte stores,
-//             lane-strided; only the < 16 bytes at either end of a span go bytewise.
+//             out at the same offset modulo 16 as its place in the output and leaves as ONE bulk copy per span
+//             (cp.async.bulk shared -> global); only the < 16 bytes at either end of a span go bytewise.  The
+//             drain is awaited (wait_group.read) just before the next pass writes into the image again.
 //
 // Every source byte is read once and every output byte written once.  A pass that does not fit the staging
 // buffers is halved; a pair that does not fit alone (reads near the length limit with very long headers) takes
 // a bytewise path.  PairedEndRenamer's id check compares the two staged ids.  The reverse-complementing
 // single-end sink stays with k_emit<16>.
-#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,6 +70,38 @@ __device__ __forceinline__ StageRec shfl_rec(const StageRec& r, int src) {
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t* sm, uint32_t a) { return *reinterpret_cast<const uint32_t*>(sm + a); }
 
+// ---- bulk copies (TMA engine, 1-D) and the mbarrier a warp waits on ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, both 16-byte aligned, bytes a multiple of 16; completion is counted on `mbar`
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+// shared -> global, same constraints; part of the thread's current bulk group
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // n bytes from shared offset s to shared offset d, any alignment on both sides.  Looks at most 7 bytes beyond s + n.
 __device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, uint32_t n) {
     if (n == 0) return;
@@ -82,9 +115,24 @@ __device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, ui
     const uint32_t sh = (s & 3u) * 8u;
     uint32_t sa = s & ~3u;
     uint32_t w0 = lds32(sm, sa);
-    const uint32_t nw = n >> 2;
-#pragma unroll 4
-    for (uint32_t i = 0; i < nw; i++) {
+    if ((d & 4u) && n >= 4u) {  // one word to reach an 8-byte boundary of the output
+        sa += 4;
+        const uint32_t w1 = lds32(sm, sa);
+        *reinterpret_cast<uint32_t*>(sm + d) = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+        d += 4;
+        n -= 4;
+    }
+    const uint32_t nd = n >> 3;
+#pragma unroll 2
+    for (uint32_t i = 0; i < nd; i++) {
+        const uint32_t w1 = lds32(sm, sa + 4), w2 = lds32(sm, sa + 8);
+        *reinterpret_cast<uint2*>(sm + d) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+        w0 = w2;
+        sa += 8;
+        d += 8;
+    }
+    if (n & 4u) {
         sa += 4;
         const uint32_t w1 = lds32(sm, sa);
         *reinterpret_cast<uint32_t*>(sm + d) = __funnelshift_r(w0, w1, sh);
@@ -125,12 +173,18 @@ template <bool PAIRED, bool ONE_POOL>
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_constant__ EmitParams E) {
     extern __shared__ __align__(16) uint8_t es_smem[];
     __shared__ unsigned int wtot[8][ES_WARPS];  // per-stream totals of every warp
+    __shared__ __align__(8) unsigned long long load_bar[ES_WARPS];  // one mbarrier per warp: its bulk loads have landed
     const PairParams& P = E.pp;
     const uint32_t base = blockIdx.x * CSQ_PAIR_BLOCK;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr bool paired = PAIRED;
     constexpr int n_mates = PAIRED ? 2 : 1;
     uint8_t* const sm = es_smem + (uint32_t)wid * ES_WARP_BYTES;
+    const uint32_t sm_u32 = smem_u32(sm), bar = smem_u32(&load_bar[wid]);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     // ---- phase 1: where does every record go (thread per pair) ----
     const uint32_t idx = base + threadIdx.x;
@@ -208,6 +262,8 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
     const int my_mt = paired ? (q & 1) : 0;
     const int my_pp = paired ? (q >> 1) : q;  // pair of the pass this lane works on
     bool id_mismatch = false;
+    uint32_t bar_phase = 0;
+    bool draining = false;  // a bulk store of this warp may still be reading the output image
 
     for (int p0 = 0; p0 < n_warp;) {
         const int src_lane = (p0 + my_pp) & 31;
@@ -226,6 +282,16 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
         phi[1] = R.sq + b;
         plo[2] = R.ql + a;
         phi[2] = R.ql + b;
+        // the UMI parts are staged with the bases of the mate whose read they were cut from
+        const uint32_t lb = lab - la;
+        if (la && (!PAIRED || my_mt == 0)) {
+            plo[1] = min(plo[1], R.pa);
+            phi[1] = max(phi[1], R.pa + la);
+        }
+        if (lb && (!PAIRED || my_mt == 1)) {
+            plo[1] = min(plo[1], R.pb);
+            phi[1] = max(phi[1], R.pb + lb);
+        }
         if (one_pool) {
             uint32_t lo = 0xFFFFFFFFu, hi = 0;
 #pragma unroll
@@ -336,47 +402,40 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             continue;
         }
 
-        // ---- load: source spans -> shared memory, UMI parts -> their place in the output image ----
+        // ---- load: one bulk copy per source span ----
+        if (lane == 0) {
+            uint32_t total = 0;
 #pragma unroll
-        for (int mt = 0; mt < 2; mt++)
+            for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                if (sp_n16[mt][k] == 0) continue;
-                const MateDev& md = P.md[mt];
-                const uint8_t* pool = k == 0 ? (one_pool ? md.seq : md.name) : k == 1 ? md.seq : md.qual;
-                const uint8_t* src = pool + sp_lo16[mt][k];
-                uint8_t* dst = sm + ES_SRC0 + sp_base[mt][k];
-                for (uint32_t c = lane; c < sp_n16[mt][k]; c += 32) __pipeline_memcpy_async(dst + 16u * c, src + 16u * c, 16);
-            }
-        __pipeline_commit();
-        const uint32_t d0 = ES_DST0 + ddelta + R.off;  // my record in the output image
-        if (valid && role == 0 && lab) {
-            const MateDev& md = P.md[my_mt];
-            const uint8_t* __restrict__ pa = (poolA ? poolA : md.seq) + R.pa;
-            const uint8_t* __restrict__ pb = (poolB ? poolB : md.seq) + R.pb;
-            const uint32_t du = d0 + 1u + id_len + 1u;
-            const uint32_t lb = lab - la;
-#pragma unroll 1
-            for (uint32_t x0 = 0; x0 < max(la, lb); x0 += 8) {
-                uint8_t va[8], vb[8];
+                for (int k = 0; k < 3; k++) total += sp_n16[mt][k] << 4;
+            if (total) mbar_expect_tx(bar, total);
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    va[u] = vb[u] = 0;
-                    if (x0 + u < la) va[u] = pa[x0 + u];
-                    if (x0 + u < lb) vb[u] = pb[x0 + u];
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (sp_n16[mt][k] == 0) continue;
+                    const MateDev& md = P.md[mt];
+                    const uint8_t* pool = k == 0 ? (one_pool ? md.seq : md.name) : k == 1 ? md.seq : md.qual;
+                    bulk_load(sm_u32 + ES_SRC0 + sp_base[mt][k], pool + sp_lo16[mt][k], sp_n16[mt][k] << 4, bar);
                 }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (x0 + u < la) sm[du + x0 + u] = va[u];
-                    if (x0 + u < lb) sm[du + la + x0 + u] = vb[u];
-                }
-            }
         }
-        __pipeline_wait_prior(0);
+        const uint32_t d0 = ES_DST0 + ddelta + R.off;  // my record in the output image
+        const uint32_t sd_name = sdelta[0], sd_seq = one_pool ? sdelta[0] : sdelta[1], sd_qual = one_pool ? sdelta[0] : sdelta[2];
+        // staged bases of the mates the UMI parts come from (paired: lanes 4 pp .. 4 pp + 3 hold one pair)
+        const uint32_t sd_a = PAIRED ? __shfl_sync(FULL, sd_seq, lane & ~3) : sd_seq;
+        const uint32_t sd_b = PAIRED ? __shfl_sync(FULL, sd_seq, (lane & ~3) | 2) : sd_seq;
+        if (draining) {  // the previous pass's bulk stores must have read the output image before it is written again
+            if (lane == 0) bulk_wait_read();
+            draining = false;
+        }
+        if (__shfl_sync(FULL, sp_n16[0][0] | sp_n16[0][1] | sp_n16[0][2] | sp_n16[1][0] | sp_n16[1][1] | sp_n16[1][2], 0)) {
+            mbar_wait(bar, bar_phase);
+            bar_phase ^= 1u;
+        }
         __syncwarp();
 
         // ---- reformat ----
-        const uint32_t sd_name = sdelta[0], sd_seq = one_pool ? sdelta[0] : sdelta[1], sd_qual = one_pool ? sdelta[0] : sdelta[2];
         const uint32_t s_id = ES_SRC0 + sd_name + R.nm;
         if (valid) {
             const uint32_t d_seq = d0 + 1u + id_len + umi_len + 1u;
@@ -386,7 +445,11 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             if (role == 0) {
                 sm[d0] = '@';
                 copy_s2s(sm, s_id, d0 + 1u, id_len);
-                if (umi_len) sm[d0 + 1u + id_len] = '_';
+                if (umi_len) {
+                    sm[d0 + 1u + id_len] = '_';
+                    copy_s2s(sm, ES_SRC0 + sd_a + R.pa, d0 + 2u + id_len, la);
+                    copy_s2s(sm, ES_SRC0 + sd_b + R.pb, d0 + 2u + id_len + la, lb);
+                }
                 sm[d_seq - 1u] = '\n';
                 sm[d_seq + seq_len] = '\n';
             } else {
@@ -401,7 +464,9 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
         }
         __syncwarp();
 
-        // ---- flush: every (destination, mate) span of the pass, 16 bytes per lane and store ----
+        // ---- flush: every (destination, mate) span of the pass leaves as one bulk copy ----
+        fence_async_smem();  // the image was written through the generic proxy, the bulk copy reads it through the async proxy
+        __syncwarp();
         {
             uint32_t dcursor = 0;
 #pragma unroll
@@ -419,19 +484,20 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                         dcursor = dstart + bytes;
                         const uint8_t* __restrict__ sp = sm + ES_DST0 + dstart;
                         const uint32_t head = min((16u - mis) & 15u, bytes);
+                        const uint32_t body = (bytes - head) & ~15u;
+                        const uint32_t done = head + body, tail = bytes - done;
+                        if (lane == 0 && body) bulk_store(gp + head, sm_u32 + ES_DST0 + dstart + head, body);
                         if ((uint32_t)lane < head) gp[lane] = sp[lane];
-                        const uint32_t nvec = (bytes - head) >> 4;
-                        const uint4* __restrict__ sv = reinterpret_cast<const uint4*>(sp + head);
-                        uint4* __restrict__ gv = reinterpret_cast<uint4*>(gp + head);
-                        for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
-                        const uint32_t done = head + (nvec << 4), tail = bytes - done;
-                        if ((uint32_t)lane < tail) gp[done + lane] = sp[done + lane];
+                        if ((uint32_t)lane >= 16u && (uint32_t)lane - 16u < tail) gp[done + lane - 16u] = sp[done + lane - 16u];
                     }
                 }
         }
+        if (lane == 0) bulk_commit();
+        draining = true;
         __syncwarp();
         p0 += g;
     }
+    if (draining && lane == 0) bulk_wait_read();  // shared memory must outlive the reads of the last bulk stores
     if (__any_sync(FULL, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
 }
 

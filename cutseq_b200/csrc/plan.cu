@@ -899,29 +899,16 @@ int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, floa
         if ((rc = check_device_error(s, 13))) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(st));
-    // Timed region.  Every batch runs on the streams of its own slot, as it does behind csq_submit: consecutive
-    // steps work on different batches and may overlap (the HBM-bound parse / emit kernels of one batch beside the
-    // ALU-bound DP kernels of another, single-CTA scans beside anything); steps on the same slot stay in order.
-    // CSQ_PLAN_ONE_STREAM keeps the whole run on one stream.  Bracket: ev[0] on the first slot's stream, which
-    // every other stream waits for; ev[1] there again after it has waited for the last work of every stream.
-    const bool overlap = !(plan->flags & CSQ_PLAN_ONE_STREAM) && n_slots > 1;
+    // Timed region: step i on slots[i % n_slots], back to back on the first slot's stream pair (the chains of the two
+    // mates side by side).  Running every batch on the streams of its own slot, so that steps overlap, was measured
+    // and did not help (4.66 ms against 4.51 ms per step, profiles/r01_overlap_steps.md): the large kernels fill the
+    // machine on their own and five batches in flight only add L2 pressure.
     CUDA_TRY(cudaEventRecord(s0.ev[0], st));
-    bool used[CSQ_N_SLOTS] = {};
     for (int it = 0; it < steps; it++) {
         Slot& s = plan->slots[slots[it % n_slots]];
-        cudaStream_t ss = overlap ? s.stream : st;
-        if (overlap && &s != &s0 && !used[slots[it % n_slots]]) CUDA_TRY(cudaStreamWaitEvent(ss, s0.ev[0], 0));
-        used[slots[it % n_slots]] = true;
-        if ((rc = enqueue_front(plan, s, nullptr, ss, overlap ? s.stream2 : s0.stream2))) return rc;
-        if ((rc = enqueue_emit(plan, s, nullptr, ss))) return rc;
+        if ((rc = enqueue_front(plan, s, nullptr, st, s0.stream2))) return rc;
+        if ((rc = enqueue_emit(plan, s, nullptr, st))) return rc;
     }
-    if (overlap)
-        for (int i = 0; i < CSQ_N_SLOTS; i++) {
-            Slot& s = plan->slots[i];
-            if (!used[i] || &s == &s0) continue;
-            CUDA_TRY(cudaEventRecord(s.ev[5], s.stream));
-            CUDA_TRY(cudaStreamWaitEvent(st, s.ev[5], 0));
-        }
     CUDA_TRY(cudaEventRecord(s0.ev[1], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;

@@ -256,12 +256,10 @@ int csq_slot_times(csq_plan* plan, int slot, float* total_ms, float* kernel_ms);
 int csq_upload(csq_plan* plan, int slot, const csq_batch_in* in);
 int csq_upload_text(csq_plan* plan, int slot, const csq_batch_text* in);
 int csq_run_resident(csq_plan* plan, int slot, int iters, float* ms_per_iter);
-/* The same over several uploaded slots: after an untimed sizing pass per slot, `steps` steps run,
- * step i on slots[i % n_slots] and on that slot's own streams - as behind csq_submit, steps on different
- * slots may overlap, steps on one slot stay in order (CSQ_PLAN_ONE_STREAM: everything on one stream).
- * total_ms is the CUDA-event time from before the first to after the last kernel of the whole loop
- * (consecutive steps touch different data, each far larger than L2).  One further, untimed step on a
- * single stream follows for the per-kernel times (csq_kernel_times). */
+/* The same over several uploaded slots: after an untimed sizing pass per slot, `steps` steps run
+ * back to back on one stream pair, step i on slots[i % n_slots]; total_ms is the CUDA-event time of
+ * the whole loop (consecutive steps touch different data, each far larger than L2).  One further,
+ * untimed step on a single stream follows for the per-kernel times (csq_kernel_times). */
 int csq_run_steps(csq_plan* plan, const int* slots, int n_slots, int steps, float* total_ms);
 /* Per-kernel device times (ms, last step of the last csq_run_resident / csq_run_steps call; for
  * csq_run_steps query the first slot of the list). names
