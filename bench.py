@@ -394,14 +394,14 @@ def main():
                    f"launches; peak = csq_int_peak measured live (ALU-only {alu_peak / 1e12:.2f}, ALU+FMA mix {mixed_peak / 1e12:.2f} "
                    "T lane-op/s). With the bit-parallel prefilter most nominal cells are never visited, so this can exceed 1.",
         }
-    roofline_hbm = {"bound": "hbm", "kernel": "k_emit", "achieved": (emit_bytes / (emit_ms * 1e-3) / 1e9) if emit_ms else None,
+    roofline_hbm = {"bound": "hbm", "kernel": {"stage": "k_emit_stage", "rec": "k_emit_rec"}.get(args.emit, "k_emit<%s>" % args.emit[1:]), "achieved": (emit_bytes / (emit_ms * 1e-3) / 1e9) if emit_ms else None,
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "traffic": None,
                     "how": "algorithmic bytes per launch (input records read once + FASTQ text written once) / CUDA-event duration"}
     if roofline_hbm["achieved"]:
         roofline_hbm["frac"] = roofline_hbm["achieved"] / hbm_peak
     try:  # DRAM bytes of one launch from the committed ncu capture (per pair, scaled to this batch size)
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f)["k_emit"]
+            tr = json.load(f)[{"stage": "k_emit", "g16": "k_emit_g16"}[args.emit]]
         roofline_hbm["traffic"] = tr["dram_bytes_per_pair"] * P
         roofline_hbm["traffic_source"] = tr["source"]
     except Exception:

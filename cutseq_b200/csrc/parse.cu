@@ -63,17 +63,29 @@ __global__ void __launch_bounds__(TILE_THREADS) k_nl_count(const uint8_t* __rest
     }
 }
 
-// One CTA: exclusive scan of n_tiles counts in place; total[0] = number of line ends.
+// One CTA: exclusive scan of n_tiles counts in place; total[0] = number of line ends.  Thread t takes 8
+// consecutive tiles per sweep (two 16-byte loads), so a 715 MB mate (43 600 tiles) needs 6 sweeps.
 __global__ void __launch_bounds__(1024) k_tile_scan(uint32_t n_tiles, uint32_t* __restrict__ tile_cnt, uint32_t* __restrict__ total) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_tiles ? tile_cnt[i] : 0u;
-        uint32_t x = v;
+    for (uint32_t base = 0; base < n_tiles; base += 8192) {
+        const uint32_t i0 = base + threadIdx.x * 8u;
+        uint32_t v[8];
+        if (i0 + 8 <= n_tiles) {  // the buffer is 16-byte aligned and i0 a multiple of 8
+            const uint4 lo = *reinterpret_cast<const uint4*>(tile_cnt + i0), hi = *reinterpret_cast<const uint4*>(tile_cnt + i0 + 4);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+            v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = i0 + u < n_tiles ? tile_cnt[i0 + u] : 0u;
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) mine += v[u];
+        uint32_t x = mine;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
@@ -89,10 +101,24 @@ __global__ void __launch_bounds__(1024) k_tile_scan(uint32_t n_tiles, uint32_t* 
             warp_sums[lane] = ws;
         }
         __syncthreads();
-        const uint32_t before = carry + (wid ? warp_sums[wid - 1] : 0u) + (x - v);
-        if (i < n_tiles) tile_cnt[i] = before;
+        uint32_t run = carry + (wid ? warp_sums[wid - 1] : 0u) + (x - mine);  // line ends in front of tile i0
+        const uint32_t sweep_total = warp_sums[31];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t c = v[u];
+            v[u] = run;
+            run += c;
+        }
+        if (i0 + 8 <= n_tiles) {
+            *reinterpret_cast<uint4*>(tile_cnt + i0) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(tile_cnt + i0 + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (i0 + u < n_tiles) tile_cnt[i0 + u] = v[u];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == 0) carry += sweep_total;
         __syncthreads();
     }
     if (threadIdx.x == 0) total[0] = carry;

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -637,6 +638,8 @@ int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, 
     if (rc) return rc;
     csq_plan* plan = new csq_plan();
     plan->device = device;
+    // CSQ_PLAN_FLAGS=<int>: extra plan flags for A/B and tool runs without touching the caller (e.g. 256 = direct emitter)
+    if (const char* extra = getenv("CSQ_PLAN_FLAGS")) flags |= (uint32_t)strtoul(extra, nullptr, 0);
     plan->flags = flags;
     plan->flt = *filters;
     plan->n_mates = n2 > 0 ? 2 : 1;
