@@ -32,6 +32,10 @@
 
 namespace {
 
+#ifndef CSQ_HOMO_COLUMNS
+#define CSQ_HOMO_COLUMNS 4  // DP columns a thread computes side by side for homopolymer adapters (dp_homo)
+#endif
+
 constexpr int SP_SHIFT = 10, PRIO_SHIFT = 20, COST_SHIFT = 22;
 constexpr int ORG_BIAS = 128;
 constexpr uint32_t D_MATCH = 1u << SP_SHIFT;
@@ -209,10 +213,12 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
 // Homopolymer adapter (the poly-A / poly-T 100-mers of run.py:389-404): every row compares against the same
 // base, so a column needs one match/mismatch delta and no match mask.  A thread walks a column top to bottom,
 // each cell waiting for the one above it: a dependent chain of 3 instructions x M cells that a register-bound
-// kernel (M + 1 live cells, 2 CTAs per SM) cannot hide.  Two columns are therefore computed side by side, column
-// j + 1 one row behind column j - two independent chains, same cells, same order of the row-m / last-column
-// rules.  Everything else (init, early stop after k + 1 foreign characters, best-match rules) is dp_exact's.
-template <int M>
+// kernel (M + 1 live cells, 2 CTAs per SM) cannot hide.  KC columns are therefore computed side by side, column
+// j + c running c rows behind column j (a skewed wavefront inside the thread): KC independent chains, the same
+// cells, the same order of the row-m / last-column rules.  Chain c keeps its two newest cells (p1, p2); cell
+// (r, j + c) = min3(p2[c-1] + delta_c, p1[c] + INS, p1[c-1] + DEL), chain -1 being the stored column j - 1.
+// Everything else (init, early stop after k + 1 foreign characters, best-match rules) is dp_exact's.
+template <int M, int KC>
 __device__ __forceinline__ void dp_homo(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P, int j0,
                                         csq_match& r) {
     const int n = b - a;
@@ -238,55 +244,67 @@ __device__ __forceinline__ void dp_homo(const uint8_t* __restrict__ s, int a, in
     bool cut_short = false;
     int j = min_n + 1;
     while (j <= max_n) {
-        const bool eq0 = ((uint32_t)*p & 0xDFu) == letter;
-        if (!siq) {
-            foreign += eq0 ? 0 : 1;
-            if (foreign > k) {  // no cell of this or any later column can be accepted (see dp_exact)
-                cut_short = true;
-                break;
-            }
-        }
-        const uint32_t d0 = eq0 ? D_MATCH : D_MIS;
-        bool two = j + 1 <= max_n;
-        bool eq1 = false;
-        if (two) {
-            eq1 = ((uint32_t)p[step] & 0xDFu) == letter;
-            if (!siq && foreign + (eq1 ? 0 : 1) > k) two = false;  // the scan stops at column j + 1: finish column j alone
-        }
-        if (two) {
-            if (!siq) foreign += eq1 ? 0 : 1;
-            const uint32_t d1 = eq1 ? D_MATCH : D_MIS;
-            uint32_t wd = W[0];                        // cell (i - 1, j - 1)
-            const uint32_t a0 = wd + row0_delta;       // cell (0, j)
-            const uint32_t b0 = a0 + row0_delta;       // cell (0, j + 1)
-            W[0] = b0;
-            uint32_t am2 = a0, am1 = a0, bm1 = b0;     // cells (i - 2, j), (i - 1, j), (i - 2, j + 1)
-            uint32_t wm_a = 0, wm_b = 0;
+        // a block of KC columns, unless the read or the early stop ends inside it
+        bool block = j + KC - 1 <= max_n;
+        uint32_t d[KC];
+        int f = foreign;
+        if (block) {
 #pragma unroll
-            for (int i = 1; i <= M + 1; i++) {
-                uint32_t ai = 0;
-                if (i <= M) {
-                    const uint32_t wl = W[i];          // cell (i, j - 1)
-                    ai = __vimin3_u32(wd + d0, am1 + D_INS, wl + D_DEL) & PRIO_CLEAR;
-                    wd = wl;
-                    if (i == M) wm_a = ai;
+            for (int c = 0; c < KC; c++) {
+                const bool eq = ((uint32_t)p[c * step] & 0xDFu) == letter;
+                d[c] = eq ? D_MATCH : D_MIS;
+                f += eq ? 0 : 1;
+            }
+            if (!siq && f > k) block = false;  // the scan stops inside the block: column by column from here
+        }
+        if (block) {
+            foreign = f;
+            uint32_t p1[KC], p2[KC], wm[KC];
+            uint32_t wd = W[0];  // stored column j - 1, one row up
+#pragma unroll
+            for (int c = 0; c < KC; c++) {
+                p1[c] = p2[c] = W[0] + (uint32_t)(c + 1) * row0_delta;  // row 0 of column j + c
+                wm[c] = 0;
+            }
+            W[0] = p1[KC - 1];
+#pragma unroll
+            for (int i = 1; i <= M + KC - 1; i++) {
+#pragma unroll
+                for (int c = KC - 1; c >= 0; c--) {  // descending: chain c - 1 still holds the previous step's cells
+                    const int row = i - c;
+                    if (row < 1 || row > M) continue;
+                    uint32_t diag, left;
+                    if (c == 0) {
+                        left = W[row];  // stored column j - 1
+                        diag = wd;
+                        wd = left;
+                    } else {
+                        left = p1[c - 1];
+                        diag = p2[c - 1];
+                    }
+                    const uint32_t cell = __vimin3_u32(diag + d[c], p1[c] + D_INS, left + D_DEL) & PRIO_CLEAR;
+                    p2[c] = p1[c];
+                    p1[c] = cell;
+                    if (c == KC - 1) W[row] = cell;
+                    if (row == M) wm[c] = cell;
                 }
-                if (i >= 2) {                          // cell (i - 1, j + 1)
-                    const uint32_t bi = __vimin3_u32(am2 + d1, bm1 + D_INS, am1 + D_DEL) & PRIO_CLEAR;
-                    W[i - 1] = bi;
-                    bm1 = bi;
-                    if (i - 1 == M) wm_b = bi;
-                }
-                am2 = am1;
-                am1 = ai;
             }
             if (eiq) {
-                row_m_update(wm_a, j, M, n, P, best);
-                row_m_update(wm_b, j + 1, M, n, P, best);
+#pragma unroll
+                for (int c = 0; c < KC; c++) row_m_update(wm[c], j + c, M, n, P, best);
             }
-            j += 2;
-            p += 2 * step;
+            j += KC;
+            p += KC * step;
         } else {
+            const bool eq = ((uint32_t)*p & 0xDFu) == letter;
+            if (!siq) {
+                foreign += eq ? 0 : 1;
+                if (foreign > k) {  // no cell of this or any later column can be accepted (see dp_exact)
+                    cut_short = true;
+                    break;
+                }
+            }
+            const uint32_t d0 = eq ? D_MATCH : D_MIS;
             uint32_t wd = W[0];
             W[0] += row0_delta;
 #pragma unroll
@@ -353,7 +371,7 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
 }
 
 // HOMO: 0 = any adapter, 1 = homopolymer adapter, one column at a time (CSQ_PLAN_HOMO_V1, A/B runs),
-// 2 = homopolymer adapter, two columns side by side (dp_homo)
+// 2 = homopolymer adapter, CSQ_HOMO_COLUMNS columns side by side (dp_homo)
 template <int M, int HOMO>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
@@ -415,7 +433,7 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
         }
     }
     if constexpr (HOMO == 2)
-        dp_homo<M>(s, st.a, st.b, P, j0, r);
+        dp_homo<M, CSQ_HOMO_COLUMNS>(s, st.a, st.b, P, j0, r);
     else if constexpr (M > 0)
         dp_exact<M, HOMO>(s, st.a, st.b, P, lut, j0, r);
     else
