@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="stage", choices=["stage", "g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
     ap.add_argument("--homo", default="two", choices=["two", "v1"], help="poly-A / poly-T exact DP: two columns side by side (default) or one (A/B runs)")
+    ap.add_argument("--no-exact-stop", action="store_true", help="exact DP walks on after an error-free full match (CSQ_PLAN_NO_EXACT_STOP, A/B runs)")
     ap.add_argument("--parse", default="v1", choices=["onepass", "v1"], help="text-batch parse (A/B runs); v1 (four kernels) is the product default, onepass = single look-back kernel")
     ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
     ap.add_argument("--input", default="text", choices=["text", "soa"], help="batch form handed to the library")
@@ -235,7 +236,7 @@ def main():
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
     plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0)
-                       | (A.PLAN_PARSE_ONEPASS if args.parse == "onepass" else 0) | (A.PLAN_HOMO_V1 if args.homo == "v1" else 0))
+                       | (A.PLAN_PARSE_ONEPASS if args.parse == "onepass" else 0) | (A.PLAN_HOMO_V1 if args.homo == "v1" else 0) | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
@@ -433,7 +434,7 @@ def main():
                                f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
                                f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
-                   "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse, "homo_dp": args.homo, "numa_node": numa_node},
+                   "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse, "homo_dp": args.homo, "exact_stop": not args.no_exact_stop, "numa_node": numa_node},
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
         "roofline": roofline, "roofline_dp": roofline_dp, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
         "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,

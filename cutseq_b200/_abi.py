@@ -47,6 +47,7 @@ PLAN_ONE_STREAM = 64
 PLAN_PARSE_ONEPASS = 128
 PLAN_EMIT_G16 = 256
 PLAN_HOMO_V1 = 512
+PLAN_NO_EXACT_STOP = 1024
 
 
 class csq_op(C.Structure):

@@ -12,7 +12,8 @@
 // cost is stored in 10 bits                  -> m + n <= 1023
 #define CSQ_FAST_MAX_READ 895
 #define CSQ_MAX_PRE 12 /* scalar ops executed in front of one ALIGN op */
-#define CSQ_PF_BINS 4   /* prefilter survivor lists (classes of DP columns left for the exact pass) */
+#define CSQ_PF_BINS 5   /* prefilter survivor lists: classes of DP columns left for the exact pass (0..2 long to medium, 4 short)
+                           and 3 = reads that hold an error-free copy of the adapter (the exact pass stops there) */
 
 // Scalar (O(1)) ops that sit between alignments: CUT, COND_CUT, RENAME(capture).
 struct DevOp {
@@ -74,6 +75,7 @@ struct AlignParams {
     DevOp pre[CSQ_MAX_PRE];
     // the adapter
     int32_t m, flags, reversed, trim_front, min_overlap, k, adapter_bit, homopolymer;
+    int32_t exact_stop;    // 1: leave the column loop at an error-free full match, as Aligner.locate does ("exact match, stop early")
     uint8_t thr[CSQ_MAX_ADAPTER + 1];  // thr[L] = floor(L * max_error_rate) with host doubles
     uint32_t peq[4][4];                // [A,C,G,T][word]: bit i-1 set <=> adapter[i-1] == letter
     uint8_t letter;                    // homopolymer base

@@ -72,13 +72,17 @@ __device__ __forceinline__ void init_cell(int i, int min_n, bool sir, bool siq, 
 }
 
 // Row-m rule of Aligner.locate (only evaluated where cost[m] <= k, as upstream's band does).
-__device__ __forceinline__ void row_m_update(uint32_t wm, int j, int m, int n, const AlignParams& P, Best& best) {
+// Returns true when the new best match is error-free and starts inside the read: Aligner.locate leaves its column
+// loop there ("exact match, stop early").  Nothing later could replace such a match anyway - its score is m, no cell
+// scores higher and an equal score needs cost 0 as well - so stopping and walking on give the same result; the
+// caller stops when P.exact_stop is set.
+__device__ __forceinline__ bool row_m_update(uint32_t wm, int j, int m, int n, const AlignParams& P, Best& best) {
     const int cost = cell_cost(wm);
-    if (cost > P.k) return;
+    if (cost > P.k) return false;
     const int origin = cell_origin(wm), score = cell_score(wm);
     const int length = m + min(origin, 0);
     const bool acceptable = length >= P.min_overlap && cost <= (int)P.thr[length];
-    if (!acceptable) return;
+    if (!acceptable) return false;
     const int best_length = m + min(best.origin, 0);
     if (best.cost == m + n + 1 || (origin <= best.origin + m / 2 && score > best.score) ||
         (length > best_length && score > best.score)) {
@@ -87,7 +91,9 @@ __device__ __forceinline__ void row_m_update(uint32_t wm, int j, int m, int n, c
         best.origin = origin;
         best.ref_stop = m;
         best.query_stop = j;
+        return cost == 0 && origin >= 0;
     }
+    return false;
 }
 
 __device__ __forceinline__ void last_col_update(uint32_t w, int i, int n, const AlignParams& P, Best& best) {
@@ -199,7 +205,10 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
             W[i] = __vimin3_u32(cd, cu, cl) & PRIO_CLEAR;
             wd = wl;
         }
-        if (eiq) row_m_update(W[M], j, M, n, P, best);
+        if (eiq && row_m_update(W[M], j, M, n, P, best) && P.exact_stop) {
+            cut_short = true;  // the last-column rule cannot change an error-free full match either
+            break;
+        }
     }
     if (max_n == n && !cut_short) {
         const int first_i = eir ? 0 : M;
@@ -290,8 +299,13 @@ __device__ __forceinline__ void dp_homo(const uint8_t* __restrict__ s, int a, in
                 }
             }
             if (eiq) {
+                bool stop = false;
 #pragma unroll
-                for (int c = 0; c < KC; c++) row_m_update(wm[c], j + c, M, n, P, best);
+                for (int c = 0; c < KC; c++) stop |= row_m_update(wm[c], j + c, M, n, P, best);
+                if (stop && P.exact_stop) {
+                    cut_short = true;
+                    break;
+                }
             }
             j += KC;
             p += KC * step;
@@ -313,7 +327,10 @@ __device__ __forceinline__ void dp_homo(const uint8_t* __restrict__ s, int a, in
                 W[i] = __vimin3_u32(wd + d0, W[i - 1] + D_INS, wl + D_DEL) & PRIO_CLEAR;
                 wd = wl;
             }
-            if (eiq) row_m_update(W[M], j, M, n, P, best);
+            if (eiq && row_m_update(W[M], j, M, n, P, best) && P.exact_stop) {
+                cut_short = true;
+                break;
+            }
             j += 1;
             p += step;
         }
@@ -347,6 +364,7 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
     const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
     const int step = P.reversed ? -1 : 1;
     const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    bool exact_stop = false;
     for (int j = min_n + 1; j <= max_n; j++, p += step) {
         const uint32_t c = *p & 0xDFu;
         const int li = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
@@ -361,9 +379,12 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
             W[i] = __vimin3_u32(cd, cu, cl) & PRIO_CLEAR;
             wd = wl;
         }
-        if (eiq) row_m_update(W[m], j, m, n, P, best);
+        if (eiq && row_m_update(W[m], j, m, n, P, best) && P.exact_stop) {
+            exact_stop = true;
+            break;
+        }
     }
-    if (max_n == n) {
+    if (max_n == n && !exact_stop) {
         const int first_i = eir ? 0 : m;
         for (int i = m; i >= first_i; i--) last_col_update(W[i], i, n, P, best);
     }
@@ -433,7 +454,14 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
         }
     }
     if constexpr (HOMO == 2)
-        dp_homo<M, CSQ_HOMO_COLUMNS>(s, st.a, st.b, P, j0, r);
+    {
+        // measured (profiles/r01_homo_columns.md): four columns side by side win where the early stop ends most
+        // scans after ~20 columns (read start not free, NonInternalFront), two where every read walks all m + k columns
+        if (P.flags & 2)
+            dp_homo<M, 2>(s, st.a, st.b, P, j0, r);
+        else
+            dp_homo<M, CSQ_HOMO_COLUMNS>(s, st.a, st.b, P, j0, r);
+    }
     else if constexpr (M > 0)
         dp_exact<M, HOMO>(s, st.a, st.b, P, lut, j0, r);
     else

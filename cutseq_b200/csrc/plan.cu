@@ -472,6 +472,7 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
     MateProgram& mp = plan->prog[m];
     for (Segment& sg : mp.segs) {
         AlignParams ap = sg.ap;
+        ap.exact_stop = (plan->flags & CSQ_PLAN_NO_EXACT_STOP) ? 0 : 1;
         if (ap.homopolymer && !(plan->flags & CSQ_PLAN_HOMO_V1)) ap.homopolymer = 2;  // two DP columns side by side
         ap.md = mate_dev(s, m);
         ap.n = n;

@@ -229,7 +229,11 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
             const int w0 = max(min_n, jn - (m + 3 * k + 3));
             j0 = (uint32_t)w0;
             const int cols = max_n - w0;
-            bin = cols > 112 ? 0 : cols > 80 ? 1 : cols > 48 ? 2 : 3;  // longest first
+            // an error-free copy of the whole adapter (row-m cost 0 somewhere): Aligner.locate stops at that column
+            // ("exact match, stop early"), about m + 3k + 3 + 16 columns behind w0 - a list of its own, so that the
+            // warps of the exact pass that work on such reads leave together
+            const bool exact_copy = smin == 0 && P.exact_stop;
+            bin = exact_copy ? 3 : cols > 112 ? 0 : cols > 80 ? 1 : cols > 48 ? 2 : 4;  // longest first
         }
     }
     // nominal DP cells of the launch (GCUPS numerator) and warp-aggregated append of the survivors
