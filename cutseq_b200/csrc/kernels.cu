@@ -392,7 +392,7 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
 }
 
 // HOMO: 0 = any adapter, 1 = homopolymer adapter, one column at a time (CSQ_PLAN_HOMO_V1, A/B runs),
-// 2 = homopolymer adapter, CSQ_HOMO_COLUMNS columns side by side (dp_homo)
+// 2, 4 = homopolymer adapter, that many columns side by side (dp_homo)
 template <int M, int HOMO>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
@@ -453,15 +453,8 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
             atomicAdd(dst, (unsigned long long)mine);
         }
     }
-    if constexpr (HOMO == 2)
-    {
-        // measured (profiles/r01_homo_columns.md): four columns side by side win where the early stop ends most
-        // scans after ~20 columns (read start not free, NonInternalFront), two where every read walks all m + k columns
-        if (P.flags & 2)
-            dp_homo<M, 2>(s, st.a, st.b, P, j0, r);
-        else
-            dp_homo<M, CSQ_HOMO_COLUMNS>(s, st.a, st.b, P, j0, r);
-    }
+    if constexpr (HOMO >= 2)
+        dp_homo<M, HOMO>(s, st.a, st.b, P, j0, r);
     else if constexpr (M > 0)
         dp_exact<M, HOMO>(s, st.a, st.b, P, lut, j0, r);
     else
@@ -1087,7 +1080,13 @@ cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t 
     const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
     if constexpr (M == 100) {  // the poly-A / poly-T adapters of run.py:389-404
         if (p.homopolymer == 2) {
-            k_align<M, 2><<<grid, block, 0, stream>>>(p);
+            // measured (profiles/r01_homo_columns.md): four columns side by side win where the early stop ends most
+            // scans after ~20 columns (read start not free: NonInternalFront), two where every read walks all m + k
+            // columns; one kernel per variant (both bodies in one kernel cost 15 %)
+            if (p.flags & 2)
+                k_align<M, 2><<<grid, block, 0, stream>>>(p);
+            else
+                k_align<M, CSQ_HOMO_COLUMNS><<<grid, block, 0, stream>>>(p);
             return cudaGetLastError();
         }
         if (p.homopolymer) {

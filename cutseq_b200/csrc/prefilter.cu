@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
     const bool valid = idx < P.n;
     bool pass = false;
     unsigned int cells = 0;
+    int bin = 0;
     if (valid) {
         ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
         for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
@@ -291,8 +292,8 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
         const uint8_t* s = P.md.seq + P.md.seq_off[idx];
         const uint8_t* p = from_end ? (s + b - 1) : (s + a);
         const int step = from_end ? -1 : 1;
-        int e = 0;
-        for (int l = 1; l <= span; l++, p += step) {
+        int e = 0, l = 1;
+        for (; l <= span; l++, p += step) {
             e += ((uint32_t)(*p & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
             if (e > k) break;
             const int L = min(m, l + e);
@@ -300,6 +301,20 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
                 pass = true;
                 break;
             }
+        }
+        if (pass) {
+            // DP columns the exact pass will walk: all `span` of them when the read start is free, else up to the
+            // column with the (k + 1)-th foreign character (dp_homo's early stop) - survivors are listed by that
+            // number so that the threads of a k_align warp finish together
+            int cols = span;
+            if (!from_end) {
+                for (l++, p += step; l <= span; l++, p += step) {
+                    e += ((uint32_t)(*p & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
+                    if (e > k) break;
+                }
+                cols = min(l, span);
+            }
+            bin = cols > 80 ? 0 : cols > 48 ? 1 : cols > 32 ? 2 : 4;  // longest first (list 3 is not used here)
         }
         if (!pass && P.matches) {
             csq_match r;
@@ -310,7 +325,7 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
     for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
     const int lane = threadIdx.x & 31;
     if (lane == 0 && cells) atomicAdd(P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS), (unsigned long long)cells);
-    append_survivor(P, list, list_count, pass, idx, 0, 0xFFFFu, lane);
+    append_survivor(P, list, list_count, pass, idx, bin, 0xFFFFu, lane);
 }
 
 }  // namespace
