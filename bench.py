@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--file-pairs", type=int, default=2_000_000, help="pairs in the whole-file leg")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="stage", choices=["stage", "g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
-    ap.add_argument("--homo", default="two", choices=["two", "v1"], help="poly-A / poly-T exact DP: two columns side by side (default) or one (A/B runs)")
+    ap.add_argument("--homo", default="split", choices=["split", "one-lane", "v1"], help="poly-A / poly-T exact DP: column split over two lanes (default), whole column per thread with 2-4 columns side by side, or one column at a time (A/B runs)")
     ap.add_argument("--no-exact-stop", action="store_true", help="exact DP walks on after an error-free full match (CSQ_PLAN_NO_EXACT_STOP, A/B runs)")
     ap.add_argument("--parse", default="v1", choices=["onepass", "v1"], help="text-batch parse (A/B runs); v1 (four kernels) is the product default, onepass = single look-back kernel")
     ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
@@ -236,7 +236,7 @@ def main():
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
     plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0)
-                       | (A.PLAN_PARSE_ONEPASS if args.parse == "onepass" else 0) | (A.PLAN_HOMO_V1 if args.homo == "v1" else 0) | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
+                       | (A.PLAN_PARSE_ONEPASS if args.parse == "onepass" else 0) | {"split": 0, "one-lane": A.PLAN_HOMO_ONE_LANE, "v1": A.PLAN_HOMO_V1}[args.homo] | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.

@@ -48,6 +48,7 @@ PLAN_PARSE_ONEPASS = 128
 PLAN_EMIT_G16 = 256
 PLAN_HOMO_V1 = 512
 PLAN_NO_EXACT_STOP = 1024
+PLAN_HOMO_ONE_LANE = 2048
 
 
 class csq_op(C.Structure):

@@ -59,6 +59,7 @@ struct ParseParams {  // FASTQ text of one mate -> record index (parse.cu)
     uint32_t* nl_total;     // [1] line ends found
     uint32_t *seq_off, *qual_off, *seq_len, *name_off, *name_end;
     unsigned long long* perr;  // smallest (record << 3 | kind) of a malformed record, ~0 when clean
+    uint32_t* any_cr;          // [1] set by k_nl_count when the text holds a '\r' anywhere (CRLF files)
 };
 
 struct AlignParams {
@@ -96,6 +97,9 @@ struct FinishParams {
     int32_t mate;
     int32_t has_rename;  // 0: the header is written unchanged (after suffix stripping)
     unsigned long long* counters;
+    // text batches: the '@' / '+' line starts are checked here, where the header and the end of the bases are
+    // fetched anyway (k_records then needs no look at the text); same (record << 3 | kind) key as ParseParams.perr
+    unsigned long long* perr;
 };
 
 #define CSQ_PAIR_BLOCK 256  // pairs per CTA in the pair/emit kernels (scan granule)

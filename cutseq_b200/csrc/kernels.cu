@@ -494,6 +494,19 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishPa
         const uint8_t* nm = P.md.name + P.md.name_off[idx];
         int nl = (int)(P.md.name_end[idx] - P.md.name_off[idx]);
         const uint4 nm0 = fetch16(nm);
+        if (P.perr) {
+            // text batch: the header line must start with '@' (the byte in front of the name) and the line behind the
+            // bases with '+'; both bytes sit in sectors this thread fetches anyway.  Records at or behind an error
+            // that is already known are skipped (the host reports the smallest key).
+            const unsigned long long known = *reinterpret_cast<volatile unsigned long long*>(P.perr);
+            if ((known >> 3) > (unsigned long long)idx) {
+                const uint8_t* se = P.md.seq + P.md.seq_off[idx] + len0;  // the line end behind the bases
+                int bad = 0;
+                if (nm[-1] != '@') bad = 1;                                // PERR_AT
+                else if (se[se[0] == '\r' ? 2 : 1] != '+') bad = 2;        // PERR_PLUS
+                if (bad) atomicMin(P.perr, ((unsigned long long)idx << 3) | (unsigned long long)bad);
+            }
+        }
         if (P.has_qtrim) {
             // quality_trim_index (qualtrim.pyx): running sums from either end, stop at the first negative sum.
             // Nearly every read stops within a few bases: the 16 qualities at either end are fetched at once
@@ -1048,6 +1061,222 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
     if (__any_sync(0xffffffffu, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
 }
 
+// k_align_split<M, KC>: the homopolymer DP of dp_homo with every column split over TWO lanes - lane 2q holds rows
+// 0..M/2 of entry q, lane 2q+1 rows M/2..M (its row "0" is a copy of row M/2) - so that a thread keeps M/2 + 1 cells
+// instead of M + 1: half the registers (k_align<100> needs 228-231 and fits 8 warps per SM), twice the warps, half
+// the serial chain per thread.  The lower half runs ONE column group behind the upper half: what it needs from
+// above - row M/2 of the group's columns - arrives by one shuffle per column at the end of the upper half's turn;
+// both lanes take the same decisions (group sizes, early stop after k + 1 foreign characters) from the same
+// read characters, one iteration apart.  Row-m rule and exact stop live in the lower lane (it tells the upper
+// lane to halt); the last-column rule walks rows M..M/2+1 below, hands `best` up, and rows M/2..0 follow there.
+// Cells, order of the rules and results are those of dp_homo / dp_exact.
+template <int M, int KC>
+__global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ AlignParams P) {
+    static_assert(M % 2 == 0, "even adapter length");
+    constexpr int MH = M / 2;
+    constexpr int PER_CTA = 64;  // entries per CTA: two lanes each
+    const uint32_t FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31, h = threadIdx.x & 1;
+    uint32_t t = blockIdx.x * PER_CTA + (threadIdx.x >> 1), count = P.n;
+    size_t list_base = 0;
+    if (P.list) {
+        uint32_t cta = blockIdx.x;
+        int bin = 0;
+        for (; bin < CSQ_PF_BINS; bin++) {
+            count = P.list_count[bin];
+            const uint32_t ctas = (count + PER_CTA - 1) / PER_CTA;
+            if (cta < ctas) break;
+            cta -= ctas;
+        }
+        if (bin == CSQ_PF_BINS) return;  // whole CTA
+        t = cta * PER_CTA + (threadIdx.x >> 1);
+        list_base = (size_t)bin * P.n;
+    } else if (blockIdx.x * PER_CTA >= count) {
+        return;
+    }
+    const bool active = t < count;  // the same for both lanes of a pair; idle pairs still take part in the shuffles
+    uint32_t idx = 0;
+    int j0 = -1;
+    ReadState st = fresh_state(0);
+    if (active) {
+        idx = t;
+        if (P.list) {
+            idx = P.list[list_base + t];
+            const uint32_t w = reinterpret_cast<const uint16_t*>(P.list + (size_t)CSQ_PF_BINS * P.n)[list_base + t];
+            if (w != 0xFFFFu) j0 = (int)w;
+        }
+        st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
+        for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
+    }
+    const int a = st.a, b = st.b, n = b - a, k = P.k;
+    const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
+    int max_n = n, min_n = 0;
+    if (!siq) max_n = min(n, M + k);
+    if (!eiq) min_n = max(0, n - M - k);
+    if (j0 >= 0) min_n = max(min_n, j0);
+    if (active && h == 0 && P.count_cells) {
+        int cmax = n, cmin = 0;
+        if (!siq) cmax = min(n, M + k);
+        if (!eiq) cmin = max(0, n - M - k);
+        atomicAdd(P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS), (unsigned long long)(M * (cmax - cmin)));
+    }
+    const uint8_t* s = P.md.seq + (active ? P.md.seq_off[idx] : 0u);
+
+    uint32_t W[MH + 1];  // local row r = global row h * MH + r
+#pragma unroll
+    for (int r = 0; r <= MH; r++) {
+        int cost, origin;
+        init_cell(h * MH + r, min_n, sir, siq, cost, origin);
+        W[r] = pack_cell(cost, origin);
+    }
+    Best best = {M + n + 1, 0, 0, M, n};
+    const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
+    const int step = P.reversed ? -1 : 1;
+    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    const uint32_t letter = P.letter;
+    int foreign = 0;
+    bool cut_short = false, exact_halt = false;
+    int j = min_n + 1;
+    bool running = active;
+    uint32_t recv[KC];  // lower lane: row M/2 of the columns of its next group, as computed above
+#pragma unroll
+    for (int c = 0; c < KC; c++) recv[c] = 0;
+
+    for (int iter = 0; __any_sync(FULLM, running); iter++) {
+        uint32_t bnd[KC];  // local row MH of the columns of this turn's group
+#pragma unroll
+        for (int c = 0; c < KC; c++) bnd[c] = 0;
+        if (running && iter >= h) {
+            if (j > max_n) {
+                running = false;
+            } else {
+                bool block = j + KC - 1 <= max_n;
+                uint32_t d[KC];
+                int f = foreign;
+                if (block) {
+#pragma unroll
+                    for (int c = 0; c < KC; c++) {
+                        const bool eq = ((uint32_t)p[c * step] & 0xDFu) == letter;
+                        d[c] = eq ? D_MATCH : D_MIS;
+                        f += eq ? 0 : 1;
+                    }
+                    if (!siq && f > k) block = false;
+                }
+                if (block) {
+                    foreign = f;
+                    uint32_t p1[KC], p2[KC];
+                    uint32_t wd = W[0];
+#pragma unroll
+                    for (int c = 0; c < KC; c++) p1[c] = p2[c] = h ? recv[c] : W[0] + (uint32_t)(c + 1) * row0_delta;
+                    W[0] = p1[KC - 1];
+#pragma unroll
+                    for (int i = 1; i <= MH + KC - 1; i++) {
+#pragma unroll
+                        for (int c = KC - 1; c >= 0; c--) {
+                            const int row = i - c;
+                            if (row < 1 || row > MH) continue;
+                            uint32_t diag, left;
+                            if (c == 0) {
+                                left = W[row];
+                                diag = wd;
+                                wd = left;
+                            } else {
+                                left = p1[c - 1];
+                                diag = p2[c - 1];
+                            }
+                            const uint32_t cell = __vimin3_u32(diag + d[c], p1[c] + D_INS, left + D_DEL) & PRIO_CLEAR;
+                            p2[c] = p1[c];
+                            p1[c] = cell;
+                            if (c == KC - 1) W[row] = cell;
+                            if (row == MH) bnd[c] = cell;
+                        }
+                    }
+                    if (h && eiq) {
+                        bool stop = false;
+#pragma unroll
+                        for (int c = 0; c < KC; c++) stop |= row_m_update(bnd[c], j + c, M, n, P, best);
+                        if (stop && P.exact_stop) {
+                            cut_short = exact_halt = true;
+                            running = false;
+                        }
+                    }
+                    j += KC;
+                    p += KC * step;
+                } else {
+                    const bool eq = ((uint32_t)*p & 0xDFu) == letter;
+                    bool go = true;
+                    if (!siq) {
+                        foreign += eq ? 0 : 1;
+                        if (foreign > k) {
+                            cut_short = true;
+                            running = false;
+                            go = false;
+                        }
+                    }
+                    if (go) {
+                        const uint32_t d0 = eq ? D_MATCH : D_MIS;
+                        uint32_t wd = W[0];
+                        W[0] = h ? recv[0] : W[0] + row0_delta;
+#pragma unroll
+                        for (int r = 1; r <= MH; r++) {
+                            const uint32_t wl = W[r];
+                            W[r] = __vimin3_u32(wd + d0, W[r - 1] + D_INS, wl + D_DEL) & PRIO_CLEAR;
+                            wd = wl;
+                        }
+                        bnd[0] = W[MH];
+                        if (h && eiq && row_m_update(W[MH], j, M, n, P, best) && P.exact_stop) {
+                            cut_short = exact_halt = true;
+                            running = false;
+                        }
+                        j += 1;
+                        p += step;
+                    }
+                }
+            }
+        }
+        // hand row M/2 down, and the exact stop up
+#pragma unroll
+        for (int c = 0; c < KC; c++) recv[c] = __shfl_sync(FULLM, bnd[c], lane & ~1);
+        const bool halt = __shfl_sync(FULLM, (int)exact_halt, lane | 1) != 0;
+        if (h == 0 && halt) {
+            cut_short = true;
+            running = false;
+        }
+    }
+    // last column: rows M .. M/2 + 1 below, then `best` moves up and rows M/2 .. 0 follow
+    const bool last_col = max_n == n && !cut_short;
+    const int first_i = eir ? 0 : M;
+    if (h == 1 && last_col) {
+#pragma unroll
+        for (int r = MH; r >= 1; r--)
+            if (MH + r >= first_i) last_col_update(W[r], MH + r, n, P, best);
+    }
+    best.cost = __shfl_sync(FULLM, best.cost, lane | 1);
+    best.origin = __shfl_sync(FULLM, best.origin, lane | 1);
+    best.score = __shfl_sync(FULLM, best.score, lane | 1);
+    best.ref_stop = __shfl_sync(FULLM, best.ref_stop, lane | 1);
+    best.query_stop = __shfl_sync(FULLM, best.query_stop, lane | 1);
+    if (h == 0 && active) {
+        if (last_col) {
+#pragma unroll
+            for (int r = MH; r >= 0; r--)
+                if (r >= first_i) last_col_update(W[r], r, n, P, best);
+        }
+        csq_match r;
+        best_to_match(best, M, n, P.reversed != 0, r);
+        if (r.found) {
+            st.matched |= 0x80000000u | (P.adapter_bit >= 0 ? (1u << P.adapter_bit) : 0u);
+            if (P.trim_front)
+                st.a = (uint16_t)(st.a + r.query_stop);
+            else
+                st.b = (uint16_t)(st.a + r.query_start);
+            atomicAdd(P.counters + P.counter_index, 1ULL);
+        }
+        if (P.matches) P.matches[idx] = r;
+        store_state(P.md.state + idx, st);
+    }
+}
+
 // Integer-issue microbenchmark: 8 independent dependency chains per thread.
 // variant 0: IADD3 / LOP3 / VIMNMX only (ALU pipe); variant 1: the same mixed with IMAD (FMA pipe).
 template <int VARIANT>
@@ -1079,6 +1308,14 @@ template <int M>
 cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t stream) {
     const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
     if constexpr (M == 100) {  // the poly-A / poly-T adapters of run.py:389-404
+        if (p.homopolymer == 3) {  // every column over two lanes (k_align_split)
+            const dim3 grid2((n_items + 63) / 64 + (p.list ? CSQ_PF_BINS : 0));
+            if (p.flags & 2)
+                k_align_split<M, 2><<<grid2, block, 0, stream>>>(p);
+            else
+                k_align_split<M, CSQ_HOMO_COLUMNS><<<grid2, block, 0, stream>>>(p);
+            return cudaGetLastError();
+        }
         if (p.homopolymer == 2) {
             // measured (profiles/r01_homo_columns.md): four columns side by side win where the early stop ends most
             // scans after ~20 columns (read start not free: NonInternalFront), two where every read walks all m + k

@@ -39,19 +39,27 @@ __device__ __forceinline__ uint32_t nl_mask16(uint4 v) {
 // The text buffer is 16-byte aligned and zero padded, so whole chunks never leave the allocation and padding
 // never counts as a line end.
 __global__ void __launch_bounds__(TILE_THREADS) k_nl_count(const uint8_t* __restrict__ text, uint64_t bytes,
-                                                           uint16_t* __restrict__ masks, uint32_t* __restrict__ tile_cnt) {
+                                                           uint16_t* __restrict__ masks, uint32_t* __restrict__ tile_cnt,
+                                                           uint32_t* __restrict__ any_cr) {
     __shared__ uint32_t wsum[TILE_THREADS / 32];
     const uint64_t tile_off = (uint64_t)blockIdx.x * TILE_BYTES;
-    uint32_t c = 0;
+    uint32_t c = 0, cr = 0;
 #pragma unroll
     for (int i = 0; i < TILE_CHUNKS / TILE_THREADS; i++) {
         const uint32_t chunk = i * TILE_THREADS + threadIdx.x;
         const uint64_t off = tile_off + 16ull * chunk;
         uint32_t m = 0;
-        if (off < bytes) m = nl_mask16(*reinterpret_cast<const uint4*>(text + off));
+        if (off < bytes) {
+            const uint4 v = *reinterpret_cast<const uint4*>(text + off);
+            m = nl_mask16(v);
+            // is there a '\r' anywhere?  (x - 0x01..) & ~x has bit 7 of some byte set iff x has a zero byte
+            const uint32_t x0 = v.x ^ 0x0D0D0D0Du, x1 = v.y ^ 0x0D0D0D0Du, x2 = v.z ^ 0x0D0D0D0Du, x3 = v.w ^ 0x0D0D0D0Du;
+            cr |= ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
+        }
         masks[(size_t)blockIdx.x * TILE_CHUNKS + chunk] = (uint16_t)m;
         c += __popc(m);
     }
+    if (__any_sync(0xffffffffu, (cr & 0x80808080u) != 0) && (threadIdx.x & 31) == 0) atomicOr(any_cr, 1u);
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -166,32 +174,34 @@ __global__ void __launch_bounds__(256) k_records(const ParseParams P) {
         P.name_off[i] = P.name_end[i] = P.seq_off[i] = P.seq_len[i] = P.qual_off[i] = 0;
         return;
     }
+    // The record index comes from the line ends alone.  The text is only looked at for '\r' stripping, and only when
+    // k_nl_count saw a '\r' somewhere (CRLF files); the '@' and '+' line starts are checked by k_finish, which
+    // fetches the header and the end of the bases anyway (this kernel used to pull ~5 DRAM sectors per record, 93 %
+    // of the text, for six bytes).
     const uint4 e = reinterpret_cast<const uint4*>(P.nl)[i];  // the four line ends of record i
     uint32_t s0 = i ? P.nl[4u * i - 1] + 1u : 0u;
-    const uint8_t* __restrict__ t = P.text;
-    uint32_t e0 = e.x, e1 = e.y, e2 = e.z, e3 = e.w;
-    const uint32_t s1 = e.x + 1, s2 = e.y + 1, s3 = e.z + 1;
-    if (e0 > s0 && t[e0 - 1] == '\r') e0--;
-    if (e1 > s1 && t[e1 - 1] == '\r') e1--;
-    if (e2 > s2 && t[e2 - 1] == '\r') e2--;
-    if (e3 > s3 && t[e3 - 1] == '\r') e3--;
+    uint32_t e0 = e.x, e1 = e.y, e3 = e.w;
+    const uint32_t s1 = e.x + 1, s3 = e.z + 1;
+    if (P.any_cr[0]) {
+        const uint8_t* __restrict__ t = P.text;
+        if (e0 > s0 && t[e0 - 1] == '\r') e0--;
+        if (e1 > s1 && t[e1 - 1] == '\r') e1--;
+        if (e3 > s3 && t[e3 - 1] == '\r') e3--;
+    }
     const uint32_t slen = e1 - s1, qlen = e3 - s3;
     bool ok = true;
-    if (e0 == s0 || t[s0] != '@') {
-        report(P.perr, i, PERR_AT);
-        ok = false;
-    } else if (e2 == s2 || t[s2] != '+') {
-        report(P.perr, i, PERR_PLUS);
-        ok = false;
-    } else if (slen != qlen) {
-        report(P.perr, i, PERR_LEN);
-        ok = false;
-    } else if (slen > CSQ_MAX_READ_LEN) {
-        report(P.perr, i, PERR_LIMIT);
+    if (slen != qlen || slen > CSQ_MAX_READ_LEN) {
+        // rare: this record is reported from here, in the order dnaio would meet its problems (k_finish skips it)
+        const uint8_t* __restrict__ t = P.text;
+        const uint32_t s2 = e.y + 1;
+        uint32_t e2 = e.z;
+        if (e2 > s2 && t[e2 - 1] == '\r') e2--;
+        const int kind = (e0 == s0 || t[s0] != '@') ? PERR_AT : (e2 == s2 || t[s2] != '+') ? PERR_PLUS : slen != qlen ? PERR_LEN : PERR_LIMIT;
+        report(P.perr, i, kind);
         ok = false;
     }
     // a bad record becomes an empty one: the rest of the chain stays in bounds, the batch is rejected by the host
-    P.name_off[i] = ok ? s0 + 1 : s0;
+    P.name_off[i] = ok ? min(s0 + 1, e0) : s0;  // behind the '@' (k_finish checks that it is one)
     P.name_end[i] = ok ? e0 : s0;
     P.seq_off[i] = s1;
     P.seq_len[i] = ok ? slen : 0u;
@@ -376,7 +386,9 @@ cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* mas
     if (v1) {
         uint32_t* tile_cnt = (uint32_t*)tile_buf;
         if (tiles) {
-            k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, masks, tile_cnt);
+            cudaError_t e = cudaMemsetAsync(p.any_cr, 0, 4, stream);
+            if (e != cudaSuccess) return e;
+            k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, masks, tile_cnt, p.any_cr);
             k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_cnt, p.nl_total);
             k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(masks, tile_cnt, p.nl, 4u * p.n);
         } else {

@@ -83,7 +83,7 @@ struct Slot {
     cudaStream_t stream2 = nullptr;  // chain of mate 2
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // text batches (csq_submit_text): the FASTQ bytes as they came, and the record index k_records builds
-    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16 | tile ticket[2] (u32) at +32
+    DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16 | tile ticket[2] (u32) at +32 | any_cr[2] (u32) at +40
     uint64_t text_bytes[2] = {0, 0};
     uint64_t first_record = 0;
     bool text_mode = false;
@@ -464,6 +464,7 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
         pp.name_off = (uint32_t*)s.name_off[m].p;
         pp.name_end = (uint32_t*)s.name_end[m].p;
         pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
+        pp.any_cr = (uint32_t*)((uint8_t*)s.parse_misc.p + 40) + m;
         const bool v1 = !(plan->flags & CSQ_PLAN_PARSE_ONEPASS);
         CUDA_TRY(csq_launch_parse(pp, s.tiles[m].p, (uint16_t*)s.masks[m].p, (uint32_t*)((uint8_t*)s.parse_misc.p + 32) + m, v1, st));
         plan->launches += csq_parse_tiles(pp.bytes) ? (v1 ? 4 : 2) : 1;
@@ -473,7 +474,9 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
     for (Segment& sg : mp.segs) {
         AlignParams ap = sg.ap;
         ap.exact_stop = (plan->flags & CSQ_PLAN_NO_EXACT_STOP) ? 0 : 1;
-        if (ap.homopolymer && !(plan->flags & CSQ_PLAN_HOMO_V1)) ap.homopolymer = 2;  // two DP columns side by side
+        // homopolymer adapters: 1 = one column at a time, 2 = several columns side by side in one thread, 3 = every
+        // column over two lanes on top of that (default)
+        if (ap.homopolymer && !(plan->flags & CSQ_PLAN_HOMO_V1)) ap.homopolymer = (plan->flags & CSQ_PLAN_HOMO_ONE_LANE) ? 2 : 3;
         ap.md = mate_dev(s, m);
         ap.n = n;
         ap.list = nullptr;
@@ -503,6 +506,7 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
     fp.md = mate_dev(s, m);
     fp.n = n;
     fp.counters = plan->counters;
+    fp.perr = s.text_mode ? (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m : nullptr;
     CUDA_TRY(csq_launch_finish(fp, st));
     plan->launches += n ? 1 : 0;
     if (kt) kt->mark(m == 0 ? "k_finish.r1" : "k_finish.r2");

@@ -227,6 +227,7 @@ typedef struct csq_plan csq_plan;
 #define CSQ_PLAN_PARSE_ONEPASS 128u /* text batches: the one-pass look-back parse kernel instead of the default four-kernel
                                      form (A/B runs; measured slower: one latency chain per 16 KiB tile)             */
 #define CSQ_PLAN_NO_EXACT_STOP 1024u /* exact DP walks every column even after an error-free full match (results are the same; A/B) */
+#define CSQ_PLAN_HOMO_ONE_LANE 2048u /* homopolymer exact DP with a whole column per thread (k_align<100, 2|4>) instead of two lanes per column (A/B) */
 #define CSQ_PLAN_HOMO_V1 512u     /* homopolymer (poly-A / poly-T) exact DP one column at a time instead of two side by side (A/B) */
 #define CSQ_PLAN_EMIT_REC 8u      /* emit FASTQ text with the thread-per-pair 16-byte-chunk kernel instead of the
                                      default k_emit_stage (A/B runs)                                     */

@@ -54,7 +54,7 @@ def check_locate(op, reads):
     """Both execution modes: exact DP on every read, and bit-parallel prefilter + exact DP on the survivors."""
     batch, keep = oracle.make_batch(reads)
     wants = [oracle.adapter_match(op, s) for (_, s, _) in reads]
-    for flags in (A.PLAN_NO_PREFILTER, 0, A.PLAN_NO_EXACT_STOP) + ((A.PLAN_NO_PREFILTER | A.PLAN_HOMO_V1,) if len(set(op.adapter)) == 1 else ()):
+    for flags in (A.PLAN_NO_PREFILTER, 0, A.PLAN_NO_EXACT_STOP) + ((A.PLAN_NO_PREFILTER | A.PLAN_HOMO_V1, A.PLAN_NO_PREFILTER | A.PLAN_HOMO_ONE_LANE, A.PLAN_HOMO_ONE_LANE, A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER) if len(set(op.adapter)) == 1 else ()):
         got = native.locate_batch(op, batch.mate[0], len(reads), flags=flags)
         for i, (_, s, _) in enumerate(reads):
             g = got[i]
@@ -190,7 +190,7 @@ def compare_with_oracle(prog, mates, flags=0):
     return text
 
 
-@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8, A.PLAN_HOMO_V1 | A.PLAN_NO_PREFILTER, A.PLAN_NO_EXACT_STOP], ids=["prefilter", "exact_only", "emit_rec", "emit_g32", "emit_g16", "emit_g8", "homo_v1_exact_only", "no_exact_stop"])
+@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8, A.PLAN_HOMO_V1 | A.PLAN_NO_PREFILTER, A.PLAN_NO_EXACT_STOP, A.PLAN_HOMO_ONE_LANE, A.PLAN_HOMO_ONE_LANE | A.PLAN_NO_PREFILTER], ids=["prefilter", "exact_only", "emit_rec", "emit_g32", "emit_g16", "emit_g8", "homo_v1_exact_only", "no_exact_stop", "homo_one_lane", "homo_one_lane_exact_only"])
 @pytest.mark.parametrize("case", helpers.golden_cases(), ids=lambda c: c["case"])
 def test_golden_vectors(case, flags):
     prog = helpers.program_for(case["argv"], case["n_mates"])
@@ -280,7 +280,7 @@ def test_synthetic_configs_against_oracle():
         prog = helpers.program_for(argv, n_mates)
         batch = native.synth_batch(config, 30000, first_index=12345, buffer=3)
         want = oracle.run_batch(prog, batch, n_threads=8)
-        for flags in (0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8, A.PLAN_HOMO_V1, A.PLAN_NO_EXACT_STOP, A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER):
+        for flags in (0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8, A.PLAN_HOMO_V1, A.PLAN_NO_EXACT_STOP, A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER, A.PLAN_HOMO_ONE_LANE):
             with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES | flags) as plan:
                 text, records = plan.run_batch(batch)
                 stats = plan.stats()
