@@ -25,14 +25,45 @@ constexpr int TILE_THREADS = 256;
 constexpr int TILE_BYTES = 16384;               // 1024 chunks of 16 bytes; thread t owns the 64 bytes at 64 t
 constexpr int TILE_CHUNKS = TILE_BYTES / 16;
 
-// bit i set <=> byte i of the 16-byte chunk is '\n'
-__device__ __forceinline__ uint32_t nl_mask16(uint4 v) {
-    auto nib = [](uint32_t w) {
-        const uint32_t x = (__vcmpeq4(w, 0x0A0A0A0Au) >> 7) & 0x01010101u;  // bits 0, 8, 16, 24
-        return ((x * 0x00204081u) >> 21) & 0xFu;                             // gathered into bits 0..3
-    };
-    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+// Byte tests on 32-bit words, one LOP3 per step: the constants live in registers (handed in through an opaque asm
+// so that ptxas does not turn every step into two immediate-form instructions - the count kernel is ALU bound).
+struct ByteConsts {
+    uint32_t k7f, k80, k0a, k0d, k01;
+};
+__device__ __forceinline__ ByteConsts byte_consts() {
+    ByteConsts k;
+    asm volatile("mov.b32 %0, 0x7F7F7F7F;" : "=r"(k.k7f));
+    asm volatile("mov.b32 %0, 0x80808080;" : "=r"(k.k80));
+    asm volatile("mov.b32 %0, 0x0A0A0A0A;" : "=r"(k.k0a));
+    asm volatile("mov.b32 %0, 0x0D0D0D0D;" : "=r"(k.k0d));
+    asm volatile("mov.b32 %0, 0x01010101;" : "=r"(k.k01));
+    return k;
 }
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c, int lut) {
+    uint32_t d;
+    switch (lut) {  // the look-up table has to be an immediate
+        case 0x6A: asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); break;  // (a & b) ^ c
+        case 0x02: asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); break;  // ~(a | b) & c
+        default: asm("lop3.b32 %0, %1, %2, %3, 0xF2;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); break;    // a | (~b & c)
+    }
+    return d;
+}
+// bits 7, 15, 23, 31 of the result: byte of w equals the byte replicated in `kc` (which must be < 0x80).
+// x = (w & 0x7f..) ^ kc is zero in the low seven bits exactly there; + 0x7f.. then leaves bit 7 clear only for those,
+// bytes do not borrow from each other, and w's own bit 7 rules out 0x80 | c.
+__device__ __forceinline__ uint32_t eq_marks(uint32_t w, uint32_t kc, const ByteConsts& k) {
+    const uint32_t y = lop3(w, k.k7f, kc, 0x6A) + k.k7f;
+    return lop3(y, w, k.k80, 0x02);
+}
+// bit i set <=> byte i of the 16-byte chunk is '\n': the four marks of a word times 0x00204081 land in bits 28..31
+// (every partial product has its own bit position, nothing carries)
+__device__ __forceinline__ uint32_t nl_mask16(uint4 v, const ByteConsts& k) {
+    const uint32_t M = 0x00204081u;
+    const uint32_t n0 = (eq_marks(v.x, k.k0a, k) * M) >> 28, n1 = (eq_marks(v.y, k.k0a, k) * M) >> 24;
+    const uint32_t n2 = (eq_marks(v.z, k.k0a, k) * M) >> 20, n3 = (eq_marks(v.w, k.k0a, k) * M) >> 16;
+    return n0 | (n1 & 0xF0u) | (n2 & 0xF00u) | (n3 & 0xF000u);
+}
+__device__ __forceinline__ uint32_t nl_mask16(uint4 v) { return nl_mask16(v, byte_consts()); }
 
 // Pass 1: the text is read ONCE, fully coalesced (chunk c of the tile by thread c % 256); what survives is a
 // 16-bit line-end mask per chunk (1/8 of the text) and the number of line ends per tile.
@@ -44,6 +75,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_nl_count(const uint8_t* __rest
     __shared__ uint32_t wsum[TILE_THREADS / 32];
     const uint64_t tile_off = (uint64_t)blockIdx.x * TILE_BYTES;
     uint32_t c = 0, cr = 0;
+    const ByteConsts k = byte_consts();
 #pragma unroll
     for (int i = 0; i < TILE_CHUNKS / TILE_THREADS; i++) {
         const uint32_t chunk = i * TILE_THREADS + threadIdx.x;
@@ -51,10 +83,14 @@ __global__ void __launch_bounds__(TILE_THREADS) k_nl_count(const uint8_t* __rest
         uint32_t m = 0;
         if (off < bytes) {
             const uint4 v = *reinterpret_cast<const uint4*>(text + off);
-            m = nl_mask16(v);
-            // is there a '\r' anywhere?  (x - 0x01..) & ~x has bit 7 of some byte set iff x has a zero byte
-            const uint32_t x0 = v.x ^ 0x0D0D0D0Du, x1 = v.y ^ 0x0D0D0D0Du, x2 = v.z ^ 0x0D0D0D0Du, x3 = v.w ^ 0x0D0D0D0Du;
-            cr |= ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3);
+            m = nl_mask16(v, k);
+            // is there a '\r' anywhere?  x = w ^ "\r\r\r\r"; (x - 0x01..) & ~x has bit 7 of some byte set iff x has a
+            // zero byte (a borrow can only start at one), accumulated with cr | (~x & (x - 0x01..))
+            const uint32_t x0 = v.x ^ k.k0d, x1 = v.y ^ k.k0d, x2 = v.z ^ k.k0d, x3 = v.w ^ k.k0d;
+            cr = lop3(cr, x0, x0 - k.k01, 0xF2);
+            cr = lop3(cr, x1, x1 - k.k01, 0xF2);
+            cr = lop3(cr, x2, x2 - k.k01, 0xF2);
+            cr = lop3(cr, x3, x3 - k.k01, 0xF2);
         }
         masks[(size_t)blockIdx.x * TILE_CHUNKS + chunk] = (uint16_t)m;
         c += __popc(m);
