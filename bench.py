@@ -395,6 +395,22 @@ def main():
                    f"launches; peak = csq_int_peak measured live (ALU-only {alu_peak / 1e12:.2f}, ALU+FMA mix {mixed_peak / 1e12:.2f} "
                    "T lane-op/s). With the bit-parallel prefilter most nominal cells are never visited, so this can exceed 1.",
         }
+    # the same op by EXECUTED integer lane-ops: instructions per read of each kernel from the committed ncu capture of
+    # this workload (deterministic for the generator), times the reads of a launch, over the live CUDA-event time
+    roofline_dp_executed = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            ops_tab = json.load(f)["dp_lane_ops_per_read"]
+        if dom_dp and not args.no_prefilter:
+            kind = dom_dp["kernel"][dom_dp["kernel"].index("("):]
+            lane_ops = ops_tab["k_prefilter" + kind] + ops_tab["k_align" + kind]
+            achieved = lane_ops * P / (dom_dp["ms"] * 1e-3) / 1e9
+            roofline_dp_executed = {"bound": "int_issue", "kernel": dom_dp["kernel"], "achieved": achieved, "peak": peak / 1e9, "unit": "Gop/s",
+                                    "frac": achieved / (peak / 1e9), "traffic": None,
+                                    "how": "executed integer lane-ops per read (smsp__inst_executed x 32 of the committed ncu capture, "
+                                           + ops_tab["source"] + ") x reads per launch / CUDA-event duration of the op's launches; peak = csq_int_peak measured live"}
+    except Exception:
+        pass
     roofline_hbm = {"bound": "hbm", "kernel": {"stage": "k_emit_stage", "rec": "k_emit_rec"}.get(args.emit, "k_emit<%s>" % args.emit[1:]), "achieved": (emit_bytes / (emit_ms * 1e-3) / 1e9) if emit_ms else None,
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "traffic": None,
                     "how": "algorithmic bytes per launch (input records read once + FASTQ text written once) / CUDA-event duration"}
@@ -436,7 +452,7 @@ def main():
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
                    "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse, "homo_dp": args.homo, "exact_stop": not args.no_exact_stop, "numa_node": numa_node},
         "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
-        "roofline": roofline, "roofline_dp": roofline_dp, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
+        "roofline": roofline, "roofline_dp": roofline_dp, "roofline_dp_executed": roofline_dp_executed, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
         "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
         "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
     }
