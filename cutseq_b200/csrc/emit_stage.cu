@@ -20,6 +20,8 @@
 //             out at the same offset modulo 16 as its place in the output and leaves as ONE bulk copy per span
 //             (cp.async.bulk shared -> global); only the < 16 bytes at either end of a span go bytewise.  The
 //             drain is awaited (wait_group.read) just before the next pass writes into the image again.
+//   The passes of a warp are software-pipelined: pass i + 1 is sized and its loads are issued right after pass i has
+//   been reformatted, so they are in flight during the flush of pass i.
 //
 // Every source byte is read once and every output byte written once.  A pass that does not fit the staging
 // buffers is halved; a pair that does not fit alone (reads near the length limit with very long headers) takes
@@ -124,7 +126,7 @@ __device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, ui
         n -= 4;
     }
     const uint32_t nd = n >> 3;
-#pragma unroll 2
+#pragma unroll 4
     for (uint32_t i = 0; i < nd; i++) {
         const uint32_t w1 = lds32(sm, sa + 4), w2 = lds32(sm, sa + 8);
         *reinterpret_cast<uint2*>(sm + d) = make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
@@ -265,14 +267,28 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
     uint32_t bar_phase = 0;
     bool draining = false;  // a bulk store of this warp may still be reading the output image
 
-    for (int p0 = 0; p0 < n_warp;) {
+    // One pass = up to `ppass` pairs starting at pair p0 of the warp.  Everything a lane has to know about it:
+    struct Pass {
+        StageRec R;            // my record
+        int dest;              // its destination
+        int g;                 // pairs in the pass; 0: none (the pair at p0 does not fit the staging buffers)
+        bool valid;            // this lane has a record
+        bool loads;            // bulk loads were issued (and have to be awaited)
+        uint32_t sdelta[3];    // staged address of pool offset x of my mate: ES_SRC0 + sdelta[pool] + x
+        uint32_t ddelta;       // staged address of my record: ES_DST0 + ddelta + R.off
+    };
+
+    // Sizes the pass at p0 (halving it until it fits) and, if it fits, issues one bulk load per source span.
+    // The source buffer must be free: the previous pass has been reformatted.
+    auto prepare = [&](int p0, Pass& ps) {
         const int src_lane = (p0 + my_pp) & 31;
         const StageRec r0 = shfl_rec(rec[0], src_lane), r1 = shfl_rec(rec[1], src_lane);
-        const StageRec R = my_mt ? r1 : r0;
-        const int my_dest = __shfl_sync(FULL, dest, src_lane);
-        const uint32_t a = R.ab & 0xFFFFu, b = R.ab >> 16, seq_len = b - a;
-        const uint32_t id_len = R.idl & 0xFFFFu, umi_len = R.idl >> 16;
-        const uint32_t la = R.lab & 0xFFFFu, lab = la + (R.lab >> 16);
+        ps.R = my_mt ? r1 : r0;
+        const StageRec& R = ps.R;
+        ps.dest = __shfl_sync(FULL, dest, src_lane);
+        const uint32_t a = R.ab & 0xFFFFu, b = R.ab >> 16;
+        const uint32_t id_len = R.idl & 0xFFFFu;
+        const uint32_t la = R.lab & 0xFFFFu, lb = R.lab >> 16;
         // source pieces of this record in pool coordinates: name [nm, nm + id_len), bases [sq + a, sq + b),
         // qualities [ql + a, ql + b); empty pieces take no part in the spans
         uint32_t plo[3], phi[3];
@@ -283,7 +299,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
         plo[2] = R.ql + a;
         phi[2] = R.ql + b;
         // the UMI parts are staged with the bases of the mate whose read they were cut from
-        const uint32_t lb = lab - la;
         if (la && (!PAIRED || my_mt == 0)) {
             plo[1] = min(plo[1], R.pa);
             phi[1] = max(phi[1], R.pa + la);
@@ -303,14 +318,12 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             plo[0] = lo;
             phi[0] = hi;
         }
-
         int g = min(ppass, n_warp - p0);
-        bool valid = false;
-        uint32_t sdelta[3] = {0, 0, 0};   // staged address of pool offset x of my mate: ES_SRC0 + sdelta[pool] + x
-        uint32_t ddelta = 0;              // staged address of my record: ES_DST0 + ddelta + R.off
-        uint32_t sp_lo16[2][3], sp_n16[2][3], sp_base[2][3];  // source spans of the pass: pool offset, 16-byte chunks, staged offset
+        uint32_t sp_lo16[2][3], sp_n16[2][3], sp_base[2][3];  // source spans: pool offset, 16-byte chunks, staged offset
+        ps.sdelta[0] = ps.sdelta[1] = ps.sdelta[2] = 0;
+        ps.ddelta = 0;
         for (;;) {
-            valid = my_pp < g;
+            ps.valid = my_pp < g;
             uint32_t cursor = 0;
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                     sp_n16[mt][k] = 0;
                     sp_lo16[mt][k] = sp_base[mt][k] = 0;
                     if (mt < n_mates && k < n_pools) {
-                        const bool part = valid && role == 0 && my_mt == mt && phi[k] > plo[k];
+                        const bool part = ps.valid && role == 0 && my_mt == mt && phi[k] > plo[k];
                         const uint32_t lo = __reduce_min_sync(FULL, part ? plo[k] : 0xFFFFFFFFu);
                         const uint32_t hi = __reduce_max_sync(FULL, part ? phi[k] : 0u);
                         if (hi > lo) {
@@ -328,7 +341,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                             sp_lo16[mt][k] = lo16;
                             sp_n16[mt][k] = n16;
                             sp_base[mt][k] = cursor;
-                            if (my_mt == mt) sdelta[k] = cursor - lo16;
+                            if (my_mt == mt) ps.sdelta[k] = cursor - lo16;
                             cursor += n16 << 4;
                         }
                     }
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             for (int d = 0; d < CSQ_N_DEST; d++)
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++) {
-                    const bool part = valid && role == 0 && my_mt == mt && my_dest == d;
+                    const bool part = ps.valid && role == 0 && my_mt == mt && ps.dest == d;
                     const uint32_t mask = __ballot_sync(FULL, part);
                     if (mask) {
                         const uint32_t goff = __shfl_sync(FULL, R.off, __ffs((int)mask) - 1);
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                         const uint32_t mis = (uint32_t)(uintptr_t)(gbase[d][mt] + goff) & 15u;
                         const uint32_t dstart = ((dcursor + 15u) & ~15u) + mis;
                         dcursor = dstart + bytes;
-                        if (my_mt == mt && my_dest == d) ddelta = dstart - goff;
+                        if (my_mt == mt && ps.dest == d) ps.ddelta = dstart - goff;
                     }
                 }
             if (cursor <= ES_SRC_CAP && dcursor <= ES_DST_CAP) break;
@@ -357,58 +370,16 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             }
             g >>= 1;
         }
-
-        if (g == 0) {
-            // ---- the pair at p0 does not fit the staging buffers: bytewise, straight from and to global memory ----
-            const int sl = p0 & 31;
-            const int fd = __shfl_sync(FULL, dest, sl);
-            const uint8_t* idp[2] = {nullptr, nullptr};
-            uint32_t idn[2] = {0, 0};
+        ps.g = g;
+        ps.loads = false;
+        if (g == 0) return;
+        uint32_t total = 0;
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-                if (mt >= n_mates) continue;
-                const StageRec F = shfl_rec(rec[mt], sl);
-                const MateDev& md = P.md[mt];
-                const uint32_t fa = F.ab & 0xFFFFu, fb = F.ab >> 16, fl = fb - fa, fid = F.idl & 0xFFFFu, fumi = F.idl >> 16;
-                const uint32_t fla = F.lab & 0xFFFFu;
-                const uint8_t* nm = md.name + F.nm;
-                const uint8_t* sq = md.seq + F.sq + fa;
-                const uint8_t* ql = md.qual + F.ql + fa;
-                const uint8_t* pa = (poolA ? poolA : md.seq) + F.pa;
-                const uint8_t* pb = (poolB ? poolB : md.seq) + F.pb;
-                uint8_t* out = (fd == 0 ? gbase[0][mt] : fd == 1 ? gbase[1][mt] : gbase[2][mt]) + F.off;
-                const uint32_t e_name = 1u + fid, e_umi = e_name + fumi, e_seq = e_umi + 1u + fl, e_qual = e_seq + 3u + fl;
-                for (uint32_t p = lane; p < F.len; p += 32) {
-                    uint8_t c;
-                    if (p < e_name) c = p == 0 ? (uint8_t)'@' : nm[p - 1];
-                    else if (p < e_umi) {
-                        const uint32_t x = p - e_name;
-                        c = x == 0 ? (uint8_t)'_' : (x - 1 < fla ? pa[x - 1] : pb[x - 1 - fla]);
-                    } else if (p == e_umi) c = '\n';
-                    else if (p < e_seq) c = sq[p - e_umi - 1];
-                    else if (p < e_seq + 3) c = (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
-                    else if (p < e_qual) c = ql[p - e_seq - 3];
-                    else c = '\n';
-                    out[p] = c;
-                }
-                idp[mt] = nm;
-                idn[mt] = fid;
-            }
-            if (P.check_ids) {
-                id_mismatch |= idn[0] != idn[1];
-                for (uint32_t x = lane; x < min(idn[0], idn[1]); x += 32) id_mismatch |= idp[0][x] != idp[1][x];
-            }
-            p0 += 1;
-            continue;
-        }
-
-        // ---- load: one bulk copy per source span ----
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) total += sp_n16[mt][k] << 4;
+        ps.loads = total != 0;
         if (lane == 0) {
-            uint32_t total = 0;
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) total += sp_n16[mt][k] << 4;
             if (total) mbar_expect_tx(bar, total);
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
@@ -420,8 +391,79 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                     bulk_load(sm_u32 + ES_SRC0 + sp_base[mt][k], pool + sp_lo16[mt][k], sp_n16[mt][k] << 4, bar);
                 }
         }
-        const uint32_t d0 = ES_DST0 + ddelta + R.off;  // my record in the output image
-        const uint32_t sd_name = sdelta[0], sd_seq = one_pool ? sdelta[0] : sdelta[1], sd_qual = one_pool ? sdelta[0] : sdelta[2];
+    };
+
+    // The pair at p0 does not fit the staging buffers: bytewise, straight from and to global memory.
+    auto bytewise = [&](int p0) {
+        const int sl = p0 & 31;
+        const int fd = __shfl_sync(FULL, dest, sl);
+        const uint8_t* idp[2] = {nullptr, nullptr};
+        uint32_t idn[2] = {0, 0};
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            if (mt >= n_mates) continue;
+            const StageRec F = shfl_rec(rec[mt], sl);
+            const MateDev& md = P.md[mt];
+            const uint32_t fa = F.ab & 0xFFFFu, fb = F.ab >> 16, fl = fb - fa, fid = F.idl & 0xFFFFu, fumi = F.idl >> 16;
+            const uint32_t fla = F.lab & 0xFFFFu;
+            const uint8_t* nm = md.name + F.nm;
+            const uint8_t* sq = md.seq + F.sq + fa;
+            const uint8_t* ql = md.qual + F.ql + fa;
+            const uint8_t* pa = (poolA ? poolA : md.seq) + F.pa;
+            const uint8_t* pb = (poolB ? poolB : md.seq) + F.pb;
+            uint8_t* out = (fd == 0 ? gbase[0][mt] : fd == 1 ? gbase[1][mt] : gbase[2][mt]) + F.off;
+            const uint32_t e_name = 1u + fid, e_umi = e_name + fumi, e_seq = e_umi + 1u + fl, e_qual = e_seq + 3u + fl;
+            for (uint32_t p = lane; p < F.len; p += 32) {
+                uint8_t c;
+                if (p < e_name) c = p == 0 ? (uint8_t)'@' : nm[p - 1];
+                else if (p < e_umi) {
+                    const uint32_t x = p - e_name;
+                    c = x == 0 ? (uint8_t)'_' : (x - 1 < fla ? pa[x - 1] : pb[x - 1 - fla]);
+                } else if (p == e_umi) c = '\n';
+                else if (p < e_seq) c = sq[p - e_umi - 1];
+                else if (p < e_seq + 3) c = (p - e_seq == 1) ? (uint8_t)'+' : (uint8_t)'\n';
+                else if (p < e_qual) c = ql[p - e_seq - 3];
+                else c = '\n';
+                out[p] = c;
+            }
+            idp[mt] = nm;
+            idn[mt] = fid;
+        }
+        if (P.check_ids) {
+            id_mismatch |= idn[0] != idn[1];
+            for (uint32_t x = lane; x < min(idn[0], idn[1]); x += 32) id_mismatch |= idp[0][x] != idp[1][x];
+        }
+    };
+
+    // the next pass that goes through the staging buffers, starting at pair `next_p0` (pairs that do not fit are
+    // written bytewise on the way); ps.g == 0: the warp is done
+    int next_p0 = 0;
+    auto advance = [&](Pass& ps) {
+        ps.g = 0;
+        while (next_p0 < n_warp) {
+            prepare(next_p0, ps);
+            if (ps.g) {
+                next_p0 += ps.g;
+                return;
+            }
+            bytewise(next_p0);
+            next_p0 += 1;
+        }
+    };
+
+    // Software pipeline: the loads of pass i + 1 are issued as soon as pass i has been reformatted (the source buffer
+    // is free then) and are in flight during the flush of pass i and the bookkeeping of pass i + 1.
+    Pass cur;
+    advance(cur);
+    while (cur.g) {
+        const StageRec R = cur.R;
+        const bool valid = cur.valid;
+        const int my_dest = cur.dest;
+        const uint32_t a = R.ab & 0xFFFFu, b = R.ab >> 16, seq_len = b - a;
+        const uint32_t id_len = R.idl & 0xFFFFu, umi_len = R.idl >> 16;
+        const uint32_t la = R.lab & 0xFFFFu, lb = R.lab >> 16;
+        const uint32_t d0 = ES_DST0 + cur.ddelta + R.off;  // my record in the output image
+        const uint32_t sd_name = cur.sdelta[0], sd_seq = one_pool ? cur.sdelta[0] : cur.sdelta[1], sd_qual = one_pool ? cur.sdelta[0] : cur.sdelta[2];
         // staged bases of the mates the UMI parts come from (paired: lanes 4 pp .. 4 pp + 3 hold one pair)
         const uint32_t sd_a = PAIRED ? __shfl_sync(FULL, sd_seq, lane & ~3) : sd_seq;
         const uint32_t sd_b = PAIRED ? __shfl_sync(FULL, sd_seq, (lane & ~3) | 2) : sd_seq;
@@ -429,7 +471,7 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             if (lane == 0) bulk_wait_read();
             draining = false;
         }
-        if (__shfl_sync(FULL, sp_n16[0][0] | sp_n16[0][1] | sp_n16[0][2] | sp_n16[1][0] | sp_n16[1][1] | sp_n16[1][2], 0)) {
+        if (cur.loads) {
             mbar_wait(bar, bar_phase);
             bar_phase ^= 1u;
         }
@@ -462,11 +504,14 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
             const uint32_t o_id = __shfl_sync(FULL, s_id, (lane - 2) & 31), o_len = __shfl_sync(FULL, id_len, (lane - 2) & 31);
             if (valid && role == 0 && my_mt == 1) id_mismatch |= o_len != id_len || differ_s(sm, s_id, o_id, id_len);
         }
+        fence_async_smem();  // the image was written through the generic proxy, the bulk copies read it through the async proxy
         __syncwarp();
 
-        // ---- flush: every (destination, mate) span of the pass leaves as one bulk copy ----
-        fence_async_smem();  // the image was written through the generic proxy, the bulk copy reads it through the async proxy
-        __syncwarp();
+        // ---- the next pass: sized now, its loads fly during the flush below ----
+        const uint32_t f_off = R.off, f_len = R.len;
+        advance(cur);
+
+        // ---- flush: every (destination, mate) span of the finished pass leaves as one bulk copy ----
         {
             uint32_t dcursor = 0;
 #pragma unroll
@@ -476,8 +521,8 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                     const bool part = valid && role == 0 && my_mt == mt && my_dest == d;
                     const uint32_t mask = __ballot_sync(FULL, part);
                     if (mask) {
-                        const uint32_t goff = __shfl_sync(FULL, R.off, __ffs((int)mask) - 1);
-                        const uint32_t bytes = __reduce_add_sync(FULL, part ? R.len : 0u);
+                        const uint32_t goff = __shfl_sync(FULL, f_off, __ffs((int)mask) - 1);
+                        const uint32_t bytes = __reduce_add_sync(FULL, part ? f_len : 0u);
                         uint8_t* __restrict__ gp = gbase[d][mt] + goff;
                         const uint32_t mis = (uint32_t)(uintptr_t)gp & 15u;
                         const uint32_t dstart = ((dcursor + 15u) & ~15u) + mis;
@@ -495,7 +540,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
         if (lane == 0) bulk_commit();
         draining = true;
         __syncwarp();
-        p0 += g;
     }
     if (draining && lane == 0) bulk_wait_read();  // shared memory must outlive the reads of the last bulk stores
     if (__any_sync(FULL, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
