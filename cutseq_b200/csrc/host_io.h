@@ -117,8 +117,15 @@ struct MateTextReader {  // cuts the byte stream of one mate into batches of who
     bool eof = false;
     uint64_t records_done = 0;
     size_t hint_bytes = 0;       // size of the previous batch: the next buffer is reserved in one go
+    // plain regular files: several threads pread() disjoint pieces of the next batch straight into the pinned buffer
+    // and count their line ends (the page-cache copy of one thread, ~1.5 GB/s in a VM, is what bounded whole-file runs)
+    bool plain_file = false;
+    uint64_t file_off = 0, file_size = 0;
+    int read_threads = 1;
     int open(const char* path);
     int next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads);
+    int next_plain(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads);
+    int finish_at_eof(PinnedBuf& buf, size_t pos, uint64_t lines, uint64_t* bytes, uint32_t* n_reads);
 };
 
 int parse_records(const uint8_t* text, size_t n_bytes, bool at_eof, uint32_t max_reads, MateSoA& out, size_t* consumed,

@@ -212,11 +212,145 @@ int MateTextReader::open(const char* path) {
     carry_pos = 0;
     eof = false;
     records_done = 0;
-    return src.open(path);
+    plain_file = false;
+    file_off = file_size = 0;
+    const int rc = src.open(path);
+    if (rc) return rc;
+    struct stat sb;
+    if (!src.gz && fstat(src.fd, &sb) == 0 && S_ISREG(sb.st_mode)) {
+        plain_file = true;
+        file_size = (uint64_t)sb.st_size;
+        const char* env = getenv("CSQ_READ_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        read_threads = env ? atoi(env) : (int)(hw / 3);  // two mates read side by side; a third of the cores each, at most 8
+        if (!env && read_threads > 8) read_threads = 8;
+        if (read_threads < 1) read_threads = 1;
+        if (read_threads > 16) read_threads = 16;
+    }
+    return 0;
+}
+
+// End of the input: a missing final line end is accepted, and so are blank lines behind the last record (dnaio).
+int MateTextReader::finish_at_eof(PinnedBuf& buf, size_t pos, uint64_t lines, uint64_t* bytes, uint32_t* n_reads) {
+    if (pos && buf.p[pos - 1] != '\n') {
+        if (!buf.reserve(pos + 64, pos)) return io_fail(CSQ_ERR_NOMEM, "out of host memory");
+        buf.p[pos++] = '\n';
+        lines++;
+    }
+    while (lines % 4 != 0 && pos >= 2) {
+        size_t q = pos - 1;  // buf[q] == '\n'
+        if (q >= 1 && buf.p[q - 1] == '\r') q--;
+        if (q >= 1 && buf.p[q - 1] == '\n') {  // the last line is blank: drop it
+            pos = q;
+            lines--;
+        } else {
+            break;
+        }
+    }
+    if (lines == 1 && pos <= 2) {  // a file of just "\n"
+        pos = 0;
+        lines = 0;
+    }
+    if (lines % 4 != 0)
+        return io_fail(CSQ_ERR_FORMAT, "%s: FASTQ file ended prematurely (line %llu)", src.name.c_str(),
+                       (unsigned long long)(4 * records_done + lines + 1));
+    *bytes = pos;
+    *n_reads = (uint32_t)(lines / 4);
+    records_done += lines / 4;
+    return 0;
+}
+
+// Plain regular file: the next batch is [file_off, file_off + cut).  Its size is known to within a few per cent
+// from the previous batch, so `read_threads` threads pread() disjoint pieces of that range at once and count
+// their line ends; nothing is carried over between batches (what lies behind the cut is read again next time,
+// from the page cache).
+int MateTextReader::next_plain(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads) {
+    const uint64_t target = 4ull * max_reads;
+    *bytes = 0;
+    *n_reads = 0;
+    if (file_off >= file_size) {
+        eof = true;
+        return 0;
+    }
+    size_t pos = 0;        // bytes of the file, from file_off on, that are in buf
+    uint64_t lines = 0;    // line ends among them
+    size_t want = hint_bytes ? hint_bytes + hint_bytes / 32 + (64u << 10) : (size_t)max_reads * 384 + (64u << 10);
+    struct Piece {
+        size_t begin, len;
+        uint64_t lines;
+        long got;
+        int err;
+    };
+    std::vector<Piece> pieces;  // of the most recent round, in file order
+    for (;;) {
+        const uint64_t left = file_size - (file_off + pos);
+        size_t round = want > pos ? want - pos : (size_t)0;
+        if (round > left) round = (size_t)left;
+        if (round == 0) break;  // the whole rest of the file is here
+        if (!buf.reserve(pos + round + 64, pos)) return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
+        int nt = read_threads;
+        if ((size_t)nt > round / (1u << 20) + 1) nt = (int)(round / (1u << 20) + 1);  // at least 1 MiB per thread
+        pieces.assign((size_t)nt, Piece{0, 0, 0, 0, 0});
+        const size_t per = (round + (size_t)nt - 1) / (size_t)nt;
+        for (int t = 0; t < nt; t++) {
+            pieces[(size_t)t].begin = pos + (size_t)t * per;
+            const size_t end = pos + ((size_t)(t + 1) * per < round ? (size_t)(t + 1) * per : round);
+            pieces[(size_t)t].len = end > pieces[(size_t)t].begin ? end - pieces[(size_t)t].begin : 0;
+        }
+        auto work = [&](int t) {
+            Piece& pc = pieces[(size_t)t];
+            size_t done = 0;
+            while (done < pc.len) {
+                const ssize_t got = pread(src.fd, buf.p + pc.begin + done, pc.len - done, (off_t)(file_off + pc.begin + done));
+                if (got < 0) {
+                    if (errno == EINTR) continue;
+                    pc.err = errno;
+                    break;
+                }
+                if (got == 0) break;  // the file shrank under us
+                done += (size_t)got;
+            }
+            pc.got = (long)done;
+            pc.lines = count_newlines(buf.p + pc.begin, done);
+        };
+        std::vector<std::thread> helpers;
+        for (int t = 1; t < nt; t++) helpers.emplace_back(work, t);
+        work(0);
+        for (auto& th : helpers) th.join();
+        bool short_read = false;
+        for (int t = 0; t < nt; t++) {
+            const Piece& pc = pieces[(size_t)t];
+            if (pc.err) return io_fail(CSQ_ERR_IO, "read error in %s: %s", src.name.c_str(), strerror(pc.err));
+            if ((size_t)pc.got != pc.len) short_read = true;
+        }
+        if (short_read) return io_fail(CSQ_ERR_IO, "%s: file changed while it was read", src.name.c_str());
+        // is the last line end of the batch inside this round?
+        for (int t = 0; t < nt; t++) {
+            const Piece& pc = pieces[(size_t)t];
+            if (lines + pc.lines >= target) {
+                const uint64_t rel = after_kth_newline(buf.p + pc.begin, pc.len, target - lines);
+                const size_t cut = pc.begin + (size_t)rel;
+                file_off += cut;
+                hint_bytes = cut;
+                *bytes = cut;
+                *n_reads = max_reads;
+                records_done += max_reads;
+                return 0;
+            }
+            lines += pc.lines;
+        }
+        pos += round;
+        want = pos + pos / 8 + (256u << 10);  // not enough line ends yet: longer records than the previous batch had
+    }
+    // the rest of the file holds fewer than max_reads records
+    eof = true;
+    file_off = file_size;
+    return finish_at_eof(buf, pos, lines, bytes, n_reads);
 }
 
 // The next max_reads records (fewer at the end of the input) as raw text into buf.
 int MateTextReader::next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads) {
+    if (plain_file) return next_plain(max_reads, buf, bytes, n_reads);
     const uint64_t target = 4ull * max_reads;
     size_t piece = (size_t)max_reads * 512;
     piece = piece < (64u << 10) ? (64u << 10) : piece > (4u << 20) ? (4u << 20) : piece;
@@ -276,33 +410,7 @@ int MateTextReader::next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, ui
         records_done += max_reads;
         return 0;
     }
-    // end of the input: a missing final line end is accepted, and so are blank lines behind the last record (dnaio)
-    if (pos && buf.p[pos - 1] != '\n') {
-        if (!buf.reserve(pos + 64, pos)) return io_fail(CSQ_ERR_NOMEM, "out of host memory");
-        buf.p[pos++] = '\n';
-        lines++;
-    }
-    while (lines % 4 != 0 && pos >= 2) {
-        size_t q = pos - 1;  // buf[q] == '\n'
-        if (q >= 1 && buf.p[q - 1] == '\r') q--;
-        if (q >= 1 && buf.p[q - 1] == '\n') {  // the last line is blank: drop it
-            pos = q;
-            lines--;
-        } else {
-            break;
-        }
-    }
-    if (lines == 1 && pos <= 2) {  // a file of just "\n"
-        pos = 0;
-        lines = 0;
-    }
-    if (lines % 4 != 0)
-        return io_fail(CSQ_ERR_FORMAT, "%s: FASTQ file ended prematurely (line %llu)", src.name.c_str(),
-                       (unsigned long long)(4 * records_done + lines + 1));
-    *bytes = pos;
-    *n_reads = (uint32_t)(lines / 4);
-    records_done += lines / 4;
-    return 0;
+    return finish_at_eof(buf, pos, lines, bytes, n_reads);
 }
 
 }  // namespace csqio

@@ -235,6 +235,28 @@ def test_text_reader_cuts_whole_records(tmp_path, gz, tail):
         assert got1 == "".join(recs1).encode() and got2 == "".join(recs2).encode()
 
 
+@pytest.mark.parametrize("threads", ["1", "4", "7"])
+def test_text_reader_parallel_pread_of_plain_files(tmp_path, monkeypatch, threads):
+    """Plain regular files: several threads pread() pieces of a batch; batches of very different sizes in one file
+    (the size estimate comes from the previous batch), a last batch that ends at the end of the file."""
+    monkeypatch.setenv("CSQ_READ_THREADS", threads)
+    recs = _records(30000, read_len=20, seed=3) + _records(30000, read_len=300, seed=4) + _records(5000, read_len=5, seed=6)
+    text = "".join(recs).encode()
+    assert len(text) > 10 << 20
+    (tmp_path / "big.fq").write_bytes(text[:-1])  # no final line end
+    for batch in (4096, 20000, 70000):
+        got, total = [], 0
+        with native.TextReader(str(tmp_path / "big.fq")) as r:
+            while True:
+                n, texts, first_record = r.next(batch)
+                if n == 0:
+                    break
+                assert first_record == total and n <= batch and texts[0].count(b"\n") == 4 * n
+                got.append(texts[0])
+                total += n
+        assert total == len(recs) and b"".join(got) == text
+
+
 def test_text_reader_errors(tmp_path):
     (tmp_path / "short.fq").write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nAC\n")
     with native.TextReader(str(tmp_path / "short.fq")) as r:
