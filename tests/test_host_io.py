@@ -168,6 +168,21 @@ def test_no_gpu_means_loud_failure():
     assert e.value.code == A.ERR_NO_DEVICE
 
 
+def test_host_placement_calls_are_safe_without_a_gpu():
+    """csq_bind_host_to_device needs the device's PCI address: without a device it reports that and changes nothing;
+    csq_unbind_host is always callable."""
+    import os
+
+    before = os.sched_getaffinity(0)
+    if native.device_count() == 0:
+        with pytest.raises(native.NativeError):
+            native.bind_host_to_device(0)
+    else:
+        assert native.bind_host_to_device(0) >= -1
+    native.unbind_host()
+    assert os.sched_getaffinity(0) == before
+
+
 # ---- text batches: the reader only cuts the byte stream at record boundaries (text_reader.cpp) ----
 def _records(n, read_len=30, crlf=False, seed=5):
     rng = random.Random(seed)
