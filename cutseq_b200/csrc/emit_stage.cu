@@ -105,7 +105,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // n bytes from shared offset s to shared offset d, any alignment on both sides.  Looks at most 7 bytes beyond s + n.
-__device__ __forceinline__ void copy_small(uint8_t* sm, uint32_t s, uint32_t d, uint32_t n) {
+__device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, uint32_t n) {
     if (n == 0) return;
     const uint32_t h = min((4u - (d & 3u)) & 3u, n);  // bytes in front of the first whole output word
     if (h > 0) sm[d] = sm[s];
@@ -150,50 +150,9 @@ __device__ __forceinline__ void copy_small(uint8_t* sm, uint32_t s, uint32_t d, 
     }
 }
 
-// 16 output bytes per step for the long pieces (bases, qualities): the output is 16-byte aligned, the source is
-// read as aligned 16-byte lines (one LDS.128 per step, the previous line supplies the low words) and realigned by
-// a word rotation that is fixed for the whole piece (R = word of the line the piece starts in: four loop
-// variants) plus a funnel shift by the byte offset: 1 LDS.128 + 4 SHF + 1 STS.128 per 16 bytes instead of
-// 4 LDS.32 + 4 SHF + 2 STS.64, and about a third fewer shared-memory wavefronts (the lanes of a warp walk
-// different records, so every access is scattered over the banks).  Looks at most 15 bytes beyond the piece.
-template <int R>
-__device__ __forceinline__ void copy16_loop(uint8_t* sm, uint32_t line, uint32_t d, uint32_t steps, uint32_t sh) {
-    uint4 p = *reinterpret_cast<const uint4*>(sm + line);
-#pragma unroll 2
-    for (uint32_t i = 0; i < steps; i++) {
-        line += 16;
-        const uint4 nx = *reinterpret_cast<const uint4*>(sm + line);
-        uint32_t w0, w1, w2, w3, w4;
-        if (R == 0) { w0 = p.x; w1 = p.y; w2 = p.z; w3 = p.w; w4 = nx.x; }
-        if (R == 1) { w0 = p.y; w1 = p.z; w2 = p.w; w3 = nx.x; w4 = nx.y; }
-        if (R == 2) { w0 = p.z; w1 = p.w; w2 = nx.x; w3 = nx.y; w4 = nx.z; }
-        if (R == 3) { w0 = p.w; w1 = nx.x; w2 = nx.y; w3 = nx.z; w4 = nx.w; }
-        *reinterpret_cast<uint4*>(sm + d) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                                                       __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-        p = nx;
-        d += 16;
-    }
-}
-
-__device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, uint32_t n) {
-    if (n < 48) {
-        copy_small(sm, s, d, n);
-        return;
-    }
-    const uint32_t head = (16u - (d & 15u)) & 15u;  // up to the first 16-byte boundary of the output
-    copy_small(sm, s, d, head);
-    s += head;
-    d += head;
-    n -= head;
-    const uint32_t steps = n >> 4, sh = (s & 3u) * 8u, line = s & ~15u;
-    switch ((s >> 2) & 3u) {
-        case 0: copy16_loop<0>(sm, line, d, steps, sh); break;
-        case 1: copy16_loop<1>(sm, line, d, steps, sh); break;
-        case 2: copy16_loop<2>(sm, line, d, steps, sh); break;
-        default: copy16_loop<3>(sm, line, d, steps, sh); break;
-    }
-    copy_small(sm, s + (steps << 4), d + (steps << 4), n & 15u);
-}
+// (A 16-bytes-per-step form of the loop above - aligned LDS.128, the word rotation fixed per piece, STS.128 - was
+// measured and dropped: the rotation differs from lane to lane, so its four loop variants run one after the other
+// inside a warp; 0.745 ms against 0.645 ms per step, profiles/r01_emit_variants.md.)
 
 // are the n bytes at shared offsets x and y different?
 __device__ __forceinline__ bool differ_s(const uint8_t* sm, uint32_t x, uint32_t y, uint32_t n) {

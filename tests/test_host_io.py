@@ -174,7 +174,11 @@ def test_host_placement_calls_are_safe_without_a_gpu():
     import os
 
     before = os.sched_getaffinity(0)
-    if native.device_count() == 0:
+    try:
+        have_gpu = native.device_count() > 0
+    except native.NativeError:  # no driver at all
+        have_gpu = False
+    if not have_gpu:
         with pytest.raises(native.NativeError):
             native.bind_host_to_device(0)
     else:
