@@ -25,4 +25,7 @@ echo "ncu launches exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_emit_stage|k_align|k_scan}" -c ${NCU_COUNT:-8} -o $OUT/new_kernels \
   python bench.py --steps 1 --warmup 0 --no-cpu --no-files --no-e2e --batches 1 --batch-pairs 1000000 > $OUT/ncu_full.log 2>&1
 echo "ncu full exit $?"
+# gpurun brings back at most 64 MiB: keep the per-launch summary, drop a report that would not fit
+python scripts/ncu_summary.py $OUT/new_kernels.ncu-rep $OUT/ncu_summary.csv > /dev/null 2>&1
+if [ "$(stat -c %s $OUT/new_kernels.ncu-rep 2>/dev/null || echo 0)" -gt 40000000 ]; then rm -f $OUT/new_kernels.ncu-rep; fi
 ls -la $OUT
