@@ -174,7 +174,9 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     }
 
     Shared sh;
-    const int n_jobs = 2 * n_dev + 2;
+    // batches in circulation: one with the reader, two per GPU in flight, one with the writer, and one spare per stage
+    // boundary so that a slow batch in one stage does not stall the others
+    const int n_jobs = 3 * n_dev + 3;
     std::vector<std::unique_ptr<Job>> jobs;
     Queue<Job*> free_q, ready_q, done_q;
     sh.free_q = &free_q;
@@ -386,9 +388,15 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         timing->write_deflate = t_write;
         timing->total = seconds_since(t_start);
     }
-    csq_text_reader_close(reader);
-    destroy_plans();
-    jobs.clear();
+    stamp("outputs closed");
+    // tear down side by side: un-pinning the jobs' host buffers and freeing the plans' device buffers are both slow
+    // driver calls (together ~0.3 s behind a 2 M-pair run when done one after the other)
+    {
+        std::thread unpin([&] { jobs.clear(); });
+        csq_text_reader_close(reader);
+        destroy_plans();
+        unpin.join();
+    }
     stamp("teardown done");
     if (sh.err_code) {
         csq_set_error(sh.err_msg.c_str());

@@ -87,6 +87,7 @@ def main():
     ap.add_argument("--batch-reads", type=int, default=0)
     ap.add_argument("--out", default=None)
     ap.add_argument("--tmp", default=None)
+    ap.add_argument("--variants", default="plain,gz", help="comma separated: plain, gz")
     args = ap.parse_args()
     import bench
     from cutseq_b200 import native
@@ -96,7 +97,7 @@ def main():
     results = []
     try:
         batch = native.synth_batch(2, args.pairs, first_index=0, buffer=0)
-        for variant in ("plain", "gz"):
+        for variant in args.variants.split(","):
             ext = ".fq.gz" if variant == "gz" else ".fq"
             ins = [os.path.join(tmp, f"in_R{m}{ext}") for m in (1, 2)]
             t0 = time.time()
