@@ -138,6 +138,9 @@ def files_leg(prog, pairs):
                     "short": [os.path.join(tmp, f"out_short_R{m}{ext}") for m in (1, 2)]}
             best = None
             for rep in range(2):
+                for q in outs["trimmed"] + outs["short"]:  # a fresh run writes new files
+                    if os.path.exists(q):
+                        os.remove(q)
                 t0 = time.time()
                 counters, timing = native.run_files(prog, ins, outs, gpus=1, threads=os.cpu_count() or 4)
                 wall = time.time() - t0
