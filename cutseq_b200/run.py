@@ -86,31 +86,110 @@ def minimal_report_text(counters, prog) -> str:
     return "\t".join(header) + "\n" + "\t".join(str(x) for x in fields)
 
 
+_ADAPTER_TYPES = None
+
+
+def _adapter_types():
+    """csq adapter kind -> (cutadapt ``descriptive_identifier``, is 5' end).  Recalled from cutadapt 5.x adapters.py
+    (unverified here, like everything below the boundary: DESIGN.md section 2)."""
+    global _ADAPTER_TYPES
+    if _ADAPTER_TYPES is None:
+        from . import _abi as A
+
+        _ADAPTER_TYPES = {
+            A.AD_FRONT: ("regular_five_prime", True), A.AD_RIGHTMOST_FRONT: ("rightmost_five_prime", True),
+            A.AD_NI_FRONT: ("noninternal_five_prime", True), A.AD_PREFIX: ("anchored_five_prime", True),
+            A.AD_BACK: ("regular_three_prime", False), A.AD_BACK_ANYWHERE: ("regular_three_prime", False),
+            A.AD_NI_BACK: ("noninternal_three_prime", False), A.AD_SUFFIX: ("anchored_three_prime", False),
+        }
+    return _ADAPTER_TYPES
+
+
+def _error_lengths(length: int, rate: float):
+    """cutadapt ``ErrorRanges(length, error_rate).lengths()``: the last overlap length of every allowed-error count
+    but the final one (rate 0.2, 20 nt: 0 errors up to 4, 1 up to 9, 2 up to 14, 3 up to 19 -> [4, 9, 14, 19])."""
+    out, prev = [], 0
+    for n in range(1, length + 1):
+        k = int(n * rate)
+        if k != prev:
+            out.append(n - 1)
+            prev = k
+    return out
+
+
+def _adapter_entries(counters, mate, ops):
+    """``adapters_read1`` / ``adapters_read2`` of cutadapt's ``Statistics.as_json()``.  With several AdapterCutters
+    per mate only the FIRST one reaches the statistics (the reference swallows the assertion of the second,
+    run.py:58-73); cutadapt numbers unnamed adapters "1", "2", ... in the order run.py creates them, so the first
+    cutter of mate 1 holds adapter "1" and that of mate 2 adapter "2" (single-end: "1").  The reference empties
+    ``trimmed_lengths`` (run.py:286-301); a 5' end keeps no adjacent-base statistics."""
+    from . import _abi as A
+
+    for i, op in enumerate(ops):
+        if op.kind != A.OP_ALIGN:
+            continue
+        kind, five = _adapter_types()[op.adapter_kind]
+        anchored = op.adapter_kind in (A.AD_PREFIX, A.AD_SUFFIX)
+        end = {
+            "type": kind, "sequence": op.adapter, "error_rate": op.max_error_rate, "indels": True,
+            "error_lengths": None if anchored else _error_lengths(len(op.adapter), op.max_error_rate),
+            "matches": int(counters.with_adapters[mate][i]), "adjacent_bases": None, "dominant_adjacent_base": None,
+            "trimmed_lengths": [],
+        }
+        return [{"name": str(mate + 1), "total_matches": end["matches"], "on_reverse_complement": None, "linked": False,
+                 "five_prime_end": end if five else None, "three_prime_end": None if five else end}]
+    return []
+
+
 def json_report(file, counters, prog, barcode, input1, input2, output1, output2, short1, short2, untrimmed1, untrimmed2):
-    """``--json-file`` (reference run.py:222-302): paths, barcode dict and the read/base counters."""
-    total_bp = int(counters.total_bp[0]) + int(counters.total_bp[1])
+    """``--json-file`` (reference run.py:222-302): paths, barcode dict and ``stats.as_json()`` - read / base-pair
+    counters and the adapter entries in cutadapt's layout (recalled, see ``_adapter_entries``); per-length
+    histograms are not collected (the reference throws them away)."""
+    from . import _abi as A
+
+    paired = bool(input2)
+    total_bp = int(counters.total_bp[0]) + (int(counters.total_bp[1]) if paired else 0)
+    qt = [int(counters.quality_trimmed_bp[0]), int(counters.quality_trimmed_bp[1]) if paired else None]
+    has_qtrim = [any(op.kind == A.OP_QTRIM for op in ops) for ops in (prog.ops_r1, prog.ops_r2 if paired else [])] + [False]
+    qt = [q if (q is not None and has_qtrim[i]) else None for i, q in enumerate(qt)]
+    entries = [_adapter_entries(counters, 0, prog.ops_r1), _adapter_entries(counters, 1, prog.ops_r2) if paired else None]
     d = {
         "tag": "Cutadapt report",
         "cutadapt_version": f"cutseq_b200 {__version__}",
-        "input": {"path1": input1, "path2": input2, "paired": bool(input2)},
+        "input": {"path1": input1, "path2": input2, "paired": paired},
         "output": {"output1": output1, "output2": output2, "short1": short1, "short2": short2,
                    "untrimmed1": untrimmed1, "untrimmed2": untrimmed2},
         "barcode": barcode.to_dict(),
         "read_counts": {
             "input": int(counters.n),
-            "filtered": {"too_short": int(counters.too_short), "is_untrimmed_any": int(counters.untrimmed)},
+            # cutadapt lists its own filters (None = not used); cutseq's IsUntrimmedAny predicate is not one of them,
+            # its count is kept under its descriptive identifier
+            "filtered": {"too_short": int(counters.too_short), "too_long": None, "too_many_n": None,
+                         "too_many_expected_errors": None, "casava_filtered": None, "discard_trimmed": None,
+                         "discard_untrimmed": None, "is_untrimmed_any": int(counters.untrimmed)},
             "output": int(counters.written),
+            "reverse_complemented": None,
+            "read1_with_adapter": entries[0][0]["total_matches"] if entries[0] else None,
+            "read2_with_adapter": (entries[1][0]["total_matches"] if entries[1] else None) if paired else None,
         },
         "basepair_counts": {
             "input": total_bp,
             "input_read1": int(counters.total_bp[0]),
-            "input_read2": int(counters.total_bp[1]) if input2 else None,
-            "quality_trimmed_read1": int(counters.quality_trimmed_bp[0]),
-            "quality_trimmed_read2": int(counters.quality_trimmed_bp[1]) if input2 else None,
-            "output": int(counters.written_bp[0]) + int(counters.written_bp[1]),
+            "input_read2": int(counters.total_bp[1]) if paired else None,
+            "quality_trimmed": sum(q for q in qt if q is not None) if any(q is not None for q in qt) else None,
+            "quality_trimmed_read1": qt[0],
+            "quality_trimmed_read2": qt[1],
+            "poly_a_trimmed": None,
+            "poly_a_trimmed_read1": None,
+            "poly_a_trimmed_read2": None,
+            "output": int(counters.written_bp[0]) + (int(counters.written_bp[1]) if paired else 0),
             "output_read1": int(counters.written_bp[0]),
-            "output_read2": int(counters.written_bp[1]) if input2 else None,
+            "output_read2": int(counters.written_bp[1]) if paired else None,
         },
+        "adapters_read1": entries[0],
+        "adapters_read2": entries[1],
+        "poly_a_trimmed_read1": None,
+        "poly_a_trimmed_read2": None,
     }
     with open(file, "w") as fh:
         fh.write(json.dumps(d, indent=2))
