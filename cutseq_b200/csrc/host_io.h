@@ -125,6 +125,11 @@ struct MateTextReader {  // cuts the byte stream of one mate into batches of who
     int open(const char* path);
     int next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads);
     int next_plain(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads);
+    // BGZF (bgzip) files: every member carries its compressed size in a 'BC' extra field and its uncompressed size
+    // in the trailer, so the members of the next batch are inflated side by side straight into the pinned buffer
+    bool bgzf = false;
+    uint64_t gz_off = 0;         // file offset of the next member
+    int next_bgzf(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads);
     int finish_at_eof(PinnedBuf& buf, size_t pos, uint64_t lines, uint64_t* bytes, uint32_t* n_reads);
 };
 

@@ -15,6 +15,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <thread>
 
 #if defined(__SSE2__)
@@ -207,6 +208,8 @@ long RawSource::read(uint8_t* dst, size_t n) {
     return (long)done;
 }
 
+static size_t bgzf_member_size(const uint8_t* p, size_t n);
+
 int MateTextReader::open(const char* path) {
     carry.clear();
     carry_pos = 0;
@@ -217,6 +220,16 @@ int MateTextReader::open(const char* path) {
     const int rc = src.open(path);
     if (rc) return rc;
     struct stat sb;
+    bgzf = false;
+    gz_off = 0;
+    if (src.gz && src.map && bgzf_member_size(src.map, src.map_len)) {
+        bgzf = true;
+        const char* env = getenv("CSQ_READ_THREADS");
+        read_threads = env ? atoi(env) : (int)(std::thread::hardware_concurrency() / 3);
+        if (!env && read_threads > 8) read_threads = 8;
+        if (read_threads < 1) read_threads = 1;
+        if (read_threads > 16) read_threads = 16;
+    }
     if (!src.gz && fstat(src.fd, &sb) == 0 && S_ISREG(sb.st_mode)) {
         plain_file = true;
         file_size = (uint64_t)sb.st_size;
@@ -228,6 +241,124 @@ int MateTextReader::open(const char* path) {
         if (read_threads > 16) read_threads = 16;
     }
     return 0;
+}
+
+// Length of the BGZF member at p (n bytes left in the file), 0 if it is not one: gzip header with FEXTRA holding
+// the subfield 'B' 'C' of two bytes = total member size - 1 (SAM/BAM specification, section 4.1).
+static size_t bgzf_member_size(const uint8_t* p, size_t n) {
+    if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+    const size_t xlen = p[10] | ((size_t)p[11] << 8);
+    if (12 + xlen > n) return 0;
+    for (size_t q = 12; q + 4 <= 12 + xlen;) {
+        const size_t slen = p[q + 2] | ((size_t)p[q + 3] << 8);
+        if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+            const size_t total = (size_t)(p[q + 4] | ((size_t)p[q + 5] << 8)) + 1;
+            return total >= 12 + xlen + 8 && total <= n ? total : 0;
+        }
+        q += 4 + slen;
+    }
+    return 0;
+}
+
+int MateTextReader::next_bgzf(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads) {
+    const uint64_t target = 4ull * max_reads;
+    *bytes = 0;
+    *n_reads = 0;
+    size_t pos = 0;      // bytes in buf
+    uint64_t lines = 0;  // line ends among them
+    const size_t avail = carry.size() - carry_pos;
+    if (avail) {  // what the previous batch left behind its cut
+        const uint8_t* c = carry.data() + carry_pos;
+        const uint64_t k = count_newlines(c, avail);
+        if (k >= target) {
+            const uint64_t cut = after_kth_newline(c, avail, target);
+            if (!buf.reserve((size_t)cut + 64, 0)) return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
+            memcpy(buf.p, c, (size_t)cut);
+            carry_pos += (size_t)cut;
+            *bytes = cut;
+            *n_reads = max_reads;
+            records_done += max_reads;
+            return 0;
+        }
+        if (!buf.reserve(avail + 64, 0)) return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
+        memcpy(buf.p, c, avail);
+        pos = avail;
+        lines = k;
+    }
+    carry.clear();
+    carry_pos = 0;
+    struct Member {
+        const uint8_t* p;
+        size_t clen, isize, out_off;
+        uint64_t lines;
+        const char* err;
+    };
+    std::vector<Member> mems;
+    size_t want = hint_bytes ? hint_bytes + hint_bytes / 32 + (128u << 10) : (size_t)max_reads * 384 + (128u << 10);
+    while (gz_off < src.map_len) {
+        // the members that hold the next `round` bytes
+        const size_t round = want > pos ? want - pos : (size_t)(64u << 10);
+        mems.clear();
+        size_t acc = 0;
+        while (acc < round && gz_off < src.map_len) {
+            const uint8_t* p = src.map + gz_off;
+            const size_t left = src.map_len - (size_t)gz_off;
+            const size_t total = bgzf_member_size(p, left);
+            if (!total) return io_fail(CSQ_ERR_IO, "%s: not a BGZF member at offset %llu (the file started as BGZF)", src.name.c_str(), (unsigned long long)gz_off);
+            const size_t isize = p[total - 4] | ((size_t)p[total - 3] << 8) | ((size_t)p[total - 2] << 16) | ((size_t)p[total - 1] << 24);
+            mems.push_back(Member{p, total, isize, pos + acc, 0, nullptr});
+            acc += isize;
+            gz_off += total;
+        }
+        if (!buf.reserve(pos + acc + 64, pos)) return io_fail(CSQ_ERR_NOMEM, "out of host memory for a batch of %u reads", max_reads);
+        std::atomic<size_t> cursor{0};
+        auto work = [&] {
+            Inflater inf;
+            for (;;) {
+                const size_t i = cursor++;
+                if (i >= mems.size()) return;
+                Member& mb = mems[i];
+                inf.reset(mb.p, mb.clen);
+                size_t done = 0;
+                while (done < mb.isize) {
+                    const long got = inf.read(buf.p + mb.out_off + done, mb.isize - done);
+                    if (got <= 0) break;
+                    done += (size_t)got;
+                }
+                uint8_t probe;
+                if (done != mb.isize || inf.read(&probe, 1) != 0) {
+                    mb.err = inf.error()[0] ? "corrupt BGZF member" : "BGZF member size does not match its trailer";
+                    continue;
+                }
+                mb.lines = count_newlines(buf.p + mb.out_off, mb.isize);
+            }
+        };
+        int nt = read_threads;
+        if ((size_t)nt > mems.size()) nt = (int)mems.size();
+        std::vector<std::thread> helpers;
+        for (int t = 1; t < nt; t++) helpers.emplace_back(work);
+        work();
+        for (auto& th : helpers) th.join();
+        for (const Member& mb : mems)
+            if (mb.err) return io_fail(CSQ_ERR_IO, "%s: %s", src.name.c_str(), mb.err);
+        for (const Member& mb : mems) {
+            if (lines + mb.lines >= target) {
+                const uint64_t rel = after_kth_newline(buf.p + mb.out_off, mb.isize, target - lines);
+                const size_t cut = mb.out_off + (size_t)rel;
+                carry.assign(buf.p + cut, buf.p + pos + acc);
+                hint_bytes = cut;
+                *bytes = cut;
+                *n_reads = max_reads;
+                records_done += max_reads;
+                return 0;
+            }
+            lines += mb.lines;
+        }
+        pos += acc;
+        want = pos + pos / 8 + (256u << 10);
+    }
+    eof = true;
+    return finish_at_eof(buf, pos, lines, bytes, n_reads);
 }
 
 // End of the input: a missing final line end is accepted, and so are blank lines behind the last record (dnaio).
@@ -351,6 +482,7 @@ int MateTextReader::next_plain(uint32_t max_reads, PinnedBuf& buf, uint64_t* byt
 // The next max_reads records (fewer at the end of the input) as raw text into buf.
 int MateTextReader::next(uint32_t max_reads, PinnedBuf& buf, uint64_t* bytes, uint32_t* n_reads) {
     if (plain_file) return next_plain(max_reads, buf, bytes, n_reads);
+    if (bgzf) return next_bgzf(max_reads, buf, bytes, n_reads);
     const uint64_t target = 4ull * max_reads;
     size_t piece = (size_t)max_reads * 512;
     piece = piece < (64u << 10) ? (64u << 10) : piece > (4u << 20) ? (4u << 20) : piece;

@@ -276,6 +276,52 @@ def test_text_reader_parallel_pread_of_plain_files(tmp_path, monkeypatch, thread
         assert total == len(recs) and b"".join(got) == text
 
 
+def _bgzf(data: bytes, block: int = 0xFF00) -> bytes:
+    """bgzip's container: gzip members of at most 64 KiB with a 'BC' extra field (total size - 1), an empty member
+    at the end (SAM/BAM specification, section 4.1)."""
+    import struct
+    import zlib
+
+    out = b""
+    for off in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if off is None else data[off:off + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(chunk) + c.flush()
+        total = 12 + 6 + len(body) + 8
+        out += (b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, total - 1)
+                + body + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return out
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_text_reader_inflates_bgzf_members_side_by_side(tmp_path, monkeypatch, threads):
+    monkeypatch.setenv("CSQ_READ_THREADS", threads)
+    recs = _records(20000, read_len=150, seed=8) + _records(3000, read_len=5, seed=9)
+    text = "".join(recs).encode()
+    (tmp_path / "a.fq.gz").write_bytes(_bgzf(text))
+    assert gzip.decompress((tmp_path / "a.fq.gz").read_bytes()) == text  # the fixture is a valid gzip file
+    for batch in (1000, 9000, 50000):
+        got, total = [], 0
+        with native.TextReader(str(tmp_path / "a.fq.gz")) as r:
+            while True:
+                n, texts, first_record = r.next(batch)
+                if n == 0:
+                    break
+                assert first_record == total and texts[0].count(b"\n") == 4 * n
+                got.append(texts[0])
+                total += n
+        assert total == len(recs) and b"".join(got) == text
+    # a flipped byte in the middle of the file is caught by the member's CRC / structure
+    raw = bytearray(_bgzf(text))
+    raw[len(raw) // 2] ^= 0x55
+    (tmp_path / "bad.fq.gz").write_bytes(bytes(raw))
+    with native.TextReader(str(tmp_path / "bad.fq.gz")) as r:
+        with pytest.raises(native.NativeError) as e:
+            while r.next(50000)[0]:
+                pass
+        assert e.value.code == A.ERR_IO
+
+
 def test_text_reader_errors(tmp_path):
     (tmp_path / "short.fq").write_bytes(b"@r1\nACGT\n+\nIIII\n@r2\nAC\n")
     with native.TextReader(str(tmp_path / "short.fq")) as r:
