@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 
 #include <atomic>
 #include <chrono>
@@ -176,7 +177,13 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     Shared sh;
     // batches in circulation: one with the reader, two per GPU in flight, one with the writer, and one spare per stage
     // boundary so that a slow batch in one stage does not stall the others
-    const int n_jobs = 3 * n_dev + 3;
+    // (every job pins ~100 MB of host memory, ~0.1 s each in a VM: short inputs get by with the minimum of one per stage)
+    uint64_t in_bytes = 0;
+    for (int m = 0; m < n_mates; m++) {
+        struct stat sb;
+        if (stat(files->in[m], &sb) == 0) in_bytes += (uint64_t)sb.st_size * (strlen(files->in[m]) > 3 && !strcmp(files->in[m] + strlen(files->in[m]) - 3, ".gz") ? 4 : 1);
+    }
+    const int n_jobs = in_bytes < (3ull << 30) ? 2 * n_dev + 2 : 3 * n_dev + 3;
     std::vector<std::unique_ptr<Job>> jobs;
     Queue<Job*> free_q, ready_q, done_q;
     sh.free_q = &free_q;
