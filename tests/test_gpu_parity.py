@@ -233,6 +233,49 @@ def test_odd_headers_and_names():
     compare_with_oracle(prog, [[(nm, seq, q) for nm in names]])
 
 
+@pytest.mark.parametrize("flags", [0, A.PLAN_EMIT_G16], ids=["emit_stage", "emit_g16"])
+def test_long_and_mixed_length_pairs(flags):
+    """Reads of 250-850 bases beside short ones: the staged emitter has to halve its passes (8 pairs no longer fit its
+    shared-memory buffers), down to single pairs, and the DP walks windows far into long reads."""
+    prog = helpers.program_for(["-A", "TAKARAV3", "--trim-polyA"], 2)
+    rng = random.Random(99)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    p7, p5rc = "AGATCGGAAGAGCACACGTC", "AGATCGGAAGAGCGTCGTGT"
+
+    def noisy(seq):
+        out = []
+        for c in seq:
+            t = rng.random()
+            if t < 0.01:
+                out.append(rng.choice("ACGTN"))
+            elif t < 0.012:
+                continue
+            else:
+                out.append(c)
+        return "".join(out)
+
+    r1, r2 = [], []
+    for k in range(360):
+        read_len = rng.choice([250, 40, 600, 150, 850, 300])
+        insert = rng.randint(10, read_len + 200)
+        frag = "".join(rng.choice("ACGT") for _ in range(insert))
+        if rng.random() < 0.2:
+            frag = "T" * rng.randint(10, 40) + frag  # poly-T at the start of R1 (strand '-')
+        rc = "".join(comp[c] for c in reversed(frag))
+        s1 = noisy(frag + p7 + "TGAACTCCAGTCAC" + "G" * read_len)[:read_len]
+        s2 = noisy(rc + p5rc + "AGATCTCGGTGGTCGCCGTATCATT" + "G" * read_len)[:read_len]
+        q1 = "".join(rng.choice("II9-#") for _ in s1)
+        q2 = "".join(rng.choice("II9-#") for _ in s2)
+        r1.append((f"P{k}:{read_len} 1:N:0:ACGT", s1, q1))
+        r2.append((f"P{k}:{read_len} 2:N:0:ACGT", s2, q2))
+    want = compare_with_oracle(prog, [r1, r2], flags)
+    # the same records as a text batch (one source span per mate and pass in the staged emitter)
+    texts = ["".join(f"@{n}\n{s_}\n+\n{q}\n" for (n, s_, q) in recs).encode() for recs in (r1, r2)]
+    with native.Plan(prog, 0, flags) as plan:
+        got, _ = plan.run_text(texts, len(r1))
+    assert got == want
+
+
 def test_random_programs_against_oracle():
     rng = random.Random(2024)
     for it in range(12):
