@@ -217,6 +217,23 @@ def test_pairing_error_is_reported():
     assert oracle.run_batch(prog, batch)["status"] == A.ERR_PAIRING
 
 
+def test_pairing_error_in_a_pair_that_bypasses_the_staging_buffers():
+    """Headers of 30 KB: the pair does not fit the emitter's shared-memory buffers and is written bytewise; the id
+    check of PairedEndRenamer has to work there too (ids differ in their last character only)."""
+    prog = helpers.program_for(["-A", "TAKARAV3"], 2)
+    seq, q = "ACGTTGCA" * 10, "I" * 80
+    long_id = "x" * 300
+    good = [(f"{long_id}a " + "c" * 30000, seq, q), ("r2 1", seq, q)]
+    mate = [(f"{long_id}a " + "d" * 30000, seq, q), ("r2 2", seq, q)]
+    compare_with_oracle(prog, [good, mate])
+    bad = [(f"{long_id}b " + "d" * 30000, seq, q), ("r2 2", seq, q)]
+    batch, keep = oracle.make_batch(good, bad)
+    with native.Plan(prog) as plan:
+        with pytest.raises(native.NativeError) as e:
+            plan.run_batch(batch)
+        assert e.value.code == A.ERR_PAIRING
+
+
 def test_read_length_limit_is_an_error():
     prog = helpers.program_for(["-A", "TAKARAV3"], 1)
     batch, keep = oracle.make_batch([("x", "A" * 1000, "I" * 1000)])
