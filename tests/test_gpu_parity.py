@@ -406,6 +406,26 @@ def test_text_batch_odd_records(pflags):
 
 
 @pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
+def test_text_batch_mixed_line_endings(pflags):
+    """CRLF and LF records in one batch, a '\\r' in the middle of a header, a '+' line that repeats the name with
+    CRLF: only the '\\r' in front of a line end is dropped (dnaio), wherever the batch-wide CR flag is set."""
+    prog = helpers.program_for(["-A", "SMALLRNA"], 1)
+    rng = random.Random(21)
+    text, clean = b"", b""
+    for i in range(3000):
+        seq = "".join(rng.choice("ACGT") for _ in range(rng.randint(0, 60))) + "AGATCGGAAGAGCACACGTC"[: rng.randint(0, 20)]
+        name = f"r{i} co\rmment" if i % 17 == 3 else f"r{i} comment"
+        plus = name if i % 5 == 0 else ""
+        eol = "\r\n" if i % 3 else "\n"
+        text += f"@{name}{eol}{seq}{eol}+{plus}{eol}{'I' * len(seq)}{eol}".encode()
+        clean += f"@{name}\n{seq}\n+{plus}\n{'I' * len(seq)}\n".encode()
+    want = oracle_text(prog, [clean])
+    with native.Plan(prog, 0, pflags) as plan:
+        got, _ = plan.run_text([text], 3000)
+    assert got[0][0] == want[0][0] and got[1][0] == want[1][0]
+
+
+@pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
 def test_text_batch_lines_longer_than_a_parse_tile(pflags):
     """Header comments / '+' lines of 20-50 KB: whole 16 KiB parse tiles without a line end, so the start of the
     open line has to be carried across several tiles by the look-back."""
