@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
         if verbose or "warning" in out:
             sys.stderr.write(out)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static", "-lz", "-lpthread"]
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static", "-lz", "-lpthread"]
     subprocess.check_call(cmd)
     return LIB
 
