@@ -168,6 +168,13 @@ def run_reference(args):
         return 0
     prog = takara_program()
     sample = 200_000
+    # the real `cutseq -t <cores>` would be the preferred CPU arm, but it needs the cutadapt package
+    # (and the reference tree, which does not travel to the GPU box); probed here so that the line says which it is
+    try:
+        import cutadapt  # noqa: F401
+        have_cutadapt = True
+    except Exception:
+        have_cutadapt = False
     value, threads, step_s = cpu_leg(prog, args.steps, min(args.warmup, 1), sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -176,7 +183,8 @@ def run_reference(args):
         "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; step = {sample} pairs (bounded sample)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} x {sample} pairs of the config-2 generator, oracle/cutseq_oracle.c (restated "
-                                   "cutadapt chain; the reference needs the absent cutadapt package), gzip/parse excluded"},
+                                   "cutadapt chain; the reference needs the absent cutadapt package), gzip/parse excluded",
+                         "cutadapt_importable": have_cutadapt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
