@@ -197,9 +197,12 @@ def json_report(file, counters, prog, barcode, input1, input2, output1, output2,
 
 def _run_program(prog, inputs, outputs, settings):
     from . import native
+    from .transcode import Transcoders
 
-    return native.run_files(prog, inputs, outputs, gpus=getattr(settings, "gpus", 1),
-                            threads=settings.threads, batch_reads=getattr(settings, "batch_reads", 0))
+    # .bz2 / .xz files (xopen handles them in the reference) go through named pipes and Python's codecs
+    with Transcoders(inputs, outputs) as tc:
+        return native.run_files(prog, tc.inputs, tc.outputs, gpus=getattr(settings, "gpus", 1),
+                                threads=settings.threads, batch_reads=getattr(settings, "batch_reads", 0))
 
 
 def pipeline_single(input1, output1, short1, untrimmed1, barcode, settings):
@@ -275,7 +278,7 @@ def build_parser() -> argparse.ArgumentParser:
         description="Trim sequencing adapters, barcodes, UMIs and masks from NGS reads on NVIDIA B200 GPUs "
         "(cutseq-compatible command line).",
     )
-    p.add_argument("input_file", type=str, nargs="*", help="One (single-end) or two (paired-end) FASTQ files, plain or .gz.")
+    p.add_argument("input_file", type=str, nargs="*", help="One (single-end) or two (paired-end) FASTQ files: plain, .gz (incl. bgzip), .bz2 or .xz.")
     p.add_argument("-a", "--adapter-scheme", type=str,
                    help="Library scheme, e.g. P5(INLINE5)NNNNXXX>XXXNNNN(INLINE3)P7: adapters, optional inline barcodes in "
                    "parentheses, N = UMI bases, X = masked bases, and the strand symbol > (forward), < (reverse) or - (unknown).")

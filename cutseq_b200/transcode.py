@@ -1,0 +1,108 @@
+"""Compression formats that the native reader / writer does not speak itself.
+
+The reference opens every file through xopen (behind cutadapt's ``InputPaths`` / ``OutputFiles``, run.py:434-436,
+751-753), which handles ``.gz``, ``.bz2``, ``.xz`` and ``.zst`` by file name.  The native library reads plain and gzip
+(incl. BGZF) files and writes plain and gzip.  For ``.bz2`` and ``.xz`` this module puts a named pipe between the
+file and the library and a Python thread on the other end of it (``bz2`` / ``lzma`` release the GIL while they
+work): the library sees a plain FASTQ stream, nothing below the C ABI changes.  ``.zst`` needs a module that this
+interpreter does not ship; it is refused with a clear message instead of being misread as plain text.
+"""
+
+from __future__ import annotations
+
+import bz2
+import errno
+import lzma
+import os
+import shutil
+import tempfile
+import threading
+
+_OPENERS = {".bz2": bz2.open, ".xz": lzma.open, ".lzma": lzma.open}
+_UNSUPPORTED = (".zst", ".zstd")
+
+
+def _opener(path):
+    if path is None:
+        return None
+    low = str(path).lower()
+    for ext in _UNSUPPORTED:
+        if low.endswith(ext):
+            raise ValueError(f"{path}: zstd-compressed files are not supported by this build (use .gz, .bz2, .xz or plain FASTQ)")
+    for ext, fn in _OPENERS.items():
+        if low.endswith(ext):
+            return fn
+    return None
+
+
+class Transcoders:
+    """Context manager: ``tc.inputs`` / ``tc.outputs`` are what the library should open instead of the given paths."""
+
+    def __init__(self, inputs, outputs):
+        self.inputs = list(inputs)
+        self.outputs = {k: list(v) if v else v for k, v in outputs.items()}
+        self._threads = []  # (thread, fifo, "in" | "out")
+        self._errors = []
+        self._tmp = None
+        in_jobs = [(i, p, _opener(p)) for i, p in enumerate(self.inputs)]
+        out_jobs = [(k, m, p, _opener(p)) for k, v in self.outputs.items() if v for m, p in enumerate(v)]
+        self._in_jobs = [j for j in in_jobs if j[2]]
+        self._out_jobs = [j for j in out_jobs if j[3]]
+
+    def __enter__(self):
+        if not self._in_jobs and not self._out_jobs:
+            return self
+        self._tmp = tempfile.mkdtemp(prefix="cutseq_b200_")
+        for i, path, opener in self._in_jobs:
+            fifo = os.path.join(self._tmp, f"in_{i}.fq")
+            os.mkfifo(fifo)
+            self.inputs[i] = fifo
+            self._start(self._feed, (path, opener, fifo), fifo, "in")
+        for k, m, path, opener in self._out_jobs:
+            fifo = os.path.join(self._tmp, f"out_{k}_{m}.fq")  # no compression suffix: the library writes plain text
+            os.mkfifo(fifo)
+            self.outputs[k][m] = fifo
+            self._start(self._drain, (path, opener, fifo), fifo, "out")
+        return self
+
+    def _start(self, fn, args, fifo, side):
+        t = threading.Thread(target=self._guard, args=(fn, args), daemon=True)
+        t.start()
+        self._threads.append((t, fifo, side))
+
+    def _guard(self, fn, args):
+        try:
+            fn(*args)
+        except BrokenPipeError:
+            pass  # the library stopped reading (it reports its own error)
+        except Exception as exc:  # surfaced by __exit__
+            self._errors.append(exc)
+
+    @staticmethod
+    def _feed(path, opener, fifo):
+        with opener(path, "rb") as src, open(fifo, "wb") as dst:
+            shutil.copyfileobj(src, dst, 1 << 20)
+
+    @staticmethod
+    def _drain(path, opener, fifo):
+        with open(fifo, "rb") as src, opener(path, "wb") as dst:
+            shutil.copyfileobj(src, dst, 1 << 20)
+
+    def __exit__(self, exc_type, exc, tb):
+        # The library has returned: a pump that is still running is either busy (it ends at the end of its pipe) or
+        # waiting in open() for a pipe the library never opened - the other end is opened for a moment to release it.
+        for t, fifo, side in self._threads:
+            t.join(timeout=0.05 if exc_type else 0.5)
+            while t.is_alive():
+                try:
+                    fd = os.open(fifo, (os.O_RDONLY if side == "in" else os.O_WRONLY) | os.O_NONBLOCK)
+                    os.close(fd)
+                except OSError as e:
+                    if e.errno not in (errno.ENXIO, errno.ENOENT):
+                        raise
+                t.join(timeout=0.2)
+        if self._tmp:
+            shutil.rmtree(self._tmp, ignore_errors=True)
+        if exc_type is None and self._errors:
+            raise self._errors[0]
+        return False

@@ -42,6 +42,29 @@ def test_plain_outputs_and_explicit_names(tmp_path):
     assert open(s2, "rb").read() == helpers.golden_expected(case, "short_R2")
 
 
+def test_bz2_and_xz_files_through_the_cli(tmp_path):
+    """xopen's other formats: .bz2 input, .xz / .bz2 outputs (named pipes + Python codecs around the native reader /
+    writer, cutseq_b200/transcode.py); a .zst path is refused."""
+    import bz2
+    import lzma
+
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_synth_polya"][0]
+    ins = []
+    for m, p in enumerate(helpers.golden_input_paths(case)):
+        q = str(tmp_path / f"in_R{m + 1}.fq.bz2")
+        with bz2.open(q, "wb") as f:
+            f.write(gzip.open(p).read())
+        ins.append(q)
+    o1, o2, s1, s2 = (str(tmp_path / n) for n in ("t1.fq.xz", "t2.fq.bz2", "s1.fq.gz", "s2.fq.xz"))
+    run.main(case["argv"] + ["-o", o1, o2, "-s", s1, s2, "--batch-reads", "300"] + ins)
+    assert lzma.open(o1).read() == helpers.golden_expected(case, "trimmed_R1")
+    assert bz2.open(o2).read() == helpers.golden_expected(case, "trimmed_R2")
+    assert gzip.open(s1).read() == helpers.golden_expected(case, "short_R1")
+    assert lzma.open(s2).read() == helpers.golden_expected(case, "short_R2")
+    with pytest.raises(ValueError):
+        run.main(case["argv"] + ["-O", str(tmp_path / "z")] + [str(tmp_path / "a.fq.zst"), str(tmp_path / "b.fq.zst")])
+
+
 def test_batch_size_does_not_change_output(tmp_path):
     case = [c for c in helpers.golden_cases() if c["case"] == "inline_custom_ensure"][0]
     outs = []
