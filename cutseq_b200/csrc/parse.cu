@@ -4,16 +4,19 @@
 // records, cut at a record boundary by counting line ends - and these kernels do what dnaio's FASTQ
 // parser (_core.pyx, behind cutadapt's InputPaths in reference run.py:434, 751) does on the CPU:
 //
-//   k_nl_count     reads the text once: a line-end bit mask per 16-byte chunk, line ends per 16 KiB tile
-//   k_tile_scan    exclusive scan of the tile counts (one CTA)
+//   k_nl_count     reads the text once: a line-end bit mask per 16-byte chunk, line ends per 16 KiB tile, and one
+//                  flag "there is a '\r' somewhere in this batch"
+//   k_tile_scan    exclusive scan of the tile counts (one CTA, 8 tiles per thread and sweep)
 //   k_nl_index     from the masks: byte position of every line end, in order, nl[r] = offset of the r-th '\n'
-//   k_records      record i = lines 4i .. 4i+3: '@' / '+' checks, '\r' stripping, equal sequence / quality
-//                  lengths, the read-length limit; writes name / sequence / quality offsets and lengths
+//   k_records      record i = lines 4i .. 4i+3 from the line ends alone: equal sequence / quality lengths, the
+//                  read-length limit; writes name / sequence / quality offsets and lengths.  '\r' stripping only
+//                  when the flag is set; the '@' / '+' line starts are checked by k_finish (kernels.cu), which
+//                  fetches those sectors anyway
 //
 // The trimming kernels then work on the text where it lies (seq == qual == name pool == the text buffer);
 // nothing is copied into a packed layout.  Bound: HBM - the text is read once (plus 1/8 of it written and read
-// back as masks, 16 bytes of line-end offsets per record written, and the six boundary bytes of each record
-// looked at by k_records).  A malformed record is reported as the smallest (record, kind) key through `perr`.
+// back as masks and 16 bytes of line-end offsets per record written and read).  A malformed record is reported
+// as the smallest (record, kind) key through `perr`, in the order dnaio would meet the problems.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
