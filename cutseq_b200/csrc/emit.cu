@@ -1,8 +1,9 @@
 // Order-preserving FASTQ text emission ("@name\nseq\n+\nqual\n", dnaio's fastq_bytes), the sink behind
 // PairedEndSink / SingleEndSink and the two filters of reference run.py:446-471 / 763-792.
-// k_emit_rec (CSQ_PLAN_EMIT_REC) is an alternative to the default warp-per-record k_emit of kernels.cu, kept for
-// A/B runs: it needs 4x fewer instructions, but its per-thread access pattern makes it latency / L1-sector bound
-// and it measures 7 % slower (1.26 ms against 1.17 ms per 2 M pairs, profiles/r01_emit_variants.md).
+// k_emit_rec (CSQ_PLAN_EMIT_REC) is an alternative to the direct k_emit<G> of kernels.cu, kept for A/B runs (the
+// default emitter is k_emit_stage, emit_stage.cu): it needs 4x fewer instructions than k_emit<32>, but its
+// per-thread access pattern makes it latency / L1-sector bound and it measures 7 % slower (1.26 ms against
+// 1.17 ms per 2 M pairs, profiles/r01_emit_variants.md).
 //
 // k_emit_rec: one THREAD per pair (both mates).  Phase 1 is a CTA-wide exclusive scan of the record sizes per output
 // stream (destination x mate), which places every record; phase 2 streams each record into its place

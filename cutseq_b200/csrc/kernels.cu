@@ -1,10 +1,13 @@
 // sm_100a kernels of the trimming chain.
 //
-//   k_align<M>     exact adapter alignment, one thread per read, whole DP column in registers
-//   k_finish       trailing cuts, quality trimming, header suffix stripping + id parsing
+//   k_align<M,H>   exact adapter alignment, one thread per read, whole DP column in registers; H = 2 / 4: homopolymer
+//                  adapters with that many columns side by side (dp_homo)
+//   k_align_split  homopolymer adapters with every DP column over two lanes (default for the poly-A / poly-T 100-mers)
+//   k_finish       trailing cuts, quality trimming, header suffix stripping + id parsing, '@' / '+' checks of text batches
 //   k_pair         TooShort / IsUntrimmedAny decision, record sizes, per-CTA stream totals
-//   k_scan         exclusive scan of the per-CTA totals (6 output streams)
-//   k_emit         order-preserving FASTQ text emission, one warp per record
+//   k_scan         exclusive scan of the per-CTA totals (6 output streams, one sweep)
+//   k_emit<G>      order-preserving FASTQ text emission straight from and to global memory, G lanes per record
+//                  (A/B variant and the reverse-complementing sink; the default emitter is k_emit_stage, emit_stage.cu)
 //   k_int_peak     integer-issue microbenchmark (roofline denominator of the DP)
 //
 // Semantics follow cutadapt 5.x as restated in oracle/cutseq_oracle.c (Aligner.locate of
