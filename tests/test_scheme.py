@@ -97,3 +97,32 @@ def test_dry_run_lists_program(capsys):
     run.main(["-A", "TAKARAV3", "--trim-polyA", "-n", "x.fq"])
     out = capsys.readouterr().out
     assert "Step 1: SuffixRemover('.1')" in out and "NonInternalFrontAdapter" in out and "QualityTrimmer(cutoff_front=0, cutoff_back=20" in out
+
+
+def test_every_builtin_scheme_compiles_to_a_program():
+    """All 18 built-in schemes, single-end and paired, with and without the optional steps: the op program follows the
+    fixed order of run.py:326-426 / 533-731 (strip, 5' adapter, 3' adapter, inline, UMI, rename, mask, polyA, qtrim)."""
+    from cutseq_b200 import _abi as A
+    from cutseq_b200 import program, run
+    from cutseq_b200.common import BUILDIN_ADAPTERS, BarcodeConfig
+
+    for name in BUILDIN_ADAPTERS:
+        for extra in ([], ["--trim-polyA"], ["--trim-polyA-wo-direction", "--no-conditional-cutter", "--ensure-inline-barcode", "--auto-rc"]):
+            args = run.build_parser().parse_args(["-A", name] + extra + ["a.fq", "b.fq"])
+            bc = BarcodeConfig(run.resolve_scheme(args))
+            settings = run.settings_from_args(args)
+            for prog in (program.compile_single(bc, settings), program.compile_paired(bc, settings)):
+                for ops in ([prog.ops_r1, prog.ops_r2] if prog.paired else [prog.ops_r1]):
+                    kinds = [op.kind for op in ops]
+                    assert kinds[0] == A.OP_STRIP_SUFFIX and kinds.count(A.OP_RENAME) == 1 and kinds.count(A.OP_QTRIM) == 1
+                    assert len(ops) <= A.CSQ_MAX_OPS
+                    # the two full-adapter searches come first among the alignments: 5' (rightmost front), then 3' (back)
+                    aligns = [op for op in ops if op.kind == A.OP_ALIGN]
+                    assert aligns[0].adapter_kind == A.AD_RIGHTMOST_FRONT and aligns[0].min_overlap == 10
+                    assert aligns[1].adapter_kind in (A.AD_BACK, A.AD_BACK_ANYWHERE) and aligns[1].min_overlap == 3
+                    # nothing but REVCOMP may follow the quality trimmer
+                    q = kinds.index(A.OP_QTRIM)
+                    assert all(k == A.OP_REVCOMP for k in kinds[q + 1:])
+                    # the rename sits between the UMI cuts and the mask cuts: it is preceded by at most the UMI cuts
+                    assert kinds.index(A.OP_RENAME) > kinds.index(A.OP_ALIGN)
+                assert prog.describe()
