@@ -40,15 +40,9 @@ DEST_TRIMMED, DEST_SHORT, DEST_UNTRIMMED = 0, 1, 2
 
 PLAN_KEEP_MATCHES = 1
 PLAN_NO_PREFILTER = 2
-PLAN_EMIT_REC = 8
-PLAN_EMIT_G32 = 16
-PLAN_EMIT_G8 = 32
 PLAN_ONE_STREAM = 64
-PLAN_PARSE_ONEPASS = 128
 PLAN_EMIT_G16 = 256
-PLAN_HOMO_V1 = 512
 PLAN_NO_EXACT_STOP = 1024
-PLAN_HOMO_ONE_LANE = 2048
 
 
 class csq_op(C.Structure):

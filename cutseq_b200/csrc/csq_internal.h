@@ -111,7 +111,8 @@ struct PairParams {
     int32_t min_length, untrimmed_enabled;
     uint32_t required[2];
     uint32_t rename_parts;  // of the RENAME op (same on both mates)
-    int32_t check_ids;      // paired RENAME present: mate ids must be equal
+    int32_t check_ids;      // paired RENAME present: PairedEndRenamer's record_names_match on the suffix-stripped headers
+                            // (dnaio's paired reader check on the raw headers applies to every paired batch)
     int32_t revcomp;        // single-end REVCOMP op present
     uint8_t* dest;          // [n]
     uint32_t* block_tot;    // [nblk][8]: bytes per (dest,mate) stream (6 used)
@@ -134,14 +135,12 @@ enum {
 
 // launchers implemented in kernels.cu (all asynchronous on `stream`)
 cudaError_t csq_launch_align(const AlignParams& p, uint32_t n_items, cudaStream_t stream);
-cudaError_t csq_launch_finish(const FinishParams& p, cudaStream_t stream);
-cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream);
+cudaError_t csq_launch_tail(const FinishParams& f1, const FinishParams& f2, const PairParams& p, cudaStream_t stream);  // tail.cu
 cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
                             unsigned long long* block_off, unsigned long long* totals, cudaStream_t stream);
-cudaError_t csq_launch_emit(const EmitParams& p, int lanes_per_record, cudaStream_t stream);  // kernels.cu: 32 / 16 / 8 lanes per record
+cudaError_t csq_launch_emit(const EmitParams& p, int lanes_per_record, cudaStream_t stream);  // kernels.cu: direct, 16 lanes per record
 cudaError_t csq_launch_emit_stage(const EmitParams& p, cudaStream_t stream); // emit_stage.cu: staged through shared memory (default)
-cudaError_t csq_launch_emit_rec(const EmitParams& p, cudaStream_t stream);   // emit.cu: thread per pair, 16-byte chunks (CSQ_PLAN_EMIT_REC)
-cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* masks, uint32_t* ticket, bool v1, cudaStream_t stream);
+cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* masks, cudaStream_t stream);
 uint32_t csq_parse_tiles(uint64_t bytes);
 cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t* list_count, cudaStream_t stream);
 bool csq_align_has_exact_kernel(int m);

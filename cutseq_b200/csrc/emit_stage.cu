@@ -25,8 +25,8 @@
 //
 // Every source byte is read once and every output byte written once.  A pass that does not fit the staging
 // buffers is halved; a pair that does not fit alone (reads near the length limit with very long headers) takes
-// a bytewise path.  PairedEndRenamer's id check compares the two staged ids.  The reverse-complementing
-// single-end sink stays with k_emit<16>.
+// a bytewise path.  (The mate-name check of PairedEndRenamer / dnaio's paired reader is k_tail's, tail.cu.)  The
+// reverse-complementing single-end sink stays with k_emit<16>.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -154,26 +154,6 @@ __device__ __forceinline__ void copy_s2s(uint8_t* sm, uint32_t s, uint32_t d, ui
 // measured and dropped: the rotation differs from lane to lane, so its four loop variants run one after the other
 // inside a warp; 0.745 ms against 0.645 ms per step, profiles/r01_emit_variants.md.)
 
-// are the n bytes at shared offsets x and y different?
-__device__ __forceinline__ bool differ_s(const uint8_t* sm, uint32_t x, uint32_t y, uint32_t n) {
-    if (n == 0) return false;
-    const uint32_t xs = (x & 3u) * 8u, ys = (y & 3u) * 8u;
-    uint32_t xa = x & ~3u, ya = y & ~3u;
-    uint32_t x0 = lds32(sm, xa), y0 = lds32(sm, ya);
-    uint32_t diff = 0;
-    for (uint32_t i = 0; i < n; i += 4) {
-        xa += 4;
-        ya += 4;
-        const uint32_t x1 = lds32(sm, xa), y1 = lds32(sm, ya);
-        const uint32_t rem = n - i;
-        const uint32_t mask = rem >= 4 ? 0xFFFFFFFFu : ((1u << (8u * rem)) - 1u);
-        diff |= (__funnelshift_r(x0, x1, xs) ^ __funnelshift_r(y0, y1, ys)) & mask;
-        x0 = x1;
-        y0 = y1;
-    }
-    return diff != 0;
-}
-
 // PAIRED: two mates per pair; ONE_POOL: text batch (header, bases and qualities of a mate in one buffer)
 template <bool PAIRED, bool ONE_POOL>
 __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_constant__ EmitParams E) {
@@ -267,7 +247,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
     constexpr int ppass = PAIRED ? 8 : 16;
     const int my_mt = paired ? (q & 1) : 0;
     const int my_pp = paired ? (q >> 1) : q;  // pair of the pass this lane works on
-    bool id_mismatch = false;
     uint32_t bar_phase = 0;
     bool draining = false;  // a bulk store of this warp may still be reading the output image
 
@@ -401,8 +380,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
     auto bytewise = [&](int p0) {
         const int sl = p0 & 31;
         const int fd = __shfl_sync(FULL, dest, sl);
-        const uint8_t* idp[2] = {nullptr, nullptr};
-        uint32_t idn[2] = {0, 0};
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
             if (mt >= n_mates) continue;
@@ -430,12 +407,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                 else c = '\n';
                 out[p] = c;
             }
-            idp[mt] = nm;
-            idn[mt] = fid;
-        }
-        if (P.check_ids) {
-            id_mismatch |= idn[0] != idn[1];
-            for (uint32_t x = lane; x < min(idn[0], idn[1]); x += 32) id_mismatch |= idp[0][x] != idp[1][x];
         }
     };
 
@@ -504,10 +475,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
                 sm[d_qual + seq_len] = '\n';
             }
         }
-        if (P.check_ids) {  // PairedEndRenamer: the ids of the two mates must be identical (mate 1 sits two lanes below)
-            const uint32_t o_id = __shfl_sync(FULL, s_id, (lane - 2) & 31), o_len = __shfl_sync(FULL, id_len, (lane - 2) & 31);
-            if (valid && role == 0 && my_mt == 1) id_mismatch |= o_len != id_len || differ_s(sm, s_id, o_id, id_len);
-        }
         fence_async_smem();  // the image was written through the generic proxy, the bulk copies read it through the async proxy
         __syncwarp();
 
@@ -546,7 +513,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK, 2) k_emit_stage(const __grid_c
         __syncwarp();
     }
     if (draining && lane == 0) bulk_wait_read();  // shared memory must outlive the reads of the last bulk stores
-    if (__any_sync(FULL, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
 }
 
 template <bool PAIRED, bool ONE_POOL>

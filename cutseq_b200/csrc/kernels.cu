@@ -1,13 +1,12 @@
 // sm_100a kernels of the trimming chain.
 //
-//   k_align<M,H>   exact adapter alignment, one thread per read, whole DP column in registers; H = 2 / 4: homopolymer
-//                  adapters with that many columns side by side (dp_homo)
-//   k_align_split  homopolymer adapters with every DP column over two lanes (default for the poly-A / poly-T 100-mers)
-//   k_finish       trailing cuts, quality trimming, header suffix stripping + id parsing, '@' / '+' checks of text batches
-//   k_pair         TooShort / IsUntrimmedAny decision, record sizes, per-CTA stream totals
+//   k_align<M>     exact adapter alignment, one thread per read, whole DP column in registers
+//   k_align_split  the poly-A / poly-T 100-mers: KC DP columns side by side, every column over two lanes
 //   k_scan         exclusive scan of the per-CTA totals (6 output streams, one sweep)
-//   k_emit<G>      order-preserving FASTQ text emission straight from and to global memory, G lanes per record
-//                  (A/B variant and the reverse-complementing sink; the default emitter is k_emit_stage, emit_stage.cu)
+//   k_emit<16>     order-preserving FASTQ text emission straight from and to global memory, 16 lanes per record:
+//                  the reverse-complementing single-end sink and the A/B partner (CSQ_PLAN_EMIT_G16) of the default
+//                  emitter k_emit_stage (emit_stage.cu)
+// (k_tail - trailing ops, quality trimming, header, name check, filters - lives in tail.cu)
 //   k_int_peak     integer-issue microbenchmark (roofline denominator of the DP)
 //
 // Semantics follow cutadapt 5.x as restated in oracle/cutseq_oracle.c (Aligner.locate of
@@ -36,7 +35,7 @@
 namespace {
 
 #ifndef CSQ_HOMO_COLUMNS
-#define CSQ_HOMO_COLUMNS 4  // DP columns a thread computes side by side for homopolymer adapters (dp_homo)
+#define CSQ_HOMO_COLUMNS 4  // DP columns a lane pair computes side by side for homopolymer adapters (k_align_split)
 #endif
 
 constexpr int SP_SHIFT = 10, PRIO_SHIFT = 20, COST_SHIFT = 22;
@@ -139,7 +138,7 @@ __device__ __forceinline__ void best_to_match(const Best& best, int m, int n, bo
 }
 
 // Exact DP for a compile-time adapter length M: the column lives in registers W[0..M].
-template <int M, int HOMO>
+template <int M>
 __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P,
                                          const uint32_t* __restrict__ lut, int j0, csq_match& r) {
     constexpr int NW = (M + 31) / 32;
@@ -169,39 +168,18 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
     const int step = P.reversed ? -1 : 1;
     const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
 
-    // Homopolymer adapter and no free read start: every read character that differs from the adapter base
-    // adds at least 1 to EVERY cell of its column and of all later ones; once more than k such characters
-    // have been seen no cell can be accepted any more (acceptance needs cost <= k), so the scan may stop.
-    int foreign = 0;
     bool cut_short = false;
     for (int j = min_n + 1; j <= max_n; j++, p += step) {
         const uint32_t c = *p;
         uint32_t pm[NW];
-        uint32_t dcol = 0;
-        if constexpr (HOMO) {
-            const bool eq = (c & 0xDFu) == (uint32_t)P.letter;
-            dcol = eq ? D_MATCH : D_MIS;
-            if (!siq) {
-                foreign += eq ? 0 : 1;
-                if (foreign > k) {
-                    cut_short = true;
-                    break;
-                }
-            }
-        } else {
 #pragma unroll
-            for (int w = 0; w < NW; w++) pm[w] = lut[c * NW + w];
-        }
+        for (int w = 0; w < NW; w++) pm[w] = lut[c * NW + w];
         uint32_t wd = W[0];
         W[0] += row0_delta;
 #pragma unroll
         for (int i = 1; i <= M; i++) {
             const uint32_t wl = W[i];
-            uint32_t dd;
-            if constexpr (HOMO)
-                dd = dcol;
-            else
-                dd = (pm[(i - 1) >> 5] & (1u << ((i - 1) & 31))) ? D_MATCH : D_MIS;
+            const uint32_t dd = (pm[(i - 1) >> 5] & (1u << ((i - 1) & 31))) ? D_MATCH : D_MIS;
             const uint32_t cd = wd + dd;
             const uint32_t cu = W[i - 1] + D_INS;
             const uint32_t cl = wl + D_DEL;
@@ -211,131 +189,6 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
         if (eiq && row_m_update(W[M], j, M, n, P, best) && P.exact_stop) {
             cut_short = true;  // the last-column rule cannot change an error-free full match either
             break;
-        }
-    }
-    if (max_n == n && !cut_short) {
-        const int first_i = eir ? 0 : M;
-#pragma unroll
-        for (int i = M; i >= 0; i--)
-            if (i >= first_i) last_col_update(W[i], i, n, P, best);
-    }
-    best_to_match(best, M, n, P.reversed != 0, r);
-}
-
-// Homopolymer adapter (the poly-A / poly-T 100-mers of run.py:389-404): every row compares against the same
-// base, so a column needs one match/mismatch delta and no match mask.  A thread walks a column top to bottom,
-// each cell waiting for the one above it: a dependent chain of 3 instructions x M cells that a register-bound
-// kernel (M + 1 live cells, 2 CTAs per SM) cannot hide.  KC columns are therefore computed side by side, column
-// j + c running c rows behind column j (a skewed wavefront inside the thread): KC independent chains, the same
-// cells, the same order of the row-m / last-column rules.  Chain c keeps its two newest cells (p1, p2); cell
-// (r, j + c) = min3(p2[c-1] + delta_c, p1[c] + INS, p1[c-1] + DEL), chain -1 being the stored column j - 1.
-// Everything else (init, early stop after k + 1 foreign characters, best-match rules) is dp_exact's.
-template <int M, int KC>
-__device__ __forceinline__ void dp_homo(const uint8_t* __restrict__ s, int a, int b, const AlignParams& P, int j0,
-                                        csq_match& r) {
-    const int n = b - a;
-    const int k = P.k;
-    const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
-    int max_n = n, min_n = 0;
-    if (!siq) max_n = min(n, M + k);
-    if (!eiq) min_n = max(0, n - M - k);
-    if (j0 >= 0) min_n = max(min_n, j0);  // column window, see dp_exact
-    uint32_t W[M + 1];
-#pragma unroll
-    for (int i = 0; i <= M; i++) {
-        int cost, origin;
-        init_cell(i, min_n, sir, siq, cost, origin);
-        W[i] = pack_cell(cost, origin);
-    }
-    Best best = {M + n + 1, 0, 0, M, n};
-    const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
-    const int step = P.reversed ? -1 : 1;
-    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
-    const uint32_t letter = P.letter;
-    int foreign = 0;
-    bool cut_short = false;
-    int j = min_n + 1;
-    while (j <= max_n) {
-        // a block of KC columns, unless the read or the early stop ends inside it
-        bool block = j + KC - 1 <= max_n;
-        uint32_t d[KC];
-        int f = foreign;
-        if (block) {
-#pragma unroll
-            for (int c = 0; c < KC; c++) {
-                const bool eq = ((uint32_t)p[c * step] & 0xDFu) == letter;
-                d[c] = eq ? D_MATCH : D_MIS;
-                f += eq ? 0 : 1;
-            }
-            if (!siq && f > k) block = false;  // the scan stops inside the block: column by column from here
-        }
-        if (block) {
-            foreign = f;
-            uint32_t p1[KC], p2[KC], wm[KC];
-            uint32_t wd = W[0];  // stored column j - 1, one row up
-#pragma unroll
-            for (int c = 0; c < KC; c++) {
-                p1[c] = p2[c] = W[0] + (uint32_t)(c + 1) * row0_delta;  // row 0 of column j + c
-                wm[c] = 0;
-            }
-            W[0] = p1[KC - 1];
-#pragma unroll
-            for (int i = 1; i <= M + KC - 1; i++) {
-#pragma unroll
-                for (int c = KC - 1; c >= 0; c--) {  // descending: chain c - 1 still holds the previous step's cells
-                    const int row = i - c;
-                    if (row < 1 || row > M) continue;
-                    uint32_t diag, left;
-                    if (c == 0) {
-                        left = W[row];  // stored column j - 1
-                        diag = wd;
-                        wd = left;
-                    } else {
-                        left = p1[c - 1];
-                        diag = p2[c - 1];
-                    }
-                    const uint32_t cell = __vimin3_u32(diag + d[c], p1[c] + D_INS, left + D_DEL) & PRIO_CLEAR;
-                    p2[c] = p1[c];
-                    p1[c] = cell;
-                    if (c == KC - 1) W[row] = cell;
-                    if (row == M) wm[c] = cell;
-                }
-            }
-            if (eiq) {
-                bool stop = false;
-#pragma unroll
-                for (int c = 0; c < KC; c++) stop |= row_m_update(wm[c], j + c, M, n, P, best);
-                if (stop && P.exact_stop) {
-                    cut_short = true;
-                    break;
-                }
-            }
-            j += KC;
-            p += KC * step;
-        } else {
-            const bool eq = ((uint32_t)*p & 0xDFu) == letter;
-            if (!siq) {
-                foreign += eq ? 0 : 1;
-                if (foreign > k) {  // no cell of this or any later column can be accepted (see dp_exact)
-                    cut_short = true;
-                    break;
-                }
-            }
-            const uint32_t d0 = eq ? D_MATCH : D_MIS;
-            uint32_t wd = W[0];
-            W[0] += row0_delta;
-#pragma unroll
-            for (int i = 1; i <= M; i++) {
-                const uint32_t wl = W[i];
-                W[i] = __vimin3_u32(wd + d0, W[i - 1] + D_INS, wl + D_DEL) & PRIO_CLEAR;
-                wd = wl;
-            }
-            if (eiq && row_m_update(W[M], j, M, n, P, best) && P.exact_stop) {
-                cut_short = true;
-                break;
-            }
-            j += 1;
-            p += step;
         }
     }
     if (max_n == n && !cut_short) {
@@ -394,12 +247,11 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
     best_to_match(best, m, n, P.reversed != 0, r);
 }
 
-// HOMO: 0 = any adapter, 1 = homopolymer adapter, one column at a time (CSQ_PLAN_HOMO_V1, A/B runs),
-// 2, 4 = homopolymer adapter, that many columns side by side (dp_homo)
-template <int M, int HOMO>
+// M > 0: column in registers (dp_exact<M>); M == 0: any m <= CSQ_MAX_ADAPTER with the column in local memory
+template <int M>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
-    __shared__ uint32_t lut[(HOMO || M == 0) ? 1 : 256 * NW];
+    __shared__ uint32_t lut[M == 0 ? 1 : 256 * NW];
     // With survivor lists: CTA c works on 128 consecutive entries of one list, the lists (longest DP first) laid
     // end to end in units of CTAs; the grid is sized for the worst case, surplus CTAs leave at once.
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, count = P.n;
@@ -419,7 +271,7 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
     } else if (blockIdx.x * blockDim.x >= count) {
         return;
     }
-    if constexpr (!HOMO && M > 0) {
+    if constexpr (M > 0) {
         for (int c = threadIdx.x; c < 256; c += blockDim.x) {
             const int u = c & 0xDF;
             const int li = u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : -1;
@@ -456,10 +308,8 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
             atomicAdd(dst, (unsigned long long)mine);
         }
     }
-    if constexpr (HOMO >= 2)
-        dp_homo<M, HOMO>(s, st.a, st.b, P, j0, r);
-    else if constexpr (M > 0)
-        dp_exact<M, HOMO>(s, st.a, st.b, P, lut, j0, r);
+    if constexpr (M > 0)
+        dp_exact<M>(s, st.a, st.b, P, lut, j0, r);
     else
         dp_generic(s, st.a, st.b, P, j0, r);
     if (r.found) {
@@ -472,248 +322,6 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
     }
     if (P.matches) P.matches[idx] = r;
     store_state(P.md.state + idx, st);
-}
-
-// bit i set <=> byte i of the 16 is one of Python's str.split() blanks: ' ', 9..13, 28..31
-__device__ __forceinline__ uint32_t space_bits16(uint4 v) {
-    auto nib = [](uint32_t w) {
-        const uint32_t m = __vcmpeq4(w, 0x20202020u) | (__vcmpgeu4(w, 0x09090909u) & __vcmpleu4(w, 0x0D0D0D0Du)) |
-                           (__vcmpgeu4(w, 0x1C1C1C1Cu) & __vcmpleu4(w, 0x1F1F1F1Fu));
-        return (((m & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
-    };
-    return nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
-}
-
-// Trailing scalar ops, QualityTrimmer (quality_trim_index of qualtrim.pyx), SuffixRemover on the
-// header and Renamer.parse_name's id.
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ FinishParams P) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long qsum = 0, bpsum = 0;
-    if (idx < P.n) {
-        const uint32_t len0 = P.md.seq_len[idx];
-        ReadState st = P.first ? fresh_state(len0) : load_state(P.md.state + idx);
-        for (int q = 0; q < P.n_post; q++) apply_scalar(P.post[q], st);
-        // header fetches are issued before the quality scan so that both latencies overlap
-        const uint8_t* nm = P.md.name + P.md.name_off[idx];
-        int nl = (int)(P.md.name_end[idx] - P.md.name_off[idx]);
-        const uint4 nm0 = fetch16(nm);
-        if (P.perr) {
-            // text batch: the header line must start with '@' (the byte in front of the name) and the line behind the
-            // bases with '+'; both bytes sit in sectors this thread fetches anyway.  Records at or behind an error
-            // that is already known are skipped (the host reports the smallest key).
-            const unsigned long long known = *reinterpret_cast<volatile unsigned long long*>(P.perr);
-            if ((known >> 3) > (unsigned long long)idx) {
-                const uint8_t* se = P.md.seq + P.md.seq_off[idx] + len0;  // the line end behind the bases
-                int bad = 0;
-                if (nm[-1] != '@') bad = 1;                                // PERR_AT
-                else if (se[se[0] == '\r' ? 2 : 1] != '+') bad = 2;        // PERR_PLUS
-                if (bad) atomicMin(P.perr, ((unsigned long long)idx << 3) | (unsigned long long)bad);
-            }
-        }
-        if (P.has_qtrim) {
-            // quality_trim_index (qualtrim.pyx): running sums from either end, stop at the first negative sum.
-            // Nearly every read stops within a few bases: the 16 qualities at either end are fetched at once
-            // (two fetch16, issued together), the rare longer scans continue bytewise.
-            const uint8_t* ql = P.md.qual + P.md.qual_off[idx];
-            const int a = st.a, n = (int)st.b - (int)st.a;
-            int start = 0, stop = n;
-            if (n > 0) {
-                const uint4 vf = fetch16(ql + a), vb = fetch16(ql + a + n - 16);
-                const uint32_t wf[4] = {vf.x, vf.y, vf.z, vf.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-                int s = 0, mx = 0, i = 0;
-                bool open = true;
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    if (open && j < n) {
-                        s += P.cutoff_front - ((int)((wf[j >> 2] >> (8 * (j & 3))) & 0xFFu) - P.qbase);
-                        if (s < 0) {
-                            open = false;
-                        } else {
-                            if (s > mx) {
-                                mx = s;
-                                start = j + 1;
-                            }
-                            i = j + 1;
-                        }
-                    }
-                }
-                for (; open && i < n; i++) {
-                    s += P.cutoff_front - ((int)ql[a + i] - P.qbase);
-                    if (s < 0) break;
-                    if (s > mx) {
-                        mx = s;
-                        start = i + 1;
-                    }
-                }
-                s = 0;
-                mx = 0;
-                open = true;
-                i = n - 1;
-#pragma unroll
-                for (int j = 15; j >= 0; j--) {  // byte j of vb is quality n - 16 + j
-                    if (open && n - 16 + j >= 0) {
-                        s += P.cutoff_back - ((int)((wb[j >> 2] >> (8 * (j & 3))) & 0xFFu) - P.qbase);
-                        if (s < 0) {
-                            open = false;
-                        } else {
-                            if (s > mx) {
-                                mx = s;
-                                stop = n - 16 + j;
-                            }
-                            i = n - 17 + j;
-                        }
-                    }
-                }
-                for (; open && i >= 0; i--) {
-                    s += P.cutoff_back - ((int)ql[a + i] - P.qbase);
-                    if (s < 0) break;
-                    if (s > mx) {
-                        mx = s;
-                        stop = i;
-                    }
-                }
-            }
-            if (start >= stop) start = stop = 0;
-            st.qtrim = (uint32_t)(n - (stop - start));
-            st.b = (uint16_t)(st.a + stop);
-            st.a = (uint16_t)(st.a + start);
-            qsum = st.qtrim;
-        }
-        // header: SuffixRemover ops in order, then the id of Renamer.parse_name
-        for (int q = 0; q < P.n_suffix; q++) {
-            const int sl = P.suffix_len[q];
-            if (nl >= sl) {
-                bool eq = true;
-                for (int x = 0; x < sl; x++) eq = eq && (nm[nl - sl + x] == (uint8_t)P.suffix[q][x]);
-                if (eq) nl -= sl;
-            }
-        }
-        // str.split(maxsplit=1): s0 = first non-blank, e0 = first blank behind it, p = first non-blank behind that;
-        // 16 header bytes per step, Python's whitespace set found with per-byte SIMD compares
-        int s0 = nl, e0 = nl, p = nl, state = 0;
-        for (int c = 0; c < nl && state < 3; c += 16) {
-            const uint4 v = c == 0 ? nm0 : fetch16(nm + c);
-            const uint32_t blank = space_bits16(v);
-            const uint32_t valid = nl - c >= 16 ? 0xFFFFu : ((1u << (nl - c)) - 1u);
-            uint32_t from = 0xFFFFu;  // positions still to look at in this chunk
-            if (state == 0) {
-                const uint32_t t = ~blank & valid & from;
-                if (t) {
-                    const int b = __ffs(t) - 1;
-                    s0 = c + b;
-                    from = 0xFFFEu << b;
-                    state = 1;
-                }
-            }
-            if (state == 1) {
-                const uint32_t t = blank & valid & from;
-                if (t) {
-                    const int b = __ffs(t) - 1;
-                    e0 = c + b;
-                    from = 0xFFFEu << b;
-                    state = 2;
-                }
-            }
-            if (state == 2) {
-                const uint32_t t = ~blank & valid & from;
-                if (t) {
-                    p = c + (__ffs(t) - 1);
-                    state = 3;
-                }
-            }
-        }
-        if (P.has_rename && e0 > s0 && p < nl) {
-            st.id_start = (uint16_t)s0;
-            st.id_end = (uint16_t)e0;
-        } else {
-            st.id_start = 0;
-            st.id_end = (uint16_t)min(nl, 65535);
-        }
-        store_state(P.md.state + idx, st);
-        bpsum = len0;
-    }
-    // block-level reduction of the two statistics
-    __shared__ unsigned long long sh[2];
-    if (threadIdx.x == 0) sh[0] = sh[1] = 0;
-    __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) {
-        qsum += __shfl_down_sync(0xffffffffu, qsum, o);
-        bpsum += __shfl_down_sync(0xffffffffu, bpsum, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sh[0], qsum);
-        atomicAdd(&sh[1], bpsum);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (sh[0]) atomicAdd(P.counters + CNT_QTRIM_BP + P.mate, sh[0]);
-        if (sh[1]) atomicAdd(P.counters + CNT_TOTAL_BP + P.mate, sh[1]);
-    }
-}
-
-// Filters + sink of run.py:446-471 / 763-792 and the byte size of every record.
-// Thread per pair; the per-CTA stream totals are warp-reduced (REDUX) before they touch shared memory.
-__global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_pair(const __grid_constant__ PairParams P) {
-    __shared__ unsigned int tot[8];   // bytes per (dest, mate) stream
-    __shared__ unsigned int cnt[4];   // records per dest
-    __shared__ unsigned int bp[2];    // bases written to the trimmed files, per mate
-    if (threadIdx.x < 8) tot[threadIdx.x] = 0;
-    if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
-    if (threadIdx.x < 2) bp[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t idx = blockIdx.x * CSQ_PAIR_BLOCK + threadIdx.x;
-    const bool paired = P.n_mates == 2;
-    int dest = -1;
-    uint32_t len1 = 0, len2 = 0, l1 = 0, l2 = 0;
-    if (idx < P.n) {
-        const ReadState s1 = load_state(P.md[0].state + idx);
-        const ReadState s2 = paired ? load_state(P.md[1].state + idx) : s1;
-        l1 = (uint32_t)s1.b - (uint32_t)s1.a;
-        l2 = (uint32_t)s2.b - (uint32_t)s2.a;
-        if ((int)l1 < P.min_length || (paired && (int)l2 < P.min_length))
-            dest = CSQ_DEST_SHORT;
-        else if (P.untrimmed_enabled && ((P.required[0] & ~s1.matched) != 0 || (paired && (P.required[1] & ~s2.matched) != 0)))
-            dest = CSQ_DEST_UNTRIMMED;
-        else
-            dest = CSQ_DEST_TRIMMED;
-        P.dest[idx] = (uint8_t)dest;
-        len1 = record_shape(P, s1, s1, s2).total;
-        if (paired) len2 = record_shape(P, s2, s1, s2).total;
-    }
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 0; d < CSQ_N_DEST; d++) {
-        const bool mine = dest == d;
-        const unsigned int c = __popc(__ballot_sync(0xffffffffu, mine));
-        if (c == 0) continue;  // warp-uniform
-        const unsigned int t1 = __reduce_add_sync(0xffffffffu, mine ? len1 : 0u);
-        const unsigned int t2 = __reduce_add_sync(0xffffffffu, mine ? len2 : 0u);
-        unsigned int b1 = 0, b2 = 0;
-        if (d == CSQ_DEST_TRIMMED) {
-            b1 = __reduce_add_sync(0xffffffffu, mine ? l1 : 0u);
-            b2 = __reduce_add_sync(0xffffffffu, (mine && paired) ? l2 : 0u);
-        }
-        if (lane == 0) {
-            atomicAdd(&tot[d * 2 + 0], t1);
-            if (paired) atomicAdd(&tot[d * 2 + 1], t2);
-            atomicAdd(&cnt[d], c);
-            if (d == CSQ_DEST_TRIMMED) {
-                atomicAdd(&bp[0], b1);
-                atomicAdd(&bp[1], b2);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) P.block_tot[blockIdx.x * 8 + threadIdx.x] = tot[threadIdx.x];
-    if (threadIdx.x < 4) P.block_cnt[blockIdx.x * 4 + threadIdx.x] = cnt[threadIdx.x];
-    if (threadIdx.x == 0) {
-        atomicAdd(P.counters + CNT_N, (unsigned long long)min((uint32_t)CSQ_PAIR_BLOCK, P.n - blockIdx.x * CSQ_PAIR_BLOCK));
-        if (cnt[CSQ_DEST_TRIMMED]) atomicAdd(P.counters + CNT_WRITTEN, (unsigned long long)cnt[CSQ_DEST_TRIMMED]);
-        if (bp[0]) atomicAdd(P.counters + CNT_WRITTEN_BP, (unsigned long long)bp[0]);
-        if (bp[1]) atomicAdd(P.counters + CNT_WRITTEN_BP + 1, (unsigned long long)bp[1]);
-        if (cnt[CSQ_DEST_SHORT]) atomicAdd(P.counters + CNT_TOO_SHORT, (unsigned long long)cnt[CSQ_DEST_SHORT]);
-        if (cnt[CSQ_DEST_UNTRIMMED]) atomicAdd(P.counters + CNT_UNTRIMMED, (unsigned long long)cnt[CSQ_DEST_UNTRIMMED]);
-    }
 }
 
 // Exclusive scan over CTAs of the 8 stream totals (6 used) -> byte offset of every CTA in every
@@ -931,10 +539,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
     constexpr int UI = 64 / G > 4 ? 4 : (G == 32 ? 2 : 2);  // unrolled id iterations: UI * G bytes
     constexpr int MR = (23 + G - 1) / G;    // rounds over the 16 edge slots + 7 separators
     const uint32_t sl = (uint32_t)lane % G, grp = (uint32_t)lane / G;
-    bool id_mismatch = false;
-    uint32_t id0_len = 0, id0_v[UI];        // id of mate 1 of the current pair, as held by this lane
-#pragma unroll
-    for (int u = 0; u < UI; u++) id0_v[u] = 0;
     for (int q = 0; q < 32 / NG; q++) {
         const int slot = wid * 32 + q * NG + (int)grp;
         if (base + slot >= P.n) continue;  // no warp-wide operation below: groups may leave independently
@@ -1025,19 +629,6 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
                 if (k < nw_s) { ws[u][0] = al_s[k]; ws[u][1] = al_s[k + 1]; }
                 if (k < nw_q) { wq[u][0] = al_q[k]; wq[u][1] = al_q[k + 1]; }
             }
-            if (P.check_ids) {  // PairedEndRenamer: the ids of the two mates must be identical
-                if (mt == 0) {
-                    id0_len = id_len;
-#pragma unroll
-                    for (int u = 0; u < UI; u++) id0_v[u] = idv[u];
-                } else {
-                    id_mismatch |= id0_len != id_len;
-#pragma unroll
-                    for (int u = 0; u < UI; u++) id_mismatch |= id0_v[u] != idv[u];
-                    const uint8_t* __restrict__ n0 = P.md[0].name + recs[0][slot].nm;
-                    for (uint32_t x = UI * G + sl; x < id_len; x += G) id_mismatch |= n0[x] != nm[x];
-                }
-            }
             // ---- stores ----
 #pragma unroll
             for (int r = 0; r < MR; r++)
@@ -1061,18 +652,25 @@ __global__ void __launch_bounds__(CSQ_PAIR_BLOCK) k_emit(const __grid_constant__
             }
         }
     }
-    if (__any_sync(0xffffffffu, id_mismatch) && lane == 0) atomicExch(P.error_flag, (int)CSQ_ERR_PAIRING);
 }
 
-// k_align_split<M, KC>: the homopolymer DP of dp_homo with every column split over TWO lanes - lane 2q holds rows
+// k_align_split<M, KC>: homopolymer adapter (the poly-A / poly-T 100-mers of run.py:389-404, 674-707).  Every row
+// compares against the same base, so a column needs one match / mismatch delta and no match mask; a thread that walks
+// a column top to bottom is ONE dependent chain of 3 instructions per cell, so KC columns are computed side by side,
+// column j + c running c rows behind column j (a skewed wavefront inside the thread: KC independent chains, the same
+// cells, the same order of the row-m / last-column rules; chain c keeps its two newest cells p1, p2 and
+// cell (r, j + c) = min3(p2[c-1] + delta_c, p1[c] + INS, p1[c-1] + DEL), chain -1 being the stored column j - 1).
+// Without a free read start the scan stops once more than k characters differ from the adapter base: each of them
+// adds at least 1 to every cell of its column and of all later ones, and acceptance needs cost <= k.
+// On top of that every column is split over TWO lanes - lane 2q holds rows
 // 0..M/2 of entry q, lane 2q+1 rows M/2..M (its row "0" is a copy of row M/2) - so that a thread keeps M/2 + 1 cells
-// instead of M + 1: half the registers (k_align<100> needs 228-231 and fits 8 warps per SM), twice the warps, half
-// the serial chain per thread.  The lower half runs ONE column group behind the upper half: what it needs from
+// instead of M + 1: half the registers (a whole-column k_align<100> needed 228-231 and fitted 8 warps per SM), twice
+// the warps, half the serial chain per thread (one-lane and one-column forms: measured, profiles/r01_homo_columns.md).  The lower half runs ONE column group behind the upper half: what it needs from
 // above - row M/2 of the group's columns - arrives by one shuffle per column at the end of the upper half's turn;
 // both lanes take the same decisions (group sizes, early stop after k + 1 foreign characters) from the same
 // read characters, one iteration apart.  Row-m rule and exact stop live in the lower lane (it tells the upper
 // lane to halt); the last-column rule walks rows M..M/2+1 below, hands `best` up, and rows M/2..0 follow there.
-// Cells, order of the rules and results are those of dp_homo / dp_exact.
+// Cells, order of the rules and results are those of dp_exact.
 template <int M, int KC>
 __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ AlignParams P) {
     static_assert(M % 2 == 0, "even adapter length");
@@ -1311,7 +909,10 @@ template <int M>
 cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t stream) {
     const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
     if constexpr (M == 100) {  // the poly-A / poly-T adapters of run.py:389-404
-        if (p.homopolymer == 3) {  // every column over two lanes (k_align_split)
+        if (p.homopolymer) {
+            // measured (profiles/r01_homo_columns.md): four columns side by side win where the early stop ends most
+            // scans after ~20 columns (read start not free: NonInternalFront), two where every read walks all m + k
+            // columns; one kernel per variant (both bodies in one kernel cost 15 %)
             const dim3 grid2((n_items + 63) / 64 + (p.list ? CSQ_PF_BINS : 0));
             if (p.flags & 2)
                 k_align_split<M, 2><<<grid2, block, 0, stream>>>(p);
@@ -1319,22 +920,8 @@ cudaError_t launch_align_m(const AlignParams& p, uint32_t n_items, cudaStream_t 
                 k_align_split<M, CSQ_HOMO_COLUMNS><<<grid2, block, 0, stream>>>(p);
             return cudaGetLastError();
         }
-        if (p.homopolymer == 2) {
-            // measured (profiles/r01_homo_columns.md): four columns side by side win where the early stop ends most
-            // scans after ~20 columns (read start not free: NonInternalFront), two where every read walks all m + k
-            // columns; one kernel per variant (both bodies in one kernel cost 15 %)
-            if (p.flags & 2)
-                k_align<M, 2><<<grid, block, 0, stream>>>(p);
-            else
-                k_align<M, CSQ_HOMO_COLUMNS><<<grid, block, 0, stream>>>(p);
-            return cudaGetLastError();
-        }
-        if (p.homopolymer) {
-            k_align<M, 1><<<grid, block, 0, stream>>>(p);
-            return cudaGetLastError();
-        }
     }
-    k_align<M, 0><<<grid, block, 0, stream>>>(p);
+    k_align<M><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -1355,22 +942,10 @@ cudaError_t csq_launch_align(const AlignParams& p, uint32_t n_items, cudaStream_
 #undef CSQ_CASE
         default: {
             const dim3 grid((n_items + 127) / 128 + (p.list ? CSQ_PF_BINS : 0)), block(128);
-            k_align<0, 0><<<grid, block, 0, stream>>>(p);
+            k_align<0><<<grid, block, 0, stream>>>(p);
             return cudaGetLastError();
         }
     }
-}
-
-cudaError_t csq_launch_finish(const FinishParams& p, cudaStream_t stream) {
-    if (p.n == 0) return cudaSuccess;
-    k_finish<<<(p.n + 255) / 256, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-cudaError_t csq_launch_pair(const PairParams& p, cudaStream_t stream) {
-    if (p.n == 0) return cudaSuccess;
-    k_pair<<<(p.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK, CSQ_PAIR_BLOCK, 0, stream>>>(p);
-    return cudaGetLastError();
 }
 
 cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint32_t* block_cnt,
@@ -1382,12 +957,8 @@ cudaError_t csq_launch_scan(uint32_t nblk, const uint32_t* block_tot, const uint
 cudaError_t csq_launch_emit(const EmitParams& p, int lanes_per_record, cudaStream_t stream) {
     if (p.pp.n == 0) return cudaSuccess;
     const dim3 grid((p.pp.n + CSQ_PAIR_BLOCK - 1) / CSQ_PAIR_BLOCK), block(CSQ_PAIR_BLOCK);
-    if (lanes_per_record == 32)
-        k_emit<32><<<grid, block, 0, stream>>>(p);
-    else if (lanes_per_record == 8)
-        k_emit<8><<<grid, block, 0, stream>>>(p);
-    else
-        k_emit<16><<<grid, block, 0, stream>>>(p);
+    (void)lanes_per_record;  // 32 and 8 lanes per record were measured slower (profiles/r01_emit_variants.md) and are gone
+    k_emit<16><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -66,7 +66,6 @@ __device__ __forceinline__ uint32_t nl_mask16(uint4 v, const ByteConsts& k) {
     const uint32_t n2 = (eq_marks(v.z, k.k0a, k) * M) >> 20, n3 = (eq_marks(v.w, k.k0a, k) * M) >> 16;
     return n0 | (n1 & 0xF0u) | (n2 & 0xF00u) | (n3 & 0xF000u);
 }
-__device__ __forceinline__ uint32_t nl_mask16(uint4 v) { return nl_mask16(v, byte_consts()); }
 
 // Pass 1: the text is read ONCE, fully coalesced (chunk c of the tile by thread c % 256); what survives is a
 // 16-bit line-end mask per chunk (1/8 of the text) and the number of line ends per tile.
@@ -248,200 +247,27 @@ __global__ void __launch_bounds__(256) k_records(const ParseParams P) {
 }
 
 
-// ---- one-pass form (CSQ_PLAN_PARSE_ONEPASS) -------------------------------------------------------------------------------
-// k_parse_onepass reads the text ONCE and writes the record index directly; nothing else is written or read
-// back (the four-kernel form above moves 1/8 of the text twice as masks, 16 bytes of line-end offsets per record
-// twice, and k_records looks at ~4 sectors of every record again).
-// Measured on B200 (1 M pairs, ncu, profiles/r01_ncu_onepass_stage.csv): 240 us against 187 us for the four
-// kernels - DRAM traffic is 357 MB instead of ~560 MB, but every tile is one latency chain (load -> masks ->
-// scan -> look-back -> walk, three barriers) and 8 resident CTAs x 16 KiB per SM cannot cover it (19 % of the
-// DRAM peak, top stall: barrier).  Kept behind the flag; the next form would be persistent CTAs that prefetch
-// tile i + 1 while tile i is in its look-back.
-//
-// A CTA takes the next 16 KiB tile (ticket counter, so tiles start in order), loads it fully coalesced, leaves the
-// line-end masks in shared memory, and learns what lies in front of its tile - the number of line ends and the
-// start of the line that is open at the tile boundary - by a decoupled look-back over per-tile status words
-// (Merrill & Garland 2016): status | line ends (30 bits, saturating) | last line end + 1 (32 bits), one 64-bit
-// word per tile, published first as the tile's own aggregate and then as the inclusive prefix.
-// Thread t then walks the line ends in its 64 bytes: line L = 4 rec + k ends at p and starts where the previous
-// line end left off (a prefix maximum over the CTA + the look-back value), so every line writes its own
-// fields of record rec without looking at any other line:
-//   k = 0: '@' check, name_off / name_end     k = 1: seq_off, seq_len
-//   k = 2: '+' check                          k = 3: qual_off, and the quality length into `qlen`
-// k_records_fix (thread per record, 8 bytes read) compares sequence and quality lengths, applies the
-// read-length limit and the line-count check, and empties bad records so that the chain stays in bounds.
-#define TS_AGG (1ull << 62)
-#define TS_PREFIX (2ull << 62)
-#define TS_SAT ((1u << 30) - 1u)
-
-__device__ __forceinline__ unsigned long long ts_pack(unsigned long long status, uint32_t count, uint32_t last1) {
-    return status | ((unsigned long long)min(count, TS_SAT) << 32) | (unsigned long long)last1;
-}
-
-__global__ void __launch_bounds__(TILE_THREADS) k_parse_onepass(const ParseParams P, uint32_t* __restrict__ qlen,
-                                                                unsigned long long* tile_state, uint32_t* ticket,
-                                                                uint32_t n_tiles) {
-    __shared__ __align__(8) uint16_t smask[TILE_CHUNKS];
-    __shared__ uint32_t wcnt[TILE_THREADS / 32], wlast[TILE_THREADS / 32];
-    __shared__ uint32_t s_tile, s_excl_cnt, s_excl_last;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t tile_off = (uint64_t)tile * TILE_BYTES;
-    const uint8_t* __restrict__ t = P.text;
-#pragma unroll
-    for (int i = 0; i < TILE_CHUNKS / TILE_THREADS; i++) {
-        const uint32_t chunk = i * TILE_THREADS + threadIdx.x;
-        const uint64_t off = tile_off + 16ull * chunk;
-        uint32_t m = 0;
-        if (off < P.bytes) m = nl_mask16(*reinterpret_cast<const uint4*>(t + off));
-        smask[chunk] = (uint16_t)m;
-    }
-    __syncthreads();
-    // thread t owns the 64 bytes at 64 t: four masks = one 64-bit word
-    unsigned long long m = reinterpret_cast<const unsigned long long*>(smask)[threadIdx.x];
-    const uint32_t base = (uint32_t)tile_off + 64u * threadIdx.x;
-    const uint32_t c = __popcll(m);
-    const uint32_t own_last1 = m ? base + (63u - (uint32_t)__clzll((long long)m)) + 1u : 0u;  // last line end + 1
-    uint32_t x = c, y = own_last1;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t xs = __shfl_up_sync(0xffffffffu, x, o), ys = __shfl_up_sync(0xffffffffu, y, o);
-        if (lane >= o) {
-            x += xs;
-            y = max(y, ys);
-        }
-    }
-    if (lane == 31) {
-        wcnt[wid] = x;
-        wlast[wid] = y;
-    }
-    uint32_t cnt_before = x - c;
-    uint32_t last_before = __shfl_up_sync(0xffffffffu, y, 1);
-    if (lane == 0) last_before = 0;
-    __syncthreads();
-    for (int w = 0; w < wid; w++) {
-        cnt_before += wcnt[w];
-        last_before = max(last_before, wlast[w]);
-    }
-    if (wid == 0) {
-        uint32_t tot = 0, tlast = 0;
-#pragma unroll
-        for (int w = 0; w < TILE_THREADS / 32; w++) {
-            tot += wcnt[w];
-            tlast = max(tlast, wlast[w]);
-        }
-        uint32_t ecnt = 0, elast = 0;
-        volatile unsigned long long* state = tile_state;
-        if (tile > 0) {
-            if (lane == 0) state[tile] = ts_pack(TS_AGG, tot, tlast);
-            int idx = (int)tile - 1 - lane;
-            for (;;) {
-                unsigned long long s;
-                do {
-                    s = idx >= 0 ? state[idx] : TS_PREFIX;
-                } while (__any_sync(0xffffffffu, (s >> 62) == 0));
-                const uint32_t pm = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-                const int first = pm ? __ffs((int)pm) - 1 : 32;  // the nearest tile that knows its inclusive prefix
-                const bool use = lane <= first;
-                const uint32_t scnt = use ? ((uint32_t)(s >> 32) & TS_SAT) : 0u, slast = use ? (uint32_t)s : 0u;
-                ecnt = min(ecnt + __reduce_add_sync(0xffffffffu, scnt), TS_SAT);
-                if (elast == 0) {  // the nearest line end in front of this tile
-                    const uint32_t nz = __ballot_sync(0xffffffffu, slast != 0);
-                    if (nz) elast = __shfl_sync(0xffffffffu, slast, __ffs((int)nz) - 1);
-                }
-                if (pm) break;
-                idx -= 32;
-            }
-        }
-        if (lane == 0) {
-            const uint32_t incl = min(ecnt + tot, TS_SAT);
-            state[tile] = ts_pack(TS_PREFIX, incl, tlast ? tlast : elast);
-            s_excl_cnt = ecnt;
-            s_excl_last = elast;
-            if (tile == n_tiles - 1) P.nl_total[0] = incl;
-        }
-    }
-    __syncthreads();
-    uint32_t L = s_excl_cnt + cnt_before;              // index of this thread's first line end
-    uint32_t start = max(s_excl_last, last_before);    // where the line it closes begins
-    while (m) {
-        const int bit = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const uint32_t p = base + (uint32_t)bit;
-        const uint32_t rec = L >> 2, k = L & 3u;
-        if (rec < P.n) {
-            uint32_t e = p;
-            if (e > start && t[e - 1] == '\r') e--;
-            if (k == 0) {
-                const bool ok = e > start && t[start] == '@';
-                if (!ok) report(P.perr, rec, PERR_AT);
-                P.name_off[rec] = ok ? start + 1 : start;
-                P.name_end[rec] = ok ? e : start;
-            } else if (k == 1) {
-                P.seq_off[rec] = start;
-                P.seq_len[rec] = e - start;
-            } else if (k == 2) {
-                if (e == start || t[start] != '+') report(P.perr, rec, PERR_PLUS);
-            } else {
-                P.qual_off[rec] = start;
-                qlen[rec] = e - start;
-            }
-        }
-        L++;
-        start = p + 1;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_records_fix(const ParseParams P, const uint32_t* __restrict__ qlen) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool count_ok = P.nl_total[0] == 4u * P.n;
-    if (i == 0 && !count_ok) report(P.perr, 0, PERR_COUNT);
-    if (i >= P.n) return;
-    if (!count_ok) {  // the index is not fully defined: every record becomes an empty one, the host rejects the batch
-        P.name_off[i] = P.name_end[i] = P.seq_off[i] = P.seq_len[i] = P.qual_off[i] = 0;
-        return;
-    }
-    const uint32_t slen = P.seq_len[i];
-    int bad = 0;
-    if (slen != qlen[i]) bad = PERR_LEN;
-    else if (slen > CSQ_MAX_READ_LEN) bad = PERR_LIMIT;
-    if (bad) {  // a bad record becomes an empty one: the rest of the chain stays in bounds
-        report(P.perr, i, bad);
-        P.name_end[i] = P.name_off[i];
-        P.seq_len[i] = 0;
-    }
-}
-
 }  // namespace
 
 uint32_t csq_parse_tiles(uint64_t bytes) { return (uint32_t)((bytes + TILE_BYTES - 1) / TILE_BYTES); }
 
-// v1 = the four-kernel form (default): `tiles` holds u32 tile counts, `masks` the line-end
-// masks, p.nl the line-end offsets.  One-pass form (CSQ_PLAN_PARSE_ONEPASS): `tiles` holds one u64 status word per tile (zeroed here), p.nl is
-// scratch for the quality lengths (n words), `ticket` one zeroed u32.
-cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* masks, uint32_t* ticket, bool v1, cudaStream_t stream) {
+// `tiles` holds u32 tile counts, `masks` the line-end masks, p.nl the line-end offsets.  (A one-pass form - decoupled
+// look-back over per-tile status words, the record index written by the thread that owns a line end - moved 357 MB
+// instead of ~560 MB per 1 M pairs but took 240 us against 187 us: one latency chain per 16 KiB tile.  Measured in
+// round 1, profiles/r01_ncu_onepass_stage_v1.csv, and removed.)
+cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* masks, cudaStream_t stream) {
     const uint32_t tiles = csq_parse_tiles(p.bytes);
-    if (v1) {
-        uint32_t* tile_cnt = (uint32_t*)tile_buf;
-        if (tiles) {
-            cudaError_t e = cudaMemsetAsync(p.any_cr, 0, 4, stream);
-            if (e != cudaSuccess) return e;
-            k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, masks, tile_cnt, p.any_cr);
-            k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_cnt, p.nl_total);
-            k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(masks, tile_cnt, p.nl, 4u * p.n);
-        } else {
-            cudaError_t e = cudaMemsetAsync(p.nl_total, 0, 4, stream);
-            if (e != cudaSuccess) return e;
-        }
-        k_records<<<(p.n + 255) / 256 + (p.n == 0 ? 1 : 0), 256, 0, stream>>>(p);
-        return cudaGetLastError();
+    uint32_t* tile_cnt = (uint32_t*)tile_buf;
+    if (tiles) {
+        cudaError_t e = cudaMemsetAsync(p.any_cr, 0, 4, stream);
+        if (e != cudaSuccess) return e;
+        k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, masks, tile_cnt, p.any_cr);
+        k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_cnt, p.nl_total);
+        k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(masks, tile_cnt, p.nl, 4u * p.n);
+    } else {
+        cudaError_t e = cudaMemsetAsync(p.nl_total, 0, 4, stream);
+        if (e != cudaSuccess) return e;
     }
-    cudaError_t e = cudaMemsetAsync(p.nl_total, 0, 4, stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ticket, 0, 4, stream);
-    if (e == cudaSuccess && tiles) e = cudaMemsetAsync(tile_buf, 0, (size_t)tiles * 8, stream);
-    if (e != cudaSuccess) return e;
-    if (tiles) k_parse_onepass<<<tiles, TILE_THREADS, 0, stream>>>(p, p.nl, (unsigned long long*)tile_buf, ticket, tiles);
-    k_records_fix<<<(p.n + 255) / 256 + (p.n == 0 ? 1 : 0), 256, 0, stream>>>(p, p.nl);
+    k_records<<<(p.n + 255) / 256 + (p.n == 0 ? 1 : 0), 256, 0, stream>>>(p);
     return cudaGetLastError();
 }

@@ -354,12 +354,8 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
         if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.name_off[m].ensure((size_t)n * 4 + 16))) return rc;
         if ((rc = s.name_end[m].ensure((size_t)n * 4 + 16))) return rc;
-        if (!(plan->flags & CSQ_PLAN_PARSE_ONEPASS)) {
-            if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
-            if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;  // 16 bits per 16-byte chunk
-        } else {
-            if ((rc = s.nl[m].ensure(((size_t)n + 8) * 4))) return rc;  // quality lengths (scratch of the one-pass parse)
-        }
+        if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
+        if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;  // 16 bits per 16-byte chunk
         if ((rc = s.tiles[m].ensure(((size_t)csq_parse_tiles(bytes) + 4) * 8))) return rc;
         if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
         if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
@@ -447,7 +443,7 @@ PairParams pair_params(csq_plan* plan, Slot& s) {
     return pp;
 }
 
-// One mate of a batch: parse (text batches), then prefilter / align per ALIGN op, then finish - all on `st`.
+// One mate of a batch: parse (text batches), then prefilter / align per ALIGN op - all on `st` (k_tail follows for both mates).
 int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t st) {
     const uint32_t n = s.n;
     if (s.text_mode) {
@@ -465,18 +461,14 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
         pp.name_end = (uint32_t*)s.name_end[m].p;
         pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
         pp.any_cr = (uint32_t*)((uint8_t*)s.parse_misc.p + 40) + m;
-        const bool v1 = !(plan->flags & CSQ_PLAN_PARSE_ONEPASS);
-        CUDA_TRY(csq_launch_parse(pp, s.tiles[m].p, (uint16_t*)s.masks[m].p, (uint32_t*)((uint8_t*)s.parse_misc.p + 32) + m, v1, st));
-        plan->launches += csq_parse_tiles(pp.bytes) ? (v1 ? 4 : 2) : 1;
+        CUDA_TRY(csq_launch_parse(pp, s.tiles[m].p, (uint16_t*)s.masks[m].p, st));
+        plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
         if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
     }
     MateProgram& mp = plan->prog[m];
     for (Segment& sg : mp.segs) {
         AlignParams ap = sg.ap;
         ap.exact_stop = (plan->flags & CSQ_PLAN_NO_EXACT_STOP) ? 0 : 1;
-        // homopolymer adapters: 1 = one column at a time, 2 = several columns side by side in one thread, 3 = every
-        // column over two lanes on top of that (default)
-        if (ap.homopolymer && !(plan->flags & CSQ_PLAN_HOMO_V1)) ap.homopolymer = (plan->flags & CSQ_PLAN_HOMO_ONE_LANE) ? 2 : 3;
         ap.md = mate_dev(s, m);
         ap.n = n;
         ap.list = nullptr;
@@ -502,14 +494,6 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
         plan->launches += n ? 1 : 0;
         if (kt) kt->mark(sg.name);
     }
-    FinishParams fp = mp.fin;
-    fp.md = mate_dev(s, m);
-    fp.n = n;
-    fp.counters = plan->counters;
-    fp.perr = s.text_mode ? (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m : nullptr;
-    CUDA_TRY(csq_launch_finish(fp, st));
-    plan->launches += n ? 1 : 0;
-    if (kt) kt->mark(m == 0 ? "k_finish.r1" : "k_finish.r2");
     return 0;
 }
 
@@ -538,9 +522,17 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st, cud
     if (s.text_mode)
         CUDA_TRY(cudaMemcpyAsync(s.totals_host + 14, (uint8_t*)s.parse_misc.p + 16, 16, cudaMemcpyDeviceToHost, st));
     PairParams pp = pair_params(plan, s);
-    CUDA_TRY(csq_launch_pair(pp, st));
+    FinishParams fp[2];
+    for (int m = 0; m < 2; m++) {
+        fp[m] = plan->prog[m < plan->n_mates ? m : 0].fin;
+        fp[m].md = mate_dev(s, m < plan->n_mates ? m : 0);
+        fp[m].n = n;
+        fp[m].counters = plan->counters;
+        fp[m].perr = s.text_mode ? (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m : nullptr;
+    }
+    CUDA_TRY(csq_launch_tail(fp[0], fp[1], pp, st));
     plan->launches += n ? 1 : 0;
-    if (kt) kt->mark("k_pair");
+    if (kt) kt->mark("k_tail");
     CUDA_TRY(csq_launch_scan(nblk, (const uint32_t*)s.block_tot.p, (const uint32_t*)s.block_cnt.p,
                              (unsigned long long*)s.block_off.p, (unsigned long long*)s.totals.p, st));
     plan->launches += 1;
@@ -568,10 +560,8 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < 2; m++) ep.out[d][m] = (uint8_t*)s.out[d][m].p;
     // default: staged through shared memory; the direct kernels stay for A/B runs and for the reverse-complementing sink
-    if (plan->flags & CSQ_PLAN_EMIT_REC)
-        CUDA_TRY(csq_launch_emit_rec(ep, st));
-    else if ((plan->flags & (CSQ_PLAN_EMIT_G32 | CSQ_PLAN_EMIT_G16 | CSQ_PLAN_EMIT_G8)) || ep.pp.revcomp)
-        CUDA_TRY(csq_launch_emit(ep, (plan->flags & CSQ_PLAN_EMIT_G32) ? 32 : (plan->flags & CSQ_PLAN_EMIT_G8) ? 8 : 16, st));
+    if ((plan->flags & CSQ_PLAN_EMIT_G16) || ep.pp.revcomp)
+        CUDA_TRY(csq_launch_emit(ep, 16, st));
     else
         CUDA_TRY(csq_launch_emit_stage(ep, st));
     plan->launches += s.n ? 1 : 0;

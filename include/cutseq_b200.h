@@ -221,16 +221,10 @@ typedef struct csq_plan csq_plan;
 #define CSQ_PLAN_NO_PREFILTER 2u  /* run the exact DP on every read (no bit-parallel prefilter) */
 #define CSQ_PLAN_ONE_STREAM 64u   /* run the chains of mate 1 and mate 2 on one stream (default: side by side) */
 #define CSQ_PLAN_EMIT_G16 256u    /* emit FASTQ text with the direct (global -> global) k_emit, 16 lanes per record, instead of
-                                     the default k_emit_stage (staged through shared memory); A/B runs       */
-#define CSQ_PLAN_EMIT_G32 16u     /* ... direct k_emit with 32 lanes per record */
-#define CSQ_PLAN_EMIT_G8 32u      /* ... with 8 lanes per record */
-#define CSQ_PLAN_PARSE_ONEPASS 128u /* text batches: the one-pass look-back parse kernel instead of the default four-kernel
-                                     form (A/B runs; measured slower: one latency chain per 16 KiB tile)             */
+                                     the default k_emit_stage (staged through shared memory); A/B runs, initcheck runs   */
 #define CSQ_PLAN_NO_EXACT_STOP 1024u /* exact DP walks every column even after an error-free full match (results are the same; A/B) */
-#define CSQ_PLAN_HOMO_ONE_LANE 2048u /* homopolymer exact DP with a whole column per thread (k_align<100, 2|4>) instead of two lanes per column (A/B) */
-#define CSQ_PLAN_HOMO_V1 512u     /* homopolymer (poly-A / poly-T) exact DP one column at a time instead of two side by side (A/B) */
-#define CSQ_PLAN_EMIT_REC 8u      /* emit FASTQ text with the thread-per-pair 16-byte-chunk kernel instead of the
-                                     default k_emit_stage (A/B runs)                                     */
+/* (flag values 8, 16, 32, 128, 512, 2048 selected slower kernel variants in round 1 - per-pair / 8- / 32-lane emitters,
+ * one-pass parse, one-lane / one-column homopolymer DP; those kernels were removed after measurement and the bits are ignored) */
 
 /* Library / device */
 int csq_abi_version(void);

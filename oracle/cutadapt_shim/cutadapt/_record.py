@@ -36,6 +36,24 @@ class SequenceRecord:
         return f"@{self.name}\n{self.sequence}\n+\n{self.qualities}\n".encode("ascii")
 
 
+def record_names_match(header1: str, header2: str) -> bool:
+    """dnaio.record_names_match / SequenceRecord.is_mate (upstream src/dnaio/_core.pyx record_ids_match): header 2's id
+    ends at its first space or tab; header 1 must end or carry a space / tab there; a trailing 1, 2 or 3 on BOTH ids is
+    not compared."""
+    id2 = len(header2)
+    for i, ch in enumerate(header2):
+        if ch in " \t":
+            id2 = i
+            break
+    if len(header1) < id2:
+        return False
+    if id2 < len(header1) and header1[id2] not in " \t":
+        return False
+    if id2 > 0 and header1[id2 - 1] in "123" and header2[id2 - 1] in "123":
+        id2 -= 1
+    return header1[:id2] == header2[:id2]
+
+
 def open_maybe_gz(path, mode):
     if str(path).endswith(".gz"):
         return gzip.open(path, mode, compresslevel=1) if "w" in mode else gzip.open(path, mode)

@@ -3,6 +3,7 @@
 from .adapters import MultipleAdapters
 from .info import ModificationInfo
 from .qualtrim import quality_trim_index
+from ._record import record_names_match
 
 
 class SingleEndModifier:
@@ -141,7 +142,7 @@ class PairedEndRenamer(PairedEndModifier):
     def __call__(self, read1, read2, info1, info2):
         id1, comment1 = Renamer.parse_name(read1.name)
         id2, comment2 = Renamer.parse_name(read2.name)
-        if id1 != id2:
+        if not record_names_match(read1.name, read2.name):
             raise ValueError(f"Input read IDs not identical: '{id1}' != '{id2}'")
         r1, r2 = _InfoView(info1), _InfoView(info2)
         name1 = self._template.format(header=read1.name, id=id1, comment=comment1,

@@ -1,6 +1,6 @@
 """Stand-in for upstream src/cutadapt/runners.py: a serial runner only."""
 
-from ._record import read_fastq
+from ._record import read_fastq, record_names_match
 from .report import Statistics
 
 
@@ -33,6 +33,9 @@ class SerialPipelineRunner:
                         return
                     if r1 is None or r2 is None:
                         raise ValueError("paired input files have different numbers of records")
+                    if not record_names_match(r1.name, r2.name):  # dnaio TwoFilePairedEndReader: r1.is_mate(r2)
+                        raise ValueError(f"Records are improperly paired. Read name '{r1.name}' in file 1 does not match "
+                                         f"'{r2.name}' in file 2.")
                     yield r1, r2
             n, bp1, bp2 = pipeline.process_reads(pairs(), progress)
         else:

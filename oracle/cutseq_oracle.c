@@ -295,6 +295,23 @@ static void parse_name_id(const char* name, int len, int* id_start, int* id_end)
     }
 }
 
+/* dnaio record_names_match == SequenceRecord.is_mate (upstream src/dnaio/_core.pyx, record_ids_match): the id of
+ * header 2 ends at its first ' ' or '\t' (strcspn; NOT str.split's whitespace set); header 1 must end, or carry a
+ * ' ' / '\t', at that very position; when both ids end in '1', '2' or '3' that last character is not compared
+ * ("/1" "/2" of old Illumina names, ".1" ".2" of fastq-dump -I); the rest must be byte-identical.  Used twice on the
+ * reference's path: by dnaio's paired reader on the headers as they stand in the files, and by cutadapt's
+ * PairedEndRenamer (run.py:643-645) on the headers as the SuffixRemovers of run.py:537-542 left them. */
+static int names_match(const char* h1, int n1, const char* h2, int n2) {
+    int id2 = 0;
+    while (id2 < n2 && h2[id2] != ' ' && h2[id2] != '\t') id2++;
+    if (n1 < id2) return 0;
+    if (id2 < n1 && h1[id2] != ' ' && h1[id2] != '\t') return 0;
+    if (id2 > 0 && h1[id2 - 1] >= '1' && h1[id2 - 1] <= '3' && h2[id2 - 1] >= '1' && h2[id2 - 1] <= '3') id2--;
+    return memcmp(h1, h2, (size_t)id2) == 0;
+}
+
+int orc_names_match(const char* h1, int n1, const char* h2, int n2) { return names_match(h1, n1, h2, n2); }
+
 static void slice(orc_read* r, int start, int stop) { /* python read[start:stop], 0<=start<=stop<=len */
     r->seq += start;
     r->qual += start;
@@ -489,17 +506,17 @@ static void* chunk_worker(void* arg) {
         orc_read r[2];
         load_read(&r[0], &in->mate[0], i);
         if (paired) load_read(&r[1], &in->mate[1], i);
+        /* dnaio's paired reader: "Records are improperly paired" unless r1.is_mate(r2) */
+        if (paired && !names_match(r[0].name, r[0].name_len, r[1].name, r[1].name_len)) J->status = CSQ_ERR_PAIRING;
         k->n++;
         k->total_bp[0] += (uint64_t)r[0].len;
         if (paired) k->total_bp[1] += (uint64_t)r[1].len;
         for (int t = 0; t < n1; t++) {
             if (ops1[t].kind == CSQ_OP_RENAME) {
                 if (paired) {
-                    int s1, e1, s2, e2;
-                    parse_name_id(r[0].name, r[0].name_len, &s1, &e1);
-                    parse_name_id(r[1].name, r[1].name_len, &s2, &e2);
-                    if (e1 - s1 != e2 - s2 || memcmp(r[0].name + s1, r[1].name + s2, (size_t)(e1 - s1)) != 0)
-                        J->status = CSQ_ERR_PAIRING;
+                    /* PairedEndRenamer.__call__: ValueError("Input read IDs not identical") unless
+                     * record_names_match(read1.name, read2.name); each mate then keeps its OWN id */
+                    if (!names_match(r[0].name, r[0].name_len, r[1].name, r[1].name_len)) J->status = CSQ_ERR_PAIRING;
                     orc_read a = r[0], bb = r[1]; /* both names are built from the pre-rename infos */
                     apply_rename(&ops1[t], &r[0], &a, &bb);
                     apply_rename(&ops2[t], &r[1], &a, &bb);

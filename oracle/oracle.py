@@ -44,6 +44,7 @@ def lib():
         ]
         _LIB.orc_free.argtypes = [C.POINTER(A.csq_batch_out)]
         _LIB.orc_max_threads.restype = C.c_int
+        _LIB.orc_names_match.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     return _LIB
 
 
@@ -63,6 +64,12 @@ def adapter_match(op, query: str):
     if not found:
         return None
     return (m.ref_start, m.ref_stop, m.query_start, m.query_stop, m.score, m.errors)
+
+
+def names_match(header1: str, header2: str) -> bool:
+    """dnaio.record_names_match(header1, header2)"""
+    a, b = header1.encode("latin-1"), header2.encode("latin-1")
+    return bool(lib().orc_names_match(a, len(a), b, len(b)))
 
 
 def quality_trim_index(qualities: str, cutoff_front: int, cutoff_back: int, base: int = 33):

@@ -119,6 +119,21 @@ def synth_pairs(seed, n, read_len=150, p5=P5, p7=P7, inline5="", inline3="", umi
             n1, n2 = base + ".1", base + ".2"
         elif suffix_style == "bare":
             n1 = n2 = base
+        elif suffix_style == "mixed":
+            # mate numbers inside the id with a comment behind them: SuffixRemover (run.py:537-542) only strips at the
+            # end of the whole header, so these ids keep their ".1" / "/1" and only match under dnaio's
+            # record_names_match rule (one trailing 1-3 on both ids is not compared)
+            style = i % 5
+            if style == 0:
+                n1, n2 = f"SRR1.{i + 1}.1 {i + 1} length={read_len}", f"SRR1.{i + 1}.2 {i + 1} length={read_len}"
+            elif style == 1:
+                n1, n2 = base + "/1 comment", base + "/2 comment"
+            elif style == 2:
+                n1, n2 = base + "/1", base + "/2"
+            elif style == 3:
+                n1, n2 = base + "\t1:N:0", base + "\t2:N:0"
+            else:
+                n1, n2 = base + "_1 x", base + "_2"
         else:
             n1, n2 = base + " 1:N:0:ACGTACGT+TGCATGCA", base + " 2:N:0:ACGTACGT+TGCATGCA"
         r1s.append((n1, s1, quals(rng, s1)))
@@ -197,6 +212,7 @@ CASES = [
     ("se_inline_ensure", "synth_se_inline", ["-A", "INLINE", "--ensure-inline-barcode", "--trim-polyA"]),
     ("se_takarav3_autorc", "synth_takara_r1", ["-A", "TAKARAV3", "--auto-rc", "--trim-polyA"]),
     ("unstranded_polya", "synth_takara", ["-A", "UNSTRANDED", "--trim-polyA"]),
+    ("takarav3_mate_numbers", "synth_names", ["-A", "TAKARAV3", "--trim-polyA"]),
 ]
 
 
@@ -214,6 +230,7 @@ def build_inputs():
                         readthrough=0.7, bc_error=0.03, wrong_bc=0.05, suffix_style="bare")
     sets["synth_se_inline"] = [r1]
     sets["edge"] = edge_pairs()
+    sets["synth_names"] = synth_pairs(31, 400, mask5=3, mask3=6, umi3=8, suffix_style="mixed")
     return sets
 
 

@@ -54,7 +54,7 @@ def check_locate(op, reads):
     """Both execution modes: exact DP on every read, and bit-parallel prefilter + exact DP on the survivors."""
     batch, keep = oracle.make_batch(reads)
     wants = [oracle.adapter_match(op, s) for (_, s, _) in reads]
-    for flags in (A.PLAN_NO_PREFILTER, 0, A.PLAN_NO_EXACT_STOP) + ((A.PLAN_NO_PREFILTER | A.PLAN_HOMO_V1, A.PLAN_NO_PREFILTER | A.PLAN_HOMO_ONE_LANE, A.PLAN_HOMO_ONE_LANE, A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER) if len(set(op.adapter)) == 1 else ()):
+    for flags in (A.PLAN_NO_PREFILTER, 0, A.PLAN_NO_EXACT_STOP) + ((A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER,) if len(set(op.adapter)) == 1 else ()):
         got = native.locate_batch(op, batch.mate[0], len(reads), flags=flags)
         for i, (_, s, _) in enumerate(reads):
             g = got[i]
@@ -190,7 +190,7 @@ def compare_with_oracle(prog, mates, flags=0):
     return text
 
 
-@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8, A.PLAN_HOMO_V1 | A.PLAN_NO_PREFILTER, A.PLAN_NO_EXACT_STOP, A.PLAN_HOMO_ONE_LANE, A.PLAN_HOMO_ONE_LANE | A.PLAN_NO_PREFILTER], ids=["prefilter", "exact_only", "emit_rec", "emit_g32", "emit_g16", "emit_g8", "homo_v1_exact_only", "no_exact_stop", "homo_one_lane", "homo_one_lane_exact_only"])
+@pytest.mark.parametrize("flags", [0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_G16, A.PLAN_NO_EXACT_STOP, A.PLAN_ONE_STREAM], ids=["prefilter", "exact_only", "emit_g16", "no_exact_stop", "one_stream"])
 @pytest.mark.parametrize("case", helpers.golden_cases(), ids=lambda c: c["case"])
 def test_golden_vectors(case, flags):
     prog = helpers.program_for(case["argv"], case["n_mates"])
@@ -217,9 +217,47 @@ def test_pairing_error_is_reported():
     assert oracle.run_batch(prog, batch)["status"] == A.ERR_PAIRING
 
 
+# dnaio record_names_match / is_mate (both the paired reader and PairedEndRenamer use it): header 2's id ends at its
+# first space or tab, header 1 must end or hold a space / tab there, one trailing 1-3 on BOTH ids is ignored.
+NAME_PAIRS_OK = [
+    ("r", "r"), ("r 1:N:0", "r 2:N:0"), ("r\t1", "r\t2"), ("r/1", "r/2"), ("r.1", "r.2"), ("r_1", "r_2"), ("r1", "r2"),
+    ("r3", "r1"), ("SRR1.1.1 1 length=76", "SRR1.1.2 1 length=76"), ("r/1 comment", "r/2 comment"), ("r/1 c", "r/2"),
+    ("ab1", "ab3 x"), ("a.1", "a.2"), ("q\x0bz 1", "q\x0bz 2"), ("x" * 70 + "1 c", "x" * 70 + "2 d"),
+    ("x" * 15 + " c", "x" * 15 + " d"), ("x" * 16 + " c", "x" * 16 + " d"), ("x" * 17, "x" * 17),
+]
+NAME_PAIRS_BAD = [
+    ("x 1", "y 2"), ("rA", "rB"), ("r1", "r4"), ("r", "r1"), ("r1", "r"), ("ab", "abc"), ("abc", "ab"), ("r/1", "r.2x"),
+    ("r\x0b1", "r 2"), ("a.1", "a.3"), ("r1.1", "r2.2"), ("x" * 70 + "a", "x" * 70 + "b"), ("x" * 31 + "a c", "x" * 31 + "b c"),
+    ("x" * 16 + "y" + "x" * 20, "x" * 37), ("", "r"), ("r", ""), (" r", "r"),
+]
+
+
+@pytest.mark.parametrize("argv", [["-A", "TAKARAV3"], ["-a", "AGATCGGAAGAGC>AGATCGGAAGAGC"]], ids=["umi", "plain"])
+def test_record_names_match_rule(argv):
+    prog = helpers.program_for(argv, 2)
+    seq, q = "ACGTTGCA" * 10, "I" * 80
+    r1 = [(a, seq, q) for a, _ in NAME_PAIRS_OK]
+    r2 = [(b, seq, q) for _, b in NAME_PAIRS_OK]
+    text = compare_with_oracle(prog, [r1, r2])
+    assert text[0][0].count(b"\n") == 4 * len(NAME_PAIRS_OK)  # every pair written, each mate under its own id
+    for a, b in NAME_PAIRS_BAD:
+        batch, keep = oracle.make_batch(r1[:3] + [(a, seq, q)] + r1[3:5], r2[:3] + [(b, seq, q)] + r2[3:5])
+        assert oracle.run_batch(prog, batch)["status"] == A.ERR_PAIRING, (a, b)
+        for flags in (0, A.PLAN_EMIT_G16):
+            with native.Plan(prog, 0, flags) as plan:
+                with pytest.raises(native.NativeError) as e:
+                    plan.run_batch(batch)
+                assert e.value.code == A.ERR_PAIRING, (a, b)
+                mates = [[r[i] for i in range(6)] for r in ([*r1[:3], (a, seq, q), *r1[3:5]], [*r2[:3], (b, seq, q), *r2[3:5]])]
+                texts = [("".join(f"@{n}\n{s}\n+\n{qq}\n" for n, s, qq in m)).encode("latin-1") for m in mates]
+                with pytest.raises(native.NativeError) as e:
+                    plan.run_text(texts, 6)
+                assert e.value.code == A.ERR_PAIRING, (a, b)
+
+
 def test_pairing_error_in_a_pair_that_bypasses_the_staging_buffers():
-    """Headers of 30 KB: the pair does not fit the emitter's shared-memory buffers and is written bytewise; the id
-    check of PairedEndRenamer has to work there too (ids differ in their last character only)."""
+    """Headers of 30 KB: the pair does not fit the emitter's shared-memory buffers and is written bytewise; the name
+    check has to work there too (ids differ in their last character only)."""
     prog = helpers.program_for(["-A", "TAKARAV3"], 2)
     seq, q = "ACGTTGCA" * 10, "I" * 80
     long_id = "x" * 300
@@ -340,7 +378,7 @@ def test_synthetic_configs_against_oracle():
         prog = helpers.program_for(argv, n_mates)
         batch = native.synth_batch(config, 30000, first_index=12345, buffer=3)
         want = oracle.run_batch(prog, batch, n_threads=8)
-        for flags in (0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_REC, A.PLAN_EMIT_G32, A.PLAN_EMIT_G16, A.PLAN_EMIT_G8, A.PLAN_HOMO_V1, A.PLAN_NO_EXACT_STOP, A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER, A.PLAN_HOMO_ONE_LANE):
+        for flags in (0, A.PLAN_NO_PREFILTER, A.PLAN_EMIT_G16, A.PLAN_NO_EXACT_STOP, A.PLAN_NO_EXACT_STOP | A.PLAN_NO_PREFILTER):
             with native.Plan(prog, 0, A.PLAN_KEEP_MATCHES | flags) as plan:
                 text, records = plan.run_batch(batch)
                 stats = plan.stats()
@@ -360,8 +398,8 @@ def test_synthetic_configs_against_oracle():
 
 
 # ---- text batches: raw FASTQ bytes in, the device builds the record index (parse.cu) ----
-PARSE_FLAGS = [0, A.PLAN_PARSE_ONEPASS]
-PARSE_IDS = ["parse_v1", "onepass"]
+PARSE_FLAGS = [0]
+PARSE_IDS = ["parse"]
 
 
 @pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
