@@ -1,22 +1,25 @@
 #!/usr/bin/env python
-"""bench.py - read-pairs/s of the trimming chain on BASELINE.json's workload.
+"""bench.py - read-pairs/s of the trimming chain on BASELINE.json's workload (config 2).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # this implementation
     python bench.py --impl reference [...]                       # CPU arm (oracle port, all host cores)
     torchrun --nproc-per-node N bench.py --gpus N ...            # one rank per GPU
 
-One "step" = one pass of the whole hot path (all ALIGN ops, cuts, quality trim, filters, FASTQ
-emission) over one batch of synthetic 2x150 read pairs (config 2: `-A TAKARAV3 --trim-polyA`).
-`value` is kernel throughput with the batches resident in HBM (CUDA events around exactly K steps,
-max over ranks); `e2e` is the same chain through csq_submit_text/csq_wait with pinned HOST buffers,
-host->device and device->host copies inside the timed region.  Prints ONE JSON line (rank 0).
-Input form: --input text (default; raw FASTQ bytes, the device builds the record index - what the
-file driver does) or --input soa (host-parsed packed struct-of-arrays batches).
+One "step" = one pass of the whole hot path (FASTQ parse, all ALIGN ops, cuts, quality trim, filters, FASTQ
+emission) over the 10 M synthetic 2x150 read pairs of config 2 (`-A TAKARAV3 --trim-polyA`), held as 5 batches
+of 2 M pairs per GPU.
+  value  kernel throughput with the batches resident in HBM (CUDA events around exactly K steps, max over ranks)
+  e2e    the same chain through csq_submit_text / csq_wait with pinned HOST buffers, host->device and device->host
+         copies inside the timed region; roofline_e2e relates it to the measured PCIe copy ceiling (csq_pcie_peak)
+  files  FASTQ files on disk -> csq_run_files (all GPUs of the job, driven by rank 0) -> trimmed FASTQ files, plain and
+         .gz, with the sha256 of every output and its equality to the 1-GPU run of the same files
+Prints ONE JSON line (rank 0).
 """
 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -30,10 +33,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "read-pairs/s (2x150, TAKARAV3)"
 UNIT = "pairs/s"
-BATCH_PAIRS = 2_000_000      # pairs per step and GPU
-N_BATCHES = 5                # distinct resident batches per GPU: 5 x 2M = the 10M pairs of config 2
+BATCH_PAIRS = 2_000_000      # pairs per batch and GPU
+N_BATCHES = 5                # resident batches per GPU: 5 x 2M = the 10M pairs of config 2 = one step
 ARGV = ["-A", "TAKARAV3", "--trim-polyA"]
-OPS_PER_CELL = 10            # algorithmic integer ops per DP cell
 
 
 def takara_program():
@@ -102,13 +104,66 @@ def h2d_bytes(batch):
     return int(total)
 
 
+def kernel_sources_hash():
+    """sha256 over the CUDA sources: numbers taken from a committed ncu capture are only printed next to live times
+    when the kernels are still the ones that were profiled."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "cutseq_b200", "csrc")
+    for fn in sorted(os.listdir(csrc)):
+        if fn.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(csrc, fn), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def real_reference_available():
+    """A real cutadapt 5.x + a reference tree: then the CPU arm is the reference itself (scripts/bless_against_cutadapt.py)."""
+    try:
+        from scripts import bless_against_cutadapt as bless
+
+        mod, info = bless.real_cutadapt()
+        if mod is None:
+            return None
+        for cand in (os.environ.get("CUTSEQ_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+            if cand and os.path.exists(os.path.join(cand, "cutseq", "run.py")):
+                return {"cutadapt": info, "reference": cand}
+    except Exception:
+        pass
+    return None
+
+
+def cpu_leg_real(ref, steps, sample_pairs):
+    """`cutseq -A TAKARAV3 --trim-polyA -t <cores>` of the REAL reference on files of the same generator."""
+    import shutil
+    import tempfile
+
+    from oracle import oracle
+    from scripts import bench_files
+
+    tmp = tempfile.mkdtemp()
+    try:
+        batch = oracle.synth_batch(2, sample_pairs)
+        ins = [os.path.join(tmp, f"in_R{m}.fq") for m in (1, 2)]
+        bench_files.write_fastq_from_soa(batch, ins)
+        cores = os.cpu_count() or 1
+        env = dict(os.environ, PYTHONPATH=ref["reference"] + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            subprocess.check_call([sys.executable, "-m", "cutseq.run"] + ARGV + ["-t", str(cores), "-O", os.path.join(tmp, "out")] + ins,
+                                  env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return steps * sample_pairs / dt, cores, dt / steps
+
+
 def cpu_leg(prog, steps, warmup, sample_pairs, first_index=0):
-    """The oracle port on all host cores over bounded samples of the same workload."""
-    from cutseq_b200 import native
+    """The oracle port on all host cores over bounded samples of the same workload (generator: oracle/libsynth.so,
+    the CUDA-free build of cutseq_b200/csrc/synth.cu - nothing of the product library is mapped here)."""
     from oracle import oracle
 
     threads = oracle.lib().orc_max_threads()
-    batch = native.synth_batch(2, sample_pairs, first_index=first_index, buffer=15)
+    batch = oracle.synth_batch(2, sample_pairs, first_index=first_index)
     for _ in range(max(0, warmup)):
         oracle.run_batch(prog, batch, n_threads=threads, want_matches=False)
     t0 = time.perf_counter()
@@ -118,45 +173,61 @@ def cpu_leg(prog, steps, warmup, sample_pairs, first_index=0):
     return steps * sample_pairs / dt, threads, dt / steps
 
 
-def files_leg(prog, pairs):
-    """FASTQ files on disk -> csq_run_files -> trimmed FASTQ files, plain and .gz; host stages reported separately."""
+def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
+    """FASTQ files on disk -> csq_run_files -> trimmed FASTQ files, plain and .gz (BGZF members in, gzip members out);
+    host stages reported separately; with n_devices > 1 the same files also go through ONE GPU and the outputs must
+    have the same sha256 (order-preserving reassembly, reference run.py:751-758 / 793-794 `-t N` runner)."""
     import shutil
     import tempfile
 
     from cutseq_b200 import native
     from scripts import bench_files
 
-    tmp = tempfile.mkdtemp()
-    out = {}
+    tmp = tempfile.mkdtemp(dir=os.environ.get("CSQ_BENCH_TMP"))
+    out = {"host_threads": threads, "n_devices": n_devices}
     try:
-        batch = native.synth_batch(2, pairs, first_index=0, buffer=14)
-        for variant in ("plain", "gz"):
+        for variant, pairs in (("plain", pairs_plain), ("gz", pairs_gz)):
+            if pairs <= 0:
+                continue
             ext = ".fq.gz" if variant == "gz" else ".fq"
             ins = [os.path.join(tmp, f"in_R{m}{ext}") for m in (1, 2)]
-            bench_files.write_fastq_from_batch(batch, ins, variant == "gz")
-            outs = {"trimmed": [os.path.join(tmp, f"out_trimmed_R{m}{ext}") for m in (1, 2)],
-                    "short": [os.path.join(tmp, f"out_short_R{m}{ext}") for m in (1, 2)]}
-            best = None
-            for rep in range(2):
-                for q in outs["trimmed"] + outs["short"]:  # a fresh run writes new files
-                    if os.path.exists(q):
-                        os.remove(q)
-                t0 = time.time()
-                counters, timing = native.run_files(prog, ins, outs, gpus=1, threads=os.cpu_count() or 4)
-                wall = time.time() - t0
-                if best is None or wall < best[0]:
-                    best = (wall, timing)
-            wall, timing = best
-            out[variant] = {"pairs_per_s": pairs / wall, "wall_s": wall, "read_inflate_s": timing.read_inflate,
-                            "gpu_h2d_kernels_d2h_s": timing.h2d_kernels_d2h, "gpu_kernels_s": timing.kernels,
-                            "deflate_write_s": timing.write_deflate, "input_bytes": sum(os.path.getsize(p) for p in ins)}
-            for p in ins + outs["trimmed"] + outs["short"]:
+            t0 = time.time()
+            bench_files.write_fixture(ins, pairs, variant == "gz", threads)
+            gen_s = time.time() - t0
+            res = {"pairs": pairs, "input_bytes": sum(os.path.getsize(p) for p in ins), "fixture_s": gen_s}
+            hashes = {}
+            for nd in sorted({1, n_devices}):
+                outs = {"trimmed": [os.path.join(tmp, f"out{nd}_trimmed_R{m}{ext}") for m in (1, 2)],
+                        "short": [os.path.join(tmp, f"out{nd}_short_R{m}{ext}") for m in (1, 2)]}
+                best = None
+                for rep in range(2 if nd == n_devices else 1):
+                    for q in outs["trimmed"] + outs["short"]:  # a fresh run writes new files
+                        if os.path.exists(q):
+                            os.remove(q)
+                    t0 = time.time()
+                    counters, timing = native.run_files(prog, ins, outs, gpus=nd, threads=threads)
+                    wall = time.time() - t0
+                    if best is None or wall < best[0]:
+                        best = (wall, timing, counters)
+                wall, timing, counters = best
+                hashes[nd] = bench_files.hash_outputs(outs["trimmed"] + outs["short"], variant == "gz")
+                res[f"n{nd}"] = {"pairs_per_s": pairs / wall, "wall_s": wall, "read_inflate_s": timing.read_inflate,
+                                 "gpu_h2d_kernels_d2h_s": timing.h2d_kernels_d2h, "gpu_kernels_s": timing.kernels,
+                                 "deflate_write_s": timing.write_deflate, "written_pairs": int(counters.written),
+                                 "output_bytes": sum(os.path.getsize(p) for p in outs["trimmed"] + outs["short"])}
+                for p in outs["trimmed"] + outs["short"]:
+                    if os.path.exists(p):
+                        os.remove(p)
+            res["pairs_per_s"] = res[f"n{n_devices}"]["pairs_per_s"]
+            res["sha256"] = hashes[n_devices]
+            res["same_as_1gpu"] = hashes[n_devices] == hashes[1]
+            out[variant] = res
+            for p in ins:
                 if os.path.exists(p):
                     os.remove(p)
-        out["pairs"] = pairs
-        out["host_threads"] = os.cpu_count()
-        out["note"] = ("whole run incl. plan set-up and pinned allocations (~0.5 s fixed); stage seconds are busy times of "
-                       "overlapping stages; .gz = one gzip member per input file (level 1), own inflate, zlib level-1 members out")
+        out["note"] = ("whole runs incl. plan set-up and pinned allocations; stage seconds are busy times of overlapping stages; "
+                       "sha256 over the (decompressed) bytes of trimmed_R1, trimmed_R2, short_R1, short_R2; "
+                       ".gz input = BGZF members (64 KiB blocks, level 1), .gz output = concatenated gzip members")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return out
@@ -167,24 +238,24 @@ def run_reference(args):
     if rank != 0:
         return 0
     prog = takara_program()
-    sample = 200_000
-    # the real `cutseq -t <cores>` would be the preferred CPU arm, but it needs the cutadapt package
-    # (and the reference tree, which does not travel to the GPU box); probed here so that the line says which it is
-    try:
-        import cutadapt  # noqa: F401
-        have_cutadapt = True
-    except Exception:
-        have_cutadapt = False
-    value, threads, step_s = cpu_leg(prog, args.steps, min(args.warmup, 1), sample)
+    ref = real_reference_available()
+    if ref:
+        sample = 400_000
+        value, threads, step_s = cpu_leg_real(ref, max(1, min(args.steps, 3)), sample)
+        kind, what = "reference", f"real cutseq (cutadapt {ref['cutadapt']}) -t {threads} on FASTQ files of the config-2 generator, parse and write included"
+    else:
+        sample = 200_000
+        value, threads, step_s = cpu_leg(prog, args.steps, min(args.warmup, 1), sample)
+        kind, what = "port", ("oracle/cutseq_oracle.c (restated cutadapt chain; the reference needs the absent cutadapt package), "
+                              "gzip/parse excluded")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; step = {sample} pairs (bounded sample)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} x {sample} pairs of the config-2 generator, oracle/cutseq_oracle.c (restated "
-                                   "cutadapt chain; the reference needs the absent cutadapt package), gzip/parse excluded",
-                         "cutadapt_importable": have_cutadapt},
+        "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; step = {sample} pairs (bounded sample of the 10M-pair workload)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} x {sample} pairs of the config-2 generator, {what}",
+                         "cutadapt_importable": bool(ref)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -194,7 +265,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60, help="timed steps; a step is one pass over the 10M-pair workload (default: ~1 s timed)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-pairs", type=int, default=BATCH_PAIRS)
@@ -203,12 +274,11 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
-    ap.add_argument("--file-pairs", type=int, default=2_000_000, help="pairs in the whole-file leg")
+    ap.add_argument("--file-pairs", type=int, default=20_000_000, help="pairs in the plain whole-file leg (config 5: streamed, <= 20M-pair on-disk file)")
+    ap.add_argument("--file-pairs-gz", type=int, default=8_000_000, help="pairs in the .gz whole-file leg")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
-    ap.add_argument("--emit", default="stage", choices=["stage", "g16", "g32", "g8", "rec"], help="emit kernel variant (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
-    ap.add_argument("--homo", default="split", choices=["split", "one-lane", "v1"], help="poly-A / poly-T exact DP: column split over two lanes (default), whole column per thread with 2-4 columns side by side, or one column at a time (A/B runs)")
+    ap.add_argument("--emit", default="stage", choices=["stage", "g16"], help="emit kernel (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
     ap.add_argument("--no-exact-stop", action="store_true", help="exact DP walks on after an error-free full match (CSQ_PLAN_NO_EXACT_STOP, A/B runs)")
-    ap.add_argument("--parse", default="v1", choices=["onepass", "v1"], help="text-batch parse (A/B runs); v1 (four kernels) is the product default, onepass = single look-back kernel")
     ap.add_argument("--one-stream", action="store_true", help="mate chains on one stream (CSQ_PLAN_ONE_STREAM), for A/B runs")
     ap.add_argument("--input", default="text", choices=["text", "soa"], help="batch form handed to the library")
     args = ap.parse_args()
@@ -230,7 +300,6 @@ def main():
 
     group = csq_dist.Group()  # NCCL process group when launched by torchrun with WORLD_SIZE > 1
     rank, local_rank, world = group.rank, group.local_rank, group.world
-    dist = group.dist
     torch.cuda.set_device(local_rank)
     build.build()
     native.lib()  # fails loudly when the CUDA library is missing
@@ -246,8 +315,8 @@ def main():
 
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
-    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16, "g32": A.PLAN_EMIT_G32, "g8": A.PLAN_EMIT_G8, "rec": A.PLAN_EMIT_REC}[args.emit] | (A.PLAN_ONE_STREAM if args.one_stream else 0)
-                       | (A.PLAN_PARSE_ONEPASS if args.parse == "onepass" else 0) | {"split": 0, "one-lane": A.PLAN_HOMO_ONE_LANE, "v1": A.PLAN_HOMO_V1}[args.homo] | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
+    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16}[args.emit]
+                       | (A.PLAN_ONE_STREAM if args.one_stream else 0) | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
@@ -281,16 +350,16 @@ def main():
         else:
             plan.submit(slot, bt, out)
 
-    # ---- kernel throughput, inputs resident in HBM ----
+    # ---- kernel throughput, inputs resident in HBM: a step = the B resident batches, one after the other ----
     if args.warmup > 0:
-        plan.run_steps(slots, args.warmup)
+        plan.run_steps(slots, args.warmup * B)
     c0 = plan.stats()
     l0 = plan.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     t0 = time.time()
-    ms = plan.run_steps(slots, args.steps)  # untimed sizing pass inside, then K steps between two CUDA events
+    ms = plan.run_steps(slots, args.steps * B)  # untimed sizing pass inside, then K x B batches between two CUDA events
     t1 = time.time()
     barrier()
     launches = plan.launch_count() - l0
@@ -298,22 +367,23 @@ def main():
     job_counters = group.sum_counters(c1)  # the one reduction of trim statistics (NCCL all-reduce when N > 1)
     ktimes = plan.kernel_times(slots[0])
     ms = max_over_ranks(ms)
-    value = world * args.steps * P / (ms * 1e-3)
-    # launches of the sizing pass are outside the CUDA-event bracket: count the timed ones only
-    # csq_run_steps = B sizing steps + K timed steps + 1 per-kernel profiling step
-    per_step_launches = launches // (args.steps + B + 1)
-    timed_launches = per_step_launches * args.steps
+    value = world * args.steps * B * P / (ms * 1e-3)
+    # csq_run_steps = B sizing batches + K*B timed batches + 1 per-kernel profiling batch; only the timed ones count
+    n_passes = args.steps * B + B + 1
+    per_batch_launches = launches // n_passes
+    timed_launches = per_batch_launches * args.steps * B
 
-    # nominal DP cells (device counters) over the timed + sizing steps -> cells per step
     def cells(c):
         return sum(sum(c.dp_cells[m]) for m in range(2))
 
-    cells_per_step = (cells(c1) - cells(c0)) / (args.steps + B + 1)
-    gcups_whole_chain = cells_per_step / (ms / args.steps * 1e-3) / 1e9
-
-    # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H timed) ----
-    e2e = None
+    cells_per_batch = (cells(c1) - cells(c0)) / n_passes
+    step_ms = ms / args.steps
+    gcups_nominal = cells_per_batch * B / (step_ms * 1e-3) / 1e9
     clocks = sampler.stop(t0, t1)
+
+    # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H timed); a step = B batches ----
+    e2e = None
+    roofline_e2e = None
     if not args.no_e2e:
         cap = int(in_bytes(batches[0]) // 2 + 64 * P + 4096)
         outs, keep = [], []
@@ -330,8 +400,8 @@ def main():
             outs.append(out)
         e2e_slots = [B + i for i in range(n_e2e)] if B + n_e2e <= A.CSQ_N_SLOTS else list(range(n_e2e))
 
-        def e2e_steps(k):
-            """k steps, up to n_e2e batches in flight (submit of step i+n-1 is issued before the wait of step i)."""
+        def e2e_batches(k):
+            """k batches, up to n_e2e in flight (submit of batch i+n-1 is issued before the wait of batch i)."""
             d2h = 0
             submitted = 0
             for i in range(k):
@@ -343,36 +413,76 @@ def main():
                 d2h += sum(o.text[d][m].bytes for d in range(A.CSQ_N_DEST) for m in range(2))
             return d2h
 
-        e2e_steps(max(2, min(args.warmup, 3)))
+        e2e_steps = max(2, min(args.steps, 12))  # 12 steps = 120 M pairs, ~2 s: enough for a copy-bound rate
+        e2e_batches(max(2, min(args.warmup, 3)))
         barrier()
         w0 = time.perf_counter()
-        d2h = e2e_steps(args.steps)
+        d2h = e2e_batches(e2e_steps * B)
         torch.cuda.synchronize()
         w1 = time.perf_counter()
         barrier()
         e2e_s = max_over_ranks(w1 - w0)
-        e2e = {"value": world * args.steps * P / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes(batches[0]),
-               "d2h_bytes_per_step": int(d2h // args.steps), "ms_per_step": e2e_s / args.steps * 1e3,
-               "timing": f"wall clock between device-synchronised points, {n_e2e} batches in flight through csq_submit/csq_wait, max over ranks"}
+        e2e = {"value": world * e2e_steps * B * P / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes(batches[0]) * B,
+               "d2h_bytes_per_step": int(d2h // e2e_steps), "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+               "timing": f"wall clock between device-synchronised points, {n_e2e} batches in flight through csq_submit_text/csq_wait, max over ranks"}
+        # the ceiling of this path: the same byte counts per batch as plain pinned copies, both directions at once,
+        # every rank between the same barriers (the ranks of one box share its PCIe root / host memory)
+        try:
+            hb, db = in_bytes(batches[0]), int(d2h // (e2e_steps * B))
+            native.pcie_peak(local_rank, hb, db, reps=1, mode=2)
+            barrier()
+            up, down = native.pcie_peak(local_rank, hb, db, reps=4, mode=2)
+            barrier()
+            t_ceiling = max_over_ranks(hb / (up * 1e9))  # seconds per batch of the slowest rank (both directions share the time)
+            ceiling_pairs = world * P / t_ceiling
+            roofline_e2e = {"bound": "pcie (pinned host <-> device copies, both directions at once)", "achieved": e2e["value"], "peak": ceiling_pairs,
+                            "unit": UNIT, "frac": e2e["value"] / ceiling_pairs, "h2d_GBps_ceiling": up, "d2h_GBps_ceiling": down,
+                            "h2d_GBps_achieved": e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9,
+                            "d2h_GBps_achieved": e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9,
+                            "how": "csq_pcie_peak(mode 2): cudaMemcpyAsync of one batch's input bytes up and output bytes down, 4 repetitions, "
+                                   "all ranks at once; peak = pairs/s if the chain cost nothing but those copies (rank 0's GB/s shown, time = max over ranks)"}
+        except native.NativeError as exc:
+            roofline_e2e = {"error": str(exc)}
 
     native.unbind_host()  # the host legs below (files, CPU baseline) use every core of the box
     if rank != 0:
         plan.close()
+        # rank 0 drives every GPU of the job in the files leg: wait here so that the job ends together
+        group.barrier()
         group.close()
         return 0
 
-    # ---- roofline of the dominant kernel (per-kernel CUDA events of the last timed step) ----
+    # ---- roofline of the dominant kernel (per-kernel CUDA events of one untimed batch behind the timed region) ----
     alu_peak, mixed_peak = native.int_peak(local_rank)
-    peak = max(alu_peak, mixed_peak)
-    step_ms = ms / args.steps
     dom_name, dom_ms = max(ktimes, key=lambda kv: kv[1]) if ktimes else ("n/a", 0.0)
-    # nominal cells of each ALIGN launch, in launch order (mate 1 ops then mate 2 ops)
-    align_cells = []
-    for m, ops in enumerate((prog.ops_r1, prog.ops_r2)):
-        for t, op in enumerate(ops):
-            if op.kind == A.OP_ALIGN:
-                align_cells.append((c1.dp_cells[m][t] - c0.dp_cells[m][t]) / (args.steps + B + 1))
-    # one entry per ALIGN op: its k_prefilter launch (if any) plus its k_align launch
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json, copy read+write)"
+    except Exception:
+        pass
+    d2h_per_batch = e2e["d2h_bytes_per_step"] // B if e2e else int(0.78 * in_bytes(batches[0]))
+    emit_bytes = in_bytes(batches[0]) + d2h_per_batch  # input records read once + FASTQ text written once (~1.27 KB / pair)
+    emit_ms = sum(kms for name, kms in ktimes if name == "k_emit")
+    roofline = {"bound": "hbm", "kernel": {"stage": "k_emit_stage", "g16": "k_emit<16>"}[args.emit],
+                "achieved": (emit_bytes / (emit_ms * 1e-3) / 1e9) if emit_ms else None, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": hbm_src, "traffic": None, "ms": emit_ms, "share_of_step": emit_ms * B / step_ms if step_ms else None,
+                "how": "algorithmic bytes per launch (the batch's FASTQ text read once + the trimmed FASTQ text written once) / CUDA-event "
+                       "duration of that launch (one untimed batch, events on the launching stream)"}
+    if roofline["achieved"]:
+        roofline["frac"] = roofline["achieved"] / hbm_peak
+    src_hash = kernel_sources_hash()
+    try:  # DRAM bytes of one launch from the committed ncu capture (per pair, scaled to this batch size) - only if the sources still match
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("sources_sha256_16") == src_hash:
+            roofline["traffic"] = tr[{"stage": "k_emit", "g16": "k_emit_g16"}[args.emit]]["dram_bytes_per_pair"] * P
+            roofline["traffic_source"] = tr["source"]
+        else:
+            roofline["traffic_source"] = "committed ncu capture is older than the kernel sources: not shown"
+    except Exception:
+        pass
+    # integer side: time of every ALIGN op (prefilter + exact DP) and nominal GCUPS; executed lane-ops only from a capture of THESE sources
     align_ops = []
     for name, kms in ktimes:
         if name.startswith("k_prefilter"):
@@ -383,67 +493,38 @@ def main():
                 align_ops[-1][2] = False
             else:
                 align_ops.append([name, kms, False])
-    per_kernel = []
-    for (name, kms, _), cl in zip(align_ops, align_cells):
-        per_kernel.append({"kernel": name, "ms": kms, "gcups": cl / (kms * 1e-3) / 1e9 if kms > 0 else None})
-    hbm_peak, hbm_src = 6650.0, "fallback"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            hbm_peak, hbm_src = json.load(f)["hbm_gbs"], "measured"
-    except Exception:
-        pass
-    d2h_per_step = e2e["d2h_bytes_per_step"] if e2e else int(0.72 * in_bytes(batches[0]))
-    emit_bytes = in_bytes(batches[0]) + d2h_per_step  # input read once + FASTQ text written once (~1.3 KB / pair)
-    emit_ms = sum(kms for name, kms in ktimes if name == "k_emit")
-    roofline_dp = None
-    dom_dp = max(per_kernel, key=lambda r: r["ms"]) if per_kernel else None
-    if dom_dp:
-        achieved = dom_dp["gcups"] * OPS_PER_CELL  # Gop/s (algorithmic integer lane-ops)
-        roofline_dp = {
-            "bound": "int_issue", "kernel": dom_dp["kernel"], "achieved": achieved, "peak": peak / 1e9, "unit": "Gop/s",
-            "frac": achieved / (peak / 1e9), "traffic": None,
-            "how": f"nominal DP cells of the op (m x columns, counted on the device) x {OPS_PER_CELL} ops/cell / CUDA-event duration of its "
-                   f"launches; peak = csq_int_peak measured live (ALU-only {alu_peak / 1e12:.2f}, ALU+FMA mix {mixed_peak / 1e12:.2f} "
-                   "T lane-op/s). With the bit-parallel prefilter most nominal cells are never visited, so this can exceed 1.",
-        }
-    # the same op by EXECUTED integer lane-ops: instructions per read of each kernel from the committed ncu capture of
-    # this workload (deterministic for the generator), times the reads of a launch, over the live CUDA-event time
+    align_cells = []
+    for m, ops in enumerate((prog.ops_r1, prog.ops_r2)):
+        for t, op in enumerate(ops):
+            if op.kind == A.OP_ALIGN:
+                align_cells.append((c1.dp_cells[m][t] - c0.dp_cells[m][t]) / n_passes)
+    dp_kernels = [{"kernel": name, "ms": kms, "nominal_gcups": cl / (kms * 1e-3) / 1e9 if kms > 0 else None}
+                  for (name, kms, _), cl in zip(align_ops, align_cells)]
     roofline_dp_executed = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            ops_tab = json.load(f)["dp_lane_ops_per_read"]
-        if dom_dp and not args.no_prefilter:
-            kind = dom_dp["kernel"][dom_dp["kernel"].index("("):]
-            lane_ops = ops_tab["k_prefilter" + kind] + ops_tab["k_align" + kind]
-            achieved = lane_ops * P / (dom_dp["ms"] * 1e-3) / 1e9
-            roofline_dp_executed = {"bound": "int_issue", "kernel": dom_dp["kernel"], "achieved": achieved, "peak": peak / 1e9, "unit": "Gop/s",
-                                    "frac": achieved / (peak / 1e9), "traffic": None,
-                                    "how": "executed integer lane-ops per read (smsp__inst_executed x 32 of the committed ncu capture, "
-                                           + ops_tab["source"] + ") x reads per launch / CUDA-event duration of the op's launches; peak = csq_int_peak measured live"}
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("sources_sha256_16") == src_hash and dp_kernels and not args.no_prefilter:
+            dom = max(dp_kernels, key=lambda r: r["ms"])
+            kind = dom["kernel"][dom["kernel"].index("("):]
+            lane_ops = tr["dp_lane_ops_per_read"]["k_prefilter" + kind] + tr["dp_lane_ops_per_read"]["k_align" + kind]
+            achieved = lane_ops * P / (dom["ms"] * 1e-3) / 1e9
+            peak = max(alu_peak, mixed_peak) / 1e9
+            roofline_dp_executed = {"bound": "int_issue", "kernel": dom["kernel"], "achieved": achieved, "peak": peak, "unit": "Gop/s",
+                                    "frac": achieved / peak, "sources_sha256_16": src_hash,
+                                    "how": "executed integer lane-ops per read (smsp__inst_executed x 32, " + tr["source"] + ") x reads per launch / "
+                                           "live CUDA-event duration; peak = csq_int_peak measured live (ALU + FMA pipe mix)"}
     except Exception:
         pass
-    roofline_hbm = {"bound": "hbm", "kernel": {"stage": "k_emit_stage", "rec": "k_emit_rec"}.get(args.emit, "k_emit<%s>" % args.emit[1:]), "achieved": (emit_bytes / (emit_ms * 1e-3) / 1e9) if emit_ms else None,
-                    "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "traffic": None,
-                    "how": "algorithmic bytes per launch (input records read once + FASTQ text written once) / CUDA-event duration"}
-    if roofline_hbm["achieved"]:
-        roofline_hbm["frac"] = roofline_hbm["achieved"] / hbm_peak
-    try:  # DRAM bytes of one launch from the committed ncu capture (per pair, scaled to this batch size)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f)[{"stage": "k_emit", "g16": "k_emit_g16"}[args.emit]]
-        roofline_hbm["traffic"] = tr["dram_bytes_per_pair"] * P
-        roofline_hbm["traffic_source"] = tr["source"]
-    except Exception:
-        pass
-    # the dominant kernel of the step decides which of the two is THE roofline line
-    roofline = roofline_hbm if (emit_ms and (not dom_dp or emit_ms >= dom_dp["ms"])) else roofline_dp
 
-    # ---- whole files: read / inflate, GPU chain, deflate / write (N = 1, rank 0; reported separately) ----
+    # ---- whole files: read / inflate, GPU chain, deflate / write (rank 0 drives all GPUs of the job) ----
     files = None
-    if not args.no_files and world == 1:
+    if not args.no_files:
         try:
-            files = files_leg(prog, args.file_pairs)
+            files = files_leg(prog, args.file_pairs, args.file_pairs_gz, world, os.cpu_count() or 4)
         except Exception as exc:  # the headline numbers must not die with a full /tmp
             files = {"error": repr(exc)}
+    group.barrier()
 
     cpu = None
     if not args.no_cpu and world == 1:
@@ -456,16 +537,19 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; {B} resident batches x {P} pairs per GPU "
-                               f"(= {B * P} pairs), step = one batch; consecutive steps use different batches "
+        "config": {"workload": f"config2: synthetic 2x150 read pairs, cutseq {' '.join(ARGV)}; step = {B} resident batches x {P} pairs per GPU "
+                               f"(= {B * P} pairs); consecutive batches are different data "
                                f"({in_bytes(batches[0]) / 1e9:.2f} GB in each, far larger than the 126 MB L2, no flush needed); "
                                f"input form: {'raw FASTQ text, record index built on the device' if text_mode else 'host-parsed SoA'}",
                    "parallelism": f"dp{world} (contiguous index ranges per GPU, no collective on the data path)",
-                   "prefilter": not args.no_prefilter, "emit": args.emit, "parse": args.parse, "homo_dp": args.homo, "exact_stop": not args.no_exact_stop, "numa_node": numa_node},
-        "gcups": gcups_whole_chain, "cells_per_pair": cells_per_step / P,
-        "roofline": roofline, "roofline_dp": roofline_dp, "roofline_dp_executed": roofline_dp_executed, "roofline_hbm": roofline_hbm, "kernels": [{"kernel": n, "ms": t} for n, t in ktimes],
-        "dp_kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
+                   "prefilter": not args.no_prefilter, "emit": args.emit, "exact_stop": not args.no_exact_stop, "numa_node": numa_node},
+        "nominal_gcups": gcups_nominal, "cells_per_pair": cells_per_batch / P,
+        "roofline": roofline, "roofline_e2e": roofline_e2e, "roofline_dp_executed": roofline_dp_executed,
+        "int_peak_Gops": {"alu_only": alu_peak / 1e9, "alu_fma_mix": mixed_peak / 1e9},
+        "kernels": [{"kernel": n, "ms": t} for n, t in ktimes], "kernels_note": "one batch of the step, one stream, CUDA event after every kernel",
+        "dp_kernels": dp_kernels, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
         "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
+        "sources_sha256_16": src_hash,
     }
     sys.stdout.flush()
     os.write(result_fd, (json.dumps(line) + "\n").encode())

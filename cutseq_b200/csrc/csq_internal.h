@@ -76,6 +76,7 @@ struct AlignParams {
     DevOp pre[CSQ_MAX_PRE];
     // the adapter
     int32_t m, flags, reversed, trim_front, min_overlap, k, adapter_bit, homopolymer;
+    uint32_t one;          // == 1: multiplier of the adds that are to run as IMAD on the FMA pipe (opaque to ptxas)
     int32_t exact_stop;    // 1: leave the column loop at an error-free full match, as Aligner.locate does ("exact match, stop early")
     uint8_t thr[CSQ_MAX_ADAPTER + 1];  // thr[L] = floor(L * max_error_rate) with host doubles
     uint32_t peq[4][4];                // [A,C,G,T][word]: bit i-1 set <=> adapter[i-1] == letter

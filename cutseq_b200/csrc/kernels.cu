@@ -57,6 +57,12 @@ struct Best {
     int cost, origin, score, ref_stop, query_stop;
 };
 
+__device__ __forceinline__ uint32_t mad1(uint32_t a, uint32_t b, uint32_t c) {  // a * b + c on the FMA pipe (IMAD)
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ void init_cell(int i, int min_n, bool sir, bool siq, int& cost, int& origin) {
     if (!sir && !siq) {
         cost = max(i, min_n);
@@ -144,6 +150,7 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
     constexpr int NW = (M + 31) / 32;
     const int n = b - a;
     const int k = P.k;
+    const uint32_t one = P.one;
     const bool sir = P.flags & 1, siq = P.flags & 2, eir = P.flags & 4, eiq = P.flags & 8;
     int max_n = n, min_n = 0;
     if (!siq) max_n = min(n, M + k);
@@ -178,12 +185,16 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
         W[0] += row0_delta;
 #pragma unroll
         for (int i = 1; i <= M; i++) {
+            // Two integer pipes (B300_MICROARCH.md: IADD3 / LOP3 / VIMNMX on the ALU pipe, IMAD on the FMA pipe, one
+            // warp instruction per two cycles each).  The all-ALU form of this cell was 5 instructions = 10 cycles
+            // (VIADD, predicated VIADD, 2 x VIADDMNMX, LOP3); here the diagonal candidate and its mismatch surcharge
+            // run as mad.lo on the FMA pipe (the multiplier arrives as a kernel argument, a literal 1 would be folded
+            // back into VIADD), the ALU pipe keeps the two fused add+min and the priority clear: 3 ALU + 2 FMA.
             const uint32_t wl = W[i];
-            const uint32_t dd = (pm[(i - 1) >> 5] & (1u << ((i - 1) & 31))) ? D_MATCH : D_MIS;
-            const uint32_t cd = wd + dd;
-            const uint32_t cu = W[i - 1] + D_INS;
-            const uint32_t cl = wl + D_DEL;
-            W[i] = __vimin3_u32(cd, cu, cl) & PRIO_CLEAR;
+            uint32_t cd = mad1(wd, one, D_MATCH);
+            if (!(pm[(i - 1) >> 5] & (1u << ((i - 1) & 31)))) cd = mad1(cd, one, D_MIS - D_MATCH);
+            const uint32_t t = min(cd, W[i - 1] + D_INS);
+            W[i] = min(t, wl + D_DEL) & PRIO_CLEAR;
             wd = wl;
         }
         if (eiq && row_m_update(W[M], j, M, n, P, best) && P.exact_stop) {
@@ -677,6 +688,7 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
     constexpr int MH = M / 2;
     constexpr int PER_CTA = 64;  // entries per CTA: two lanes each
     const uint32_t FULLM = 0xffffffffu;
+    const uint32_t one = P.one;
     const int lane = threadIdx.x & 31, h = threadIdx.x & 1;
     uint32_t t = blockIdx.x * PER_CTA + (threadIdx.x >> 1), count = P.n;
     size_t list_base = 0;
@@ -785,7 +797,8 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
                                 left = p1[c - 1];
                                 diag = p2[c - 1];
                             }
-                            const uint32_t cell = __vimin3_u32(diag + d[c], p1[c] + D_INS, left + D_DEL) & PRIO_CLEAR;
+                            // diagonal add on the FMA pipe (IMAD), the two fused add+min and the clear on the ALU pipe
+                            const uint32_t cell = min(min(mad1(diag, one, d[c]), p1[c] + D_INS), left + D_DEL) & PRIO_CLEAR;
                             p2[c] = p1[c];
                             p1[c] = cell;
                             if (c == KC - 1) W[row] = cell;
@@ -821,7 +834,7 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
 #pragma unroll
                         for (int r = 1; r <= MH; r++) {
                             const uint32_t wl = W[r];
-                            W[r] = __vimin3_u32(wd + d0, W[r - 1] + D_INS, wl + D_DEL) & PRIO_CLEAR;
+                            W[r] = min(min(mad1(wd, one, d0), W[r - 1] + D_INS), wl + D_DEL) & PRIO_CLEAR;
                             wd = wl;
                         }
                         bnd[0] = W[MH];

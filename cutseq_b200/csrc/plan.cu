@@ -469,6 +469,7 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
     for (Segment& sg : mp.segs) {
         AlignParams ap = sg.ap;
         ap.exact_stop = (plan->flags & CSQ_PLAN_NO_EXACT_STOP) ? 0 : 1;
+        ap.one = 1u;
         ap.md = mate_dev(s, m);
         ap.n = n;
         ap.list = nullptr;
@@ -1063,6 +1064,75 @@ int csq_int_peak(int device, double* alu_ops_per_s, double* mixed_ops_per_s) {
     cudaFree(sink);
     if (alu_ops_per_s) *alu_ops_per_s = res[0];
     if (mixed_ops_per_s) *mixed_ops_per_s = res[1];
+    return 0;
+}
+
+// Measured ceiling of the host <-> device path for the end-to-end numbers: pinned host buffers, one stream per
+// direction, `reps` copies of bytes_h2d / bytes_d2h each.  mode 0: host -> device alone, 1: device -> host alone,
+// 2: both at once (what a pipelined csq_submit_text / csq_wait loop does).  Returns GB/s per direction (for mode 2
+// both are bytes moved in that direction over the time until BOTH streams have drained).
+int csq_pcie_peak(int device, uint64_t bytes_h2d, uint64_t bytes_d2h, int reps, int mode, double* h2d_gbs, double* d2h_gbs) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (reps < 1 || mode < 0 || mode > 2) return fail(CSQ_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    const bool up = mode != 1 && bytes_h2d > 0, down = mode != 0 && bytes_d2h > 0;
+    void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    cudaEvent_t e0 = nullptr, e_up = nullptr, e_down = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    if (up) {
+        step(cudaHostAlloc(&h_in, bytes_h2d, cudaHostAllocDefault));
+        step(cudaMalloc(&d_in, bytes_h2d));
+        if (e == cudaSuccess) memset(h_in, 0x41, bytes_h2d);
+    }
+    if (down) {
+        step(cudaHostAlloc(&h_out, bytes_d2h, cudaHostAllocDefault));
+        step(cudaMalloc(&d_out, bytes_d2h));
+        if (e == cudaSuccess) step(cudaMemset(d_out, 0x42, bytes_d2h));
+        if (e == cudaSuccess) memset(h_out, 0, bytes_d2h);  // touch the pages before the timed copies
+    }
+    step(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    step(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+    step(cudaEventCreate(&e0));
+    step(cudaEventCreate(&e_up));
+    step(cudaEventCreate(&e_down));
+    float ms_up = 0, ms_down = 0;
+    for (int pass = 0; pass < 2 && e == cudaSuccess; pass++) {  // pass 0 warms up (first-touch, page tables)
+        const int n = pass == 0 ? 1 : reps;
+        step(cudaDeviceSynchronize());
+        step(cudaEventRecord(e0, s_up));
+        if (down) step(cudaStreamWaitEvent(s_down, e0, 0));
+        for (int r = 0; r < n && e == cudaSuccess; r++) {
+            if (up) step(cudaMemcpyAsync(d_in, h_in, bytes_h2d, cudaMemcpyHostToDevice, s_up));
+            if (down) step(cudaMemcpyAsync(h_out, d_out, bytes_d2h, cudaMemcpyDeviceToHost, s_down));
+        }
+        step(cudaEventRecord(e_up, s_up));
+        step(cudaEventRecord(e_down, s_down));
+        step(cudaStreamSynchronize(s_up));
+        step(cudaStreamSynchronize(s_down));
+        if (e == cudaSuccess) {
+            cudaEventElapsedTime(&ms_up, e0, e_up);
+            cudaEventElapsedTime(&ms_down, e0, e_down);
+        }
+    }
+    if (e == cudaSuccess) {
+        const float both = ms_up > ms_down ? ms_up : ms_down;
+        const float t_up = mode == 2 ? both : ms_up, t_down = mode == 2 ? both : ms_down;
+        if (h2d_gbs) *h2d_gbs = up && t_up > 0 ? (double)bytes_h2d * reps / (t_up * 1e-3) / 1e9 : 0.0;
+        if (d2h_gbs) *d2h_gbs = down && t_down > 0 ? (double)bytes_d2h * reps / (t_down * 1e-3) / 1e9 : 0.0;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e_up) cudaEventDestroy(e_up);
+    if (e_down) cudaEventDestroy(e_down);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_down) cudaStreamDestroy(s_down);
+    if (h_in) cudaFreeHost(h_in);
+    if (h_out) cudaFreeHost(h_out);
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CSQ_ERR_NOMEM : CSQ_ERR_CUDA, "csq_pcie_peak: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -15,6 +15,7 @@
 // the stored state.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "csq_internal.h"
 #include "device_common.cuh"
@@ -243,6 +244,165 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
     append_survivor(P, list, list_count, pass, idx, bin, j0, lane);
 }
 
+
+// ---- k_prefilter_fs: the hot form (BACK and RightmostFront: flags 14, m <= 32) balanced over BOTH integer pipes ---------
+// On sm_100 LOP3 / SHF / IADD3 / VIMNMX issue on the ALU pipe and IMAD on the FMA pipe, each at one warp instruction
+// per two cycles and scheduler (B300_MICROARCH.md, "fma vs alu split"); k_prefilter<1,...> above spends ~17 of its 19
+// instructions per column on the ALU pipe and is bound by it (ncu: 85 % ALU, 64 % issue).  Here a column costs
+//   ALU: 7 LOP3 (the Myers / Hyyro recurrences) + 1 PRMT (character)                                      = 8
+//   FMA: 1 IMAD (the carry-propagating add) + 2 IMAD (<< 1) + 2 IMAD.HI (row-m deltas) + 1 IMAD (table address) = 6   + 1 LDS
+// * the adapter sits in the TOP m bits of the word (row m = bit 31); the low 32 - m bits are rows that match every
+//   character and start with vertical delta 0 - with a free read start (row 0 == 0 everywhere) they stay 0 for good
+//   and hand a horizontal delta of 0 to the adapter's first row, exactly what the boundary row does;
+// * the row-m horizontal deltas are bit 31 of Ph / Mh: mad.hi(x, 2, acc) == acc + (x >> 31) counts them on the FMA
+//   pipe, 16 columns at a time, instead of tracking the score and its minimum in every column.  A chunk can only
+//   hold a column with cost[m][j] <= thr[m] if  cost at its start - decrements in it <= thr[m]; only those chunks
+//   (the ones next to a real adapter copy) are walked again, column by column, from the saved vertical deltas;
+// * adds and shifts are written as mad.lo with multipliers that come in as kernel arguments, so that ptxas cannot
+//   fold them back into ALU-pipe forms.
+// Same necessary condition, same survivor lists, same column window as k_prefilter<1, REV, false, *>.
+__device__ __forceinline__ uint32_t imad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <bool REV>
+__global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ AlignParams P, uint32_t* __restrict__ list,
+                                                      uint32_t* __restrict__ list_count, const uint32_t one, const uint32_t two,
+                                                      const uint32_t four) {
+    __shared__ uint32_t lut[256];
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut);
+    const int m = P.m, sft = 32 - m;
+    const uint32_t low = sft ? ((1u << sft) - 1u) : 0u;  // the always-matching rows below the adapter's first row
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+        const int u = c & 0xDF;
+        const int li = u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : u == 'T' ? 3 : -1;
+        lut[c] = (li >= 0 ? (P.peq[li][0] << sft) : 0u) | low;
+    }
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < P.n;
+    bool pass = false;
+    unsigned int cells = 0;
+    int bin = 0;
+    uint32_t j0 = 0xFFFFu;
+    if (valid) {
+        ReadState st = P.first ? fresh_state(P.md.seq_len[idx]) : load_state(P.md.state + idx);
+        for (int q = 0; q < P.n_pre; q++) apply_scalar(P.pre[q], st);
+        store_state(P.md.state + idx, st);
+        const int k = P.k;
+        const int a = st.a, b = st.b, n = b - a;
+        const int max_n = n, min_n = 0;  // flags 14: read start and read end are free
+        cells = (unsigned int)(m * n);
+        uint32_t Pv = ~low, Mv = 0u;
+        int score = m;             // cost[m][0]
+        int smin = 0x7FFFFFFF;     // exact wherever it is <= thr[m]
+        const int T = (int)P.thr[m];
+        int fc = -1, jc = 0;
+        // one column without bookkeeping: returns Ph, Mh before the shift (bit 31 = horizontal delta of row m)
+        // character x of the chunk: PRMT picks the byte (ALU), the scaled table address is an IMAD (FMA pipe)
+        auto column = [&](const uint32_t (&w4)[4], int x, uint32_t& Ph, uint32_t& Mh) {
+            const uint32_t c = __byte_perm(w4[x >> 2], 0u, 0x4440u + (uint32_t)(x & 3));
+            uint32_t Eq;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"(imad_lo(c, four, lut_base)));
+            const uint32_t Xv = Eq | Mv;
+            const uint32_t Xh = (imad_lo(Eq & Pv, one, Pv) ^ Pv) | Eq;
+            Ph = Mv | ~(Xh | Pv);
+            Mh = Pv & Xh;
+            const uint32_t Ph1 = imad_lo(Ph, two, 0u), Mh1 = imad_lo(Mh, two, 0u);
+            Pv = Mh1 | ~(Xv | Ph1);
+            Mv = Ph1 & Xv;
+        };
+        auto chunk16 = [&](const uint32_t (&w4)[4]) {
+            const uint32_t Pv0 = Pv, Mv0 = Mv;
+            uint32_t up = 0, dn = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int x = REV ? 15 - i : i;
+                uint32_t Ph, Mh;
+                column(w4, x, Ph, Mh);
+                up = imad_hi(Ph, two, up);
+                dn = imad_hi(Mh, two, dn);
+            }
+            if (score - (int)dn <= T) {  // a column of this chunk may reach thr[m]: walk it again, column by column
+                Pv = Pv0;
+                Mv = Mv0;
+                int s = score;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int x = REV ? 15 - i : i;
+                    uint32_t Ph, Mh;
+                    column(w4, x, Ph, Mh);
+                    s += (int)(Ph >> 31) - (int)(Mh >> 31);
+                    smin = min(smin, s);
+                }
+                if (fc < 0 && smin <= T) fc = jc;
+            }
+            score += (int)up - (int)dn;
+            jc += 16;
+        };
+        const uint8_t* s = P.md.seq + P.md.seq_off[idx];
+        int rem = max_n - min_n;
+        const uint8_t* p = REV ? (s + b) : (s + a);  // REV: one past the next character
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (rem > 0) v = fetch16(REV ? p - 16 : p);
+        for (; rem >= 16; rem -= 16) {
+            p += REV ? -16 : 16;
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            if (rem > 16) v = fetch16(REV ? p - 16 : p);
+            chunk16(w4);
+        }
+        if (rem > 0) {
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 15; i++) {
+                if (i >= rem) break;
+                const int x = REV ? 15 - i : i;
+                uint32_t Ph, Mh;
+                column(w4, x, Ph, Mh);
+                score += (int)(Ph >> 31) - (int)(Mh >> 31);
+                smin = min(smin, score);
+            }
+            if (fc < 0 && smin <= T) fc = jc;
+        }
+        if (max_n > min_n && smin <= T) pass = true;
+        if (!pass) {  // last column (max_n == n): rows i >= first_i = 0 (REFERENCE_END), cost[0][n] = 0
+            int d = 0;
+            for (int i = 1; i <= m; i++) {
+                const int bt = sft + i - 1;
+                d += (int)((Pv >> bt) & 1u) - (int)((Mv >> bt) & 1u);
+                if (d <= k) {
+                    const int L = min(i, n + d);
+                    if (L >= P.min_overlap && d <= (int)P.thr[L]) pass = true;
+                }
+            }
+        }
+        if (!pass && P.matches) {
+            csq_match r;
+            r.found = r.ref_start = r.ref_stop = r.query_start = r.query_stop = r.score = r.errors = r.reserved = 0;
+            P.matches[idx] = r;
+        }
+        if (pass) {  // column window and survivor class, as in k_prefilter
+            const int jn = fc >= 0 ? fc : n;
+            const int w0 = max(min_n, jn - (m + 3 * k + 3));
+            j0 = (uint32_t)w0;
+            const int cols = max_n - w0;
+            const bool exact_copy = smin == 0 && P.exact_stop;
+            bin = exact_copy ? 3 : cols > 112 ? 0 : cols > 80 ? 1 : cols > 48 ? 2 : 4;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && cells) atomicAdd(P.counters + P.counter_index + (CNT_DP_CELLS - CNT_WITH_ADAPTERS), (unsigned long long)cells);
+    append_survivor(P, list, list_count, pass, idx, bin, j0, lane);
+}
+
 template <int NW, bool REV, bool SIR>
 void launch_pf(const AlignParams& p, uint32_t* list, uint32_t* list_count, dim3 grid, dim3 block, cudaStream_t stream) {
     if constexpr (NW == 1) {
@@ -335,6 +495,13 @@ cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t*
     const dim3 grid((p.n + 255) / 256), block(256);
     if (p.homopolymer && !p.reversed && (p.flags == 9 || p.flags == 6)) {  // NonInternalFront / NonInternalBack
         k_prefilter_homo<<<grid, block, 0, stream>>>(p, list, list_count);
+        return cudaGetLastError();
+    }
+    if (p.flags == 14 && p.m <= 32 && !getenv("CSQ_PREFILTER_V1")) {  // BACK / RightmostFront: the two-pipe form
+        if (p.reversed)
+            k_prefilter_fs<true><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u);
+        else
+            k_prefilter_fs<false><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u);
         return cudaGetLastError();
     }
     switch ((p.m + 31) / 32) {

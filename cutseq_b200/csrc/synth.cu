@@ -2,7 +2,18 @@
 // Record i depends only on (seed, first_index + i): any rank can regenerate any range.
 // Output: packed SoA batches in library-owned pinned host memory (csq_batch_in layout).
 // Host code only (multi-threaded); it feeds both the CUDA chain and the CPU oracle.
+#ifndef CSQ_SYNTH_NO_CUDA
 #include <cuda_runtime.h>
+#else
+// oracle/libsynth.so (g++ -x c++ -DCSQ_SYNTH_NO_CUDA): the same generator with plain host memory, so that the CPU arm
+// of bench.py (--impl reference) maps nothing of the product library
+#include <stdlib.h>
+static int cudaFreeHost(void*) { return 1; }
+static int cudaHostAlloc(void**, size_t, unsigned) { return 1; }
+static int cudaGetLastError() { return 0; }
+#define cudaSuccess 0
+#define cudaHostAllocDefault 0u
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>

@@ -54,6 +54,7 @@ def lib():
     L.csq_stats.argtypes = [vp, C.POINTER(A.csq_counters)]
     L.csq_locate_batch.argtypes = [i32, C.POINTER(A.csq_op), C.POINTER(A.csq_mate_in), u32, u32, vp]
     L.csq_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.csq_pcie_peak.argtypes = [i32, C.c_uint64, C.c_uint64, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.csq_bind_host_to_device.argtypes = [i32, C.POINTER(C.c_int)]
     L.csq_unbind_host.argtypes = []
     L.csq_device_count.argtypes = [C.POINTER(i32)]
@@ -337,6 +338,13 @@ def unbind_host() -> None:
 def int_peak(device: int = 0):
     a, b = C.c_double(), C.c_double()
     check(lib().csq_int_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def pcie_peak(device: int, bytes_h2d: int, bytes_d2h: int, reps: int = 4, mode: int = 2):
+    """Measured pinned-memory copy rates (GB/s): mode 0 host->device, 1 device->host, 2 both at once."""
+    a, b = C.c_double(), C.c_double()
+    check(lib().csq_pcie_peak(device, bytes_h2d, bytes_d2h, reps, mode, C.byref(a), C.byref(b)))
     return a.value, b.value
 
 

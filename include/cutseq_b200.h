@@ -277,6 +277,11 @@ int csq_locate_batch(int device, const csq_op* align_op, const csq_mate_in* read
  * 32-bit integer lane-ops per second for (0) ALU-pipe only, (1) ALU+FMA-pipe mix. */
 int csq_int_peak(int device, double* alu_ops_per_s, double* mixed_ops_per_s);
 
+/* Host <-> device copy ceiling used as the denominator of the end-to-end numbers: pinned buffers of the given
+ * sizes, `reps` copies, mode 0 = host->device alone, 1 = device->host alone, 2 = both directions at once (what the
+ * pipelined csq_submit_text / csq_wait loop does).  GB/s per direction; in mode 2 over the time both needed. */
+int csq_pcie_peak(int device, uint64_t bytes_h2d, uint64_t bytes_d2h, int reps, int mode, double* h2d_gbs, double* d2h_gbs);
+
 /* One process (or thread) per GPU: restrict the calling thread - and the threads and pinned buffers it creates
  * afterwards - to the CPUs / memory of the NUMA node the device's PCIe root port belongs to.  *numa_node = the
  * node, or -1 when nothing was changed (single node, no sysfs entry, cpuset without CPUs of that node).

@@ -27,7 +27,34 @@ def build(force: bool = False) -> str:
     hdr = os.path.join(HERE, "..", "include", "cutseq_b200.h")
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["make", "-s", "-C", HERE, "-B", "liboracle.so"])
+    ssrc = os.path.join(HERE, "..", "cutseq_b200", "csrc", "synth.cu")
+    sso = os.path.join(HERE, "libsynth.so")
+    if force or not os.path.exists(sso) or os.path.getmtime(sso) < os.path.getmtime(ssrc):
+        subprocess.check_call(["make", "-s", "-C", HERE, "-B", "libsynth.so"])
     return so
+
+
+_SYNTH = None
+
+
+def synth_batch(config: int, n_reads: int, first_index: int = 0, buffer: int = 0) -> A.csq_batch_in:
+    """bench.py's synthetic workload (cutseq_b200/csrc/synth.cu) from oracle/libsynth.so: the same generator built
+    without CUDA, for the CPU arm (which must not map the product library)."""
+    global _SYNTH
+    if _SYNTH is None:
+        so = os.path.join(HERE, "libsynth.so")
+        src = os.path.join(HERE, "..", "cutseq_b200", "csrc", "synth.cu")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", HERE, "-B", "libsynth.so"])
+        _SYNTH = C.CDLL(so)
+        _SYNTH.csq_synth_batch.argtypes = [C.POINTER(A.csq_synth), C.c_uint64, C.c_uint32, C.c_int, C.POINTER(A.csq_batch_in)]
+    defaults = {2: (20240419, 150, True), 3: (20240420, 150, True), 4: (20240421, 75, False), 5: (20240419, 150, True)}
+    seed, read_len, paired = defaults[config]
+    cfg = A.csq_synth(seed, read_len, int(paired), 2 if config == 5 else config)
+    b = A.csq_batch_in()
+    if _SYNTH.csq_synth_batch(C.byref(cfg), first_index, n_reads, buffer, C.byref(b)) != 0:
+        raise RuntimeError("synthetic generator failed")
+    return b
 
 
 def lib():

@@ -1,135 +1,151 @@
 #!/usr/bin/env python
 """End-to-end FILE benchmark (BASELINE.json config 5, single box): synthetic FASTQ files on disk ->
 csq_run_files -> trimmed FASTQ files, with the host-side cost reported separately
-(read+inflate+parse / GPU section / deflate+write), plain and .gz variants.
+(read+inflate / GPU section / deflate+write), plain and .gz variants, 1..N GPUs, output hashes.
 
-    python scripts/bench_files.py --pairs 2000000 --gpus 1 --threads 8 --out gpurun_out/files.json
+    python scripts/bench_files.py --pairs 20000000 --gpus 1 --threads 16 --out gpurun_out/files.json
+
+Also the fixture / hashing helpers of bench.py's files leg.
 """
 
 import argparse
-import ctypes as C
-import gzip
+import hashlib
 import json
 import os
 import shutil
+import struct
 import sys
 import tempfile
 import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-
-def write_fastq_from_batch(batch, paths, compress):
-    """Serialise a synthetic SoA batch to FASTQ files (csq_format_fastq); .gz = one gzip member per file, level 1."""
-    import subprocess
-
-    from cutseq_b200 import native
-
-    procs = []
-    for m, path in enumerate(paths):
-        text = native.format_fastq(batch, m)
-        plain = path[:-3] if compress else path
-        with open(plain, "wb") as f:
-            f.write(memoryview(text))
-        if compress:
-            procs.append(subprocess.Popen(["gzip", "-1", "-f", plain]))
-    for p in procs:
-        if p.wait() != 0:
-            raise RuntimeError("gzip failed")
+BLOCK_PAIRS = 4_000_000   # pairs generated at a time; larger fixtures repeat this block (trimming does not care)
+BGZF_PIECE = 0xFF00       # uncompressed bytes per BGZF member, as bgzip
 
 
-def host_probe(paths):
-    """What the host can do at best on this box: page-cache read of the input files (two threads, reused 4 MiB
-    buffers), line-end counting and memcpy speed - the floor under any host-side FASTQ reader."""
-    import threading
+def bgzf_member(piece: bytes, level: int = 1) -> bytes:
+    """One BGZF member (SAM/BAM specification 4.1): gzip header with the 'BC' extra field = member size - 1."""
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    body = c.compress(piece) + c.flush()
+    size = 18 + len(body) + 8
+    head = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", size - 1)
+    return head + body + struct.pack("<II", zlib.crc32(piece) & 0xFFFFFFFF, len(piece) & 0xFFFFFFFF)
+
+
+BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bgzf_compress(text, threads: int) -> bytes:
+    view = memoryview(text)
+    pieces = [view[o:o + BGZF_PIECE] for o in range(0, len(view), BGZF_PIECE)]
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        members = list(ex.map(lambda p: bgzf_member(bytes(p)), pieces, chunksize=64))
+    return b"".join(members)
+
+
+def write_fastq_from_soa(batch, paths):
+    """Serialise a synthetic SoA batch to plain FASTQ files (csq_format_fastq of the product library is NOT used here:
+    this also serves the CPU arm)."""
+    import ctypes as C
 
     import numpy as np
 
+    for m, path in enumerate(paths):
+        mi = batch.mate[m]
+        n = batch.n_reads
+        noff = np.ctypeslib.as_array(C.cast(mi.name_off, C.POINTER(C.c_uint32)), (n + 1,))
+        soff = np.ctypeslib.as_array(C.cast(mi.seq_off, C.POINTER(C.c_uint32)), (n,))
+        slen = np.ctypeslib.as_array(C.cast(mi.seq_len, C.POINTER(C.c_uint32)), (n,))
+        name = C.string_at(mi.name, mi.name_bytes)
+        seq = C.string_at(mi.seq, mi.seq_bytes)
+        qual = C.string_at(mi.qual, mi.seq_bytes)
+        with open(path, "wb") as f:
+            for i in range(n):
+                f.write(b"@" + name[noff[i]:noff[i + 1]] + b"\n" + seq[soff[i]:soff[i] + slen[i]] + b"\n+\n" + qual[soff[i]:soff[i] + slen[i]] + b"\n")
+
+
+def write_fixture(paths, pairs: int, compress: bool, threads: int):
+    """Config-2 FASTQ files of `pairs` pairs: blocks of up to 4 M generated pairs, the first block repeated (names
+    repeat too; both mates stay in step).  .gz = BGZF members of 0xFF00 bytes at level 1, then the BGZF EOF marker."""
     from cutseq_b200 import native
 
-    def read_all(path, out, i):
-        buf = bytearray(4 << 20)
-        n = 0
-        with open(path, "rb", buffering=0) as f:
-            while True:
-                k = f.readinto(buf)
-                if not k:
-                    break
-                n += k
-        out[i] = n
+    block = min(pairs, BLOCK_PAIRS)
+    reps, rest = divmod(pairs, block)
+    handles = [open(p, "wb") for p in paths]
+    try:
+        for n, times in ((block, reps), (rest, 1 if rest else 0)):
+            if not times:
+                continue
+            batch = native.synth_batch(2, n, first_index=0, buffer=14)
+            for m, f in enumerate(handles):
+                text = native.format_fastq(batch, m)
+                data = bgzf_compress(text, threads) if compress else memoryview(text)
+                for _ in range(times):
+                    f.write(data)
+        if compress:
+            for f in handles:
+                f.write(BGZF_EOF)
+    finally:
+        for f in handles:
+            f.close()
+        native.lib().csq_synth_free()
 
-    res = {}
-    sizes = [0] * len(paths)
-    t0 = time.time()
-    ths = [threading.Thread(target=read_all, args=(p, sizes, i)) for i, p in enumerate(paths)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    dt = time.time() - t0
-    res["page_cache_read_GBps_2_threads"] = sum(sizes) / dt / 1e9
-    a = np.frombuffer(open(paths[0], "rb").read(256 << 20), dtype=np.uint8)
-    t0 = time.time()
-    native.lib().csq_count_newlines(a.ctypes.data, a.size)
-    res["count_newlines_GBps_1_thread"] = a.size / (time.time() - t0) / 1e9
-    b = np.empty_like(a)
-    b[:] = a
-    t0 = time.time()
-    b[:] = a
-    res["memcpy_GBps_1_thread"] = a.size / (time.time() - t0) / 1e9
-    return res
+
+def hash_outputs(paths, gz: bool):
+    """sha256 of the (decompressed) bytes of every output file, one thread per file."""
+
+    def one(path):
+        h = hashlib.sha256()
+        if not os.path.exists(path):
+            return None
+        with open(path, "rb") as f:
+            if not gz:
+                while True:
+                    b = f.read(8 << 20)
+                    if not b:
+                        break
+                    h.update(b)
+            else:
+                d = zlib.decompressobj(31)
+                while True:
+                    b = f.read(4 << 20)
+                    if not b:
+                        break
+                    while b:
+                        h.update(d.decompress(b))
+                        if d.eof:  # next gzip member
+                            b = d.unused_data
+                            d = zlib.decompressobj(31)
+                        else:
+                            b = b""
+        return h.hexdigest()
+
+    with ThreadPoolExecutor(len(paths)) as ex:
+        return dict(zip([os.path.basename(p).split("_", 1)[1] for p in paths], ex.map(one, paths)))
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--pairs", type=int, default=4_000_000)
+    ap.add_argument("--pairs", type=int, default=8_000_000)
+    ap.add_argument("--pairs-gz", type=int, default=None)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--threads", type=int, default=8)
-    ap.add_argument("--batch-reads", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--out", default=None)
-    ap.add_argument("--tmp", default=None)
     ap.add_argument("--variants", default="plain,gz", help="comma separated: plain, gz")
     args = ap.parse_args()
     import bench
-    from cutseq_b200 import native
 
     prog = bench.takara_program()
-    tmp = tempfile.mkdtemp(dir=args.tmp)
-    results = []
-    try:
-        batch = native.synth_batch(2, args.pairs, first_index=0, buffer=0)
-        for variant in args.variants.split(","):
-            ext = ".fq.gz" if variant == "gz" else ".fq"
-            ins = [os.path.join(tmp, f"in_R{m}{ext}") for m in (1, 2)]
-            t0 = time.time()
-            write_fastq_from_batch(batch, ins, variant == "gz")
-            gen_s = time.time() - t0
-            outs = {"trimmed": [os.path.join(tmp, f"out_trimmed_R{m}{ext}") for m in (1, 2)],
-                    "short": [os.path.join(tmp, f"out_short_R{m}{ext}") for m in (1, 2)]}
-            for rep in range(2):  # second repetition: page cache warm
-                for v in outs.values():  # a fresh run writes new files (truncating GBs of old ones is charged to close())
-                    for q in v:
-                        if os.path.exists(q):
-                            os.remove(q)
-                t0 = time.time()
-                counters, timing = native.run_files(prog, ins, outs, gpus=args.gpus, threads=args.threads, batch_reads=args.batch_reads)
-                wall = time.time() - t0
-            probe = host_probe(ins) if variant == "plain" else None
-            in_bytes = sum(os.path.getsize(p) for p in ins)
-            out_bytes = sum(os.path.getsize(p) for v in outs.values() for p in v)
-            results.append({
-                "variant": variant, "pairs": args.pairs, "gpus": args.gpus, "host_threads": args.threads, "batch_reads": args.batch_reads,
-                "pairs_per_s": args.pairs / wall, "wall_s": wall, "input_bytes": in_bytes, "output_bytes": out_bytes,
-                "read_inflate_parse_s": timing.read_inflate, "gpu_h2d_kernels_d2h_s": timing.h2d_kernels_d2h, "gpu_kernels_s": timing.kernels,
-                "deflate_write_s": timing.write_deflate, "total_s": timing.total, "written_pairs": int(counters.written),
-                "fixture_generation_s": gen_s, "host_probe": probe,
-                "note": "stages overlap (reader thread, GPU workers, writer thread): the stage seconds are busy times, not a sum",
-            })
-            print(json.dumps(results[-1]))
-    finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+    v = args.variants.split(",")
+    res = bench.files_leg(prog, args.pairs if "plain" in v else 0, (args.pairs_gz or args.pairs) if "gz" in v else 0, args.gpus, args.threads)
+    print(json.dumps(res, indent=1))
     if args.out:
         with open(args.out, "w") as f:
-            json.dump(results, f, indent=1)
+            json.dump(res, f, indent=1)
 
 
 if __name__ == "__main__":
