@@ -62,15 +62,63 @@ __device__ __forceinline__ void store_state(ReadState* p, const ReadState& st) {
 }
 
 
-// 16 bytes from an arbitrary byte address: five aligned 32-bit loads and four funnel shifts.
-// Touches up to 3 bytes in front of q and 4 behind q + 16; the device pools are padded for it.
-__device__ __forceinline__ uint4 fetch16(const uint8_t* __restrict__ q) {
-    const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>((uintptr_t)q & ~(uintptr_t)3);
-    const uint32_t sh = ((uint32_t)(uintptr_t)q & 3u) * 8u;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                      __funnelshift_r(w3, w4, sh));
+// 16 bytes from an arbitrary byte address: TWO aligned 128-bit loads, a select network for the word offset and four
+// funnel shifts for the byte offset.  Every thread of a warp reads its own record, so a load instruction costs one
+// L1 wavefront per thread whatever its width: five 32-bit loads per 16 bytes (the first version) made the
+// thread-per-read kernels LSU bound (160 wavefronts per warp and 16 columns; ncu round 2), 128-bit loads move four
+// times the bytes per wavefront.  Touches the 32 aligned bytes around q .. q + 16; the device pools are padded for it.
+// the 16 bytes at byte offset o (0..15) of the 32-byte register window a | b
+__device__ __forceinline__ uint4 window16(const uint4& a, const uint4& b, uint32_t o) {
+    const bool s2 = (o & 8u) != 0, s1 = (o & 4u) != 0;
+    const uint32_t x0 = s2 ? a.z : a.x, x1 = s2 ? a.w : a.y, x2 = s2 ? b.x : a.z, x3 = s2 ? b.y : a.w, x4 = s2 ? b.z : b.x,
+                   x5 = s2 ? b.w : b.y;
+    const uint32_t y0 = s1 ? x1 : x0, y1 = s1 ? x2 : x1, y2 = s1 ? x3 : x2, y3 = s1 ? x4 : x3, y4 = s1 ? x5 : x4;
+    const uint32_t sh = (o & 3u) * 8u;
+    return make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh), __funnelshift_r(y2, y3, sh),
+                      __funnelshift_r(y3, y4, sh));
 }
+__device__ __forceinline__ uint4 fetch16(const uint8_t* __restrict__ q) {
+    const uint4* __restrict__ v = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
+    return window16(v[0], v[1], (uint32_t)(uintptr_t)q & 15u);
+}
+
+// byte i (0..15, run-time index) of a 16-byte register block
+__device__ __forceinline__ uint32_t byte_of(const uint4& v, uint32_t i) {
+    const uint32_t w = (i & 8u) ? ((i & 4u) ? v.w : v.z) : ((i & 4u) ? v.y : v.x);
+    return (w >> ((i & 3u) * 8u)) & 0xFFu;
+}
+
+// The characters of a read interval one at a time, forwards or backwards, fetched 16 at a time (the exact DP kernels
+// walk a column per character; a byte load per column was one L1 wavefront per thread and column).
+struct CharWalk {
+    const uint8_t* p;  // forwards: the next character; backwards: one past the next character
+    uint4 buf;
+    uint32_t have;     // characters left in buf
+    bool rev;
+    __device__ __forceinline__ void init(const uint8_t* first, bool backwards) {
+        p = first;
+        rev = backwards;
+        have = 0;
+        buf = make_uint4(0, 0, 0, 0);
+    }
+    __device__ __forceinline__ void need(uint32_t k) {  // at least k characters in buf (k <= 16)
+        if (have < k) {
+            buf = fetch16(rev ? p - 16 : p);
+            have = 16;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t k) const { return byte_of(buf, rev ? have - 1u - k : 16u - have + k); }  // k < have
+    __device__ __forceinline__ void advance(uint32_t k) {
+        have -= k;
+        p += rev ? -(int)k : (int)k;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        need(1);
+        const uint32_t c = peek(0);
+        advance(1);
+        return c;
+    }
+};
 
 struct RecordShape {
     uint32_t id_len, umi_len, seq_len, total;

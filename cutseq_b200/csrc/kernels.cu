@@ -172,12 +172,12 @@ __device__ __forceinline__ void dp_exact(const uint8_t* __restrict__ s, int a, i
     }
     Best best = {M + n + 1, 0, 0, M, n};
     const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
-    const int step = P.reversed ? -1 : 1;
-    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    CharWalk cw;  // read characters, 16 per fetch (a byte load per column made this kernel LSU bound)
+    cw.init(P.reversed ? (s + b - min_n) : (s + a + min_n), P.reversed != 0);
 
     bool cut_short = false;
-    for (int j = min_n + 1; j <= max_n; j++, p += step) {
-        const uint32_t c = *p;
+    for (int j = min_n + 1; j <= max_n; j++) {
+        const uint32_t c = cw.next();
         uint32_t pm[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) pm[w] = lut[c * NW + w];
@@ -229,11 +229,11 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
     }
     Best best = {m + n + 1, 0, 0, m, n};
     const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
-    const int step = P.reversed ? -1 : 1;
-    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    CharWalk cw;
+    cw.init(P.reversed ? (s + b - min_n) : (s + a + min_n), P.reversed != 0);
     bool exact_stop = false;
-    for (int j = min_n + 1; j <= max_n; j++, p += step) {
-        const uint32_t c = *p & 0xDFu;
+    for (int j = min_n + 1; j <= max_n; j++) {
+        const uint32_t c = cw.next() & 0xDFu;
         const int li = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
         uint32_t wd = W[0];
         W[0] += row0_delta;
@@ -744,8 +744,8 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
     }
     Best best = {M + n + 1, 0, 0, M, n};
     const uint32_t row0_delta = siq ? 1u : ((1u << COST_SHIFT) + (2u << SP_SHIFT));
-    const int step = P.reversed ? -1 : 1;
-    const uint8_t* p = P.reversed ? (s + b - 1 - min_n) : (s + a + min_n);
+    CharWalk cw;
+    cw.init(P.reversed ? (s + b - min_n) : (s + a + min_n), P.reversed != 0);
     const uint32_t letter = P.letter;
     int foreign = 0;
     bool cut_short = false, exact_halt = false;
@@ -767,9 +767,10 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
                 uint32_t d[KC];
                 int f = foreign;
                 if (block) {
+                    cw.need(KC);
 #pragma unroll
                     for (int c = 0; c < KC; c++) {
-                        const bool eq = ((uint32_t)p[c * step] & 0xDFu) == letter;
+                        const bool eq = (cw.peek(c) & 0xDFu) == letter;
                         d[c] = eq ? D_MATCH : D_MIS;
                         f += eq ? 0 : 1;
                     }
@@ -815,9 +816,10 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
                         }
                     }
                     j += KC;
-                    p += KC * step;
+                    cw.advance(KC);
                 } else {
-                    const bool eq = ((uint32_t)*p & 0xDFu) == letter;
+                    cw.need(1);
+                    const bool eq = (cw.peek(0) & 0xDFu) == letter;
                     bool go = true;
                     if (!siq) {
                         foreign += eq ? 0 : 1;
@@ -843,7 +845,7 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
                             running = false;
                         }
                         j += 1;
-                        p += step;
+                        cw.advance(1);
                     }
                 }
             }

@@ -520,8 +520,6 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st, cud
         CUDA_TRY(cudaEventRecord(s.ev_join, st2));
         CUDA_TRY(cudaStreamWaitEvent(st, s.ev_join, 0));
     }
-    if (s.text_mode)
-        CUDA_TRY(cudaMemcpyAsync(s.totals_host + 14, (uint8_t*)s.parse_misc.p + 16, 16, cudaMemcpyDeviceToHost, st));
     PairParams pp = pair_params(plan, s);
     FinishParams fp[2];
     for (int m = 0; m < 2; m++) {
@@ -534,6 +532,8 @@ int enqueue_front(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st, cud
     CUDA_TRY(csq_launch_tail(fp[0], fp[1], pp, st));
     plan->launches += n ? 1 : 0;
     if (kt) kt->mark("k_tail");
+    if (s.text_mode)  // parse errors: k_records' and k_tail's ('@' / '+' line starts)
+        CUDA_TRY(cudaMemcpyAsync(s.totals_host + 14, (uint8_t*)s.parse_misc.p + 16, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(csq_launch_scan(nblk, (const uint32_t*)s.block_tot.p, (const uint32_t*)s.block_cnt.p,
                              (unsigned long long*)s.block_off.p, (unsigned long long*)s.totals.p, st));
     plan->launches += 1;

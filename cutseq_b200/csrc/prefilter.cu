@@ -347,18 +347,38 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
             score += (int)up - (int)dn;
             jc += 16;
         };
+        // The characters come in as aligned 128-bit vectors, ONE load per 16 columns: the chunk at byte offset o of the
+        // window (lo | hi) is cut out in registers (window16), the window then slides by one vector - forwards
+        // (lo <- hi, hi <- next) or, for the reversed walk of RightmostFront, backwards (hi <- lo, lo <- previous).
+        // The vector for the chunk after the next one is in flight while 16 columns are computed.
         const uint8_t* s = P.md.seq + P.md.seq_off[idx];
         int rem = max_n - min_n;
-        const uint8_t* p = REV ? (s + b) : (s + a);  // REV: one past the next character
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (rem > 0) v = fetch16(REV ? p - 16 : p);
+        const uint8_t* q = REV ? (s + b - 16) : (s + a);  // first byte of the first chunk
+        const uint4* vp = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
+        const uint32_t o = (uint32_t)(uintptr_t)q & 15u;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (rem > 0) {
+            lo = vp[0];
+            hi = vp[1];
+        }
         for (; rem >= 16; rem -= 16) {
-            p += REV ? -16 : 16;
+            const uint4 v = window16(lo, hi, o);
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            if (rem > 16) v = fetch16(REV ? p - 16 : p);
+            if (rem > 16) {
+                if (REV) {
+                    vp -= 1;
+                    hi = lo;
+                    lo = vp[0];
+                } else {
+                    vp += 1;
+                    lo = hi;
+                    hi = vp[1];
+                }
+            }
             chunk16(w4);
         }
         if (rem > 0) {
+            const uint4 v = window16(lo, hi, o);
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int i = 0; i < 15; i++) {
@@ -450,11 +470,11 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
         cells = (unsigned int)(m * span);
         const bool from_end = (P.flags & 2) != 0;  // NonInternalBack: anchored at the read end
         const uint8_t* s = P.md.seq + P.md.seq_off[idx];
-        const uint8_t* p = from_end ? (s + b - 1) : (s + a);
-        const int step = from_end ? -1 : 1;
+        CharWalk cw;  // 16 characters per fetch, from the anchored end inwards
+        cw.init(from_end ? (s + b) : (s + a), from_end);
         int e = 0, l = 1;
-        for (; l <= span; l++, p += step) {
-            e += ((uint32_t)(*p & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
+        for (; l <= span; l++) {
+            e += ((cw.next() & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
             if (e > k) break;
             const int L = min(m, l + e);
             if (L >= P.min_overlap && e <= (int)P.thr[L]) {
@@ -464,12 +484,12 @@ __global__ void __launch_bounds__(256) k_prefilter_homo(const __grid_constant__ 
         }
         if (pass) {
             // DP columns the exact pass will walk: all `span` of them when the read start is free, else up to the
-            // column with the (k + 1)-th foreign character (dp_homo's early stop) - survivors are listed by that
+            // column with the (k + 1)-th foreign character (the exact DP's early stop) - survivors are listed by that
             // number so that the threads of a k_align warp finish together
             int cols = span;
             if (!from_end) {
-                for (l++, p += step; l <= span; l++, p += step) {
-                    e += ((uint32_t)(*p & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
+                for (l++; l <= span; l++) {
+                    e += ((cw.next() & 0xDFu) != (uint32_t)P.letter) ? 1 : 0;
                     if (e > k) break;
                 }
                 cols = min(l, span);

@@ -19,6 +19,12 @@ COLS = [
     ("l1tex__t_sector_hit_rate.pct", "l1hit%"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu%"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+    ("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_active", "lsu_wb%"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "ldg_req"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "ldg_sectors"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum", "lsu_wavefronts"),
 ]
 STALL = "smsp__average_warps_issue_stalled_"
 
