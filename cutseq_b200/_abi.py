@@ -43,6 +43,7 @@ PLAN_NO_PREFILTER = 2
 PLAN_ONE_STREAM = 64
 PLAN_EMIT_G16 = 256
 PLAN_NO_EXACT_STOP = 1024
+PLAN_GZIP_OUT = 4096
 
 
 class csq_op(C.Structure):

@@ -128,6 +128,44 @@ struct EmitParams {
     uint8_t* out[CSQ_N_DEST][2];
 };
 
+// ---- device gzip writer (gz_deflate.cu) ----
+#define GZ_THREADS 256
+#define GZ_RUN 127                       /* literals per thread; odd, so that the runs of a warp spread over the banks */
+#define GZ_PIECE (GZ_THREADS * GZ_RUN)   /* 32512 input bytes per member (a multiple of 16)                            */
+#define GZ_SLOT 32576                    /* bytes reserved per member before packing (stored piece + framing, 16 | it) */
+#define GZ_CODE_STRIDE 260               /* words per stream in GzParams.codes                                         */
+#define GZ_HDR_STRIDE 100                /* words per stream in GzParams.hdr: header bits, then their number           */
+
+struct GzParams {  // the six output streams (destination x mate) of one batch
+    const uint8_t* text[CSQ_N_DEST * 2];  // emitted FASTQ text
+    uint64_t bytes[CSQ_N_DEST * 2];
+    uint32_t first_member[CSQ_N_DEST * 2 + 1];  // members in front of every stream (ceil(bytes / GZ_PIECE) each)
+    uint32_t* hist;        // [6][256]
+    uint32_t* codes;       // [6][GZ_CODE_STRIDE]  code | length << 16 of literal / end-of-block
+    uint32_t* hdr;         // [6][GZ_HDR_STRIDE]
+    const uint32_t* crc_tab;  // [256]
+    const uint32_t* crc_pow;  // [GZ_THREADS]  x^(8 * GZ_RUN * k) mod P
+    uint8_t* slots;        // [members][GZ_SLOT]
+    uint32_t* msize;       // [members]
+    unsigned long long* moff;    // [members] offset inside the packed stream
+    unsigned long long* totals;  // [6] packed bytes per stream
+    uint8_t* packed[CSQ_N_DEST * 2];
+};
+cudaError_t csq_launch_gz(const GzParams& p, uint32_t n_members, cudaStream_t stream);
+void csq_gz_host_tables(uint32_t* crc_tab, uint32_t* crc_pow);
+
+// ---- device gzip reader (gz_inflate.cu) ----
+struct InflateParams {
+    const uint8_t* comp;     // the compressed members, back to back as in the file (readable 16 bytes past the end)
+    const uint32_t* moff;    // [n + 1] byte offset of every member in comp
+    const uint32_t* ooff;    // [n + 1] byte offset of every member's text in out (prefix sums of ISIZE)
+    uint32_t n_members;
+    uint8_t* out;
+    uint32_t* lines;         // nullable: '\n' per member
+    int32_t* status;         // atomicMin of (error kind + 16 * member index); INT_MAX when clean
+};
+cudaError_t csq_launch_inflate(const InflateParams& p, cudaStream_t stream);
+
 // word indices inside csq_counters viewed as uint64[]
 enum {
     CNT_N = 0, CNT_TOTAL_BP = 1, CNT_WRITTEN = 3, CNT_WRITTEN_BP = 4, CNT_TOO_SHORT = 6, CNT_UNTRIMMED = 7,

@@ -84,6 +84,11 @@ struct Slot {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // text batches (csq_submit_text): the FASTQ bytes as they came, and the record index k_records builds
     DevBuf text[2], qual_off[2], name_end[2], nl[2], tiles[2], masks[2], parse_misc;  // parse_misc: nl_total[2] (u32) | perr[2] (u64) at +16 | tile ticket[2] (u32) at +32 | any_cr[2] (u32) at +40
+    // device gzip writer (CSQ_PLAN_GZIP_OUT): per-member slots, member sizes / offsets, the packed streams
+    DevBuf gz_misc, gz_slots, gz_msize, gz_moff, gz_packed;  // gz_misc: hist | codes | hdr | totals
+    unsigned long long* gz_totals_host = nullptr;            // pinned: packed bytes per stream
+    const uint8_t* gz_packed_ptr[CSQ_N_DEST * 2] = {};
+    bool gz_ready = false;                                   // packed streams of the pending batch are on the device
     uint64_t text_bytes[2] = {0, 0};
     uint64_t first_record = 0;
     bool text_mode = false;
@@ -107,6 +112,7 @@ struct csq_plan {
     Slot slots[CSQ_N_SLOTS];
     unsigned long long* counters = nullptr;  // device csq_counters
     int* error_flag = nullptr;
+    uint32_t* gz_tables = nullptr;           // device: CRC-32 byte table [256] | fold operators [GZ_THREADS]
     uint64_t launches = 0;
 };
 
@@ -570,6 +576,54 @@ int enqueue_emit(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
     return 0;
 }
 
+// Device gzip writer behind the emitter (CSQ_PLAN_GZIP_OUT): the six text streams of the slot -> packed BGZF members;
+// the packed sizes go to pinned host memory.  Layout of gz_misc: hist [6][256] | codes [6][260] | hdr [6][100] | totals [8] (u64).
+int enqueue_gz(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
+    GzParams gp;
+    memset(&gp, 0, sizeof(gp));
+    uint32_t members = 0;
+    size_t packed_cap = 0;
+    size_t packed_off[CSQ_N_DEST * 2];
+    for (int d = 0; d < CSQ_N_DEST; d++)
+        for (int m = 0; m < 2; m++) {
+            const int i = d * 2 + m;
+            const uint64_t bytes = m < s.n_mates ? s.totals_host[i] : 0;
+            gp.text[i] = (const uint8_t*)s.out[d][m].p;
+            gp.bytes[i] = bytes;
+            gp.first_member[i] = members;
+            const uint32_t k = (uint32_t)((bytes + GZ_PIECE - 1) / GZ_PIECE);
+            members += k;
+            packed_off[i] = packed_cap;
+            packed_cap += (size_t)((bytes + 32ull * k + 63) & ~(uint64_t)63);  // a stored piece grows by 31 bytes
+        }
+    gp.first_member[CSQ_N_DEST * 2] = members;
+    int rc;
+    const size_t misc_words = 6 * 256 + 6 * GZ_CODE_STRIDE + 6 * GZ_HDR_STRIDE;
+    if ((rc = s.gz_misc.ensure(misc_words * 4 + 8 * 8))) return rc;
+    if ((rc = s.gz_slots.ensure((size_t)members * GZ_SLOT + 64))) return rc;
+    if ((rc = s.gz_msize.ensure((size_t)members * 4 + 16))) return rc;
+    if ((rc = s.gz_moff.ensure((size_t)members * 8 + 16))) return rc;
+    if ((rc = s.gz_packed.ensure(packed_cap + 64))) return rc;
+    uint32_t* misc = (uint32_t*)s.gz_misc.p;
+    gp.hist = misc;
+    gp.codes = misc + 6 * 256;
+    gp.hdr = gp.codes + 6 * GZ_CODE_STRIDE;
+    gp.totals = (unsigned long long*)(misc + misc_words);
+    gp.crc_tab = plan->gz_tables;
+    gp.crc_pow = plan->gz_tables + 256;
+    gp.slots = (uint8_t*)s.gz_slots.p;
+    gp.msize = (uint32_t*)s.gz_msize.p;
+    gp.moff = (unsigned long long*)s.gz_moff.p;
+    for (int i = 0; i < CSQ_N_DEST * 2; i++) gp.packed[i] = (uint8_t*)s.gz_packed.p + packed_off[i];
+    CUDA_TRY(cudaMemsetAsync(gp.totals, 0, 8 * 8, st));
+    CUDA_TRY(csq_launch_gz(gp, members, st));
+    plan->launches += members ? 5 : 0;
+    if (kt) kt->mark("k_gz");
+    CUDA_TRY(cudaMemcpyAsync(s.gz_totals_host, gp.totals, 8 * 8, cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < CSQ_N_DEST * 2; i++) s.gz_packed_ptr[i] = gp.packed[i];
+    return 0;
+}
+
 // FASTQ format errors found by k_records, worded like dnaio's FastqFormatError
 int check_parse_error(Slot& s) {
     if (!s.text_mode) return 0;
@@ -665,6 +719,12 @@ int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, 
     if (e == cudaSuccess) e = cudaMemset(plan->counters, 0, sizeof(csq_counters));
     if (e == cudaSuccess) e = cudaMalloc((void**)&plan->error_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(plan->error_flag, 0, sizeof(int));
+    if (e == cudaSuccess && (flags & CSQ_PLAN_GZIP_OUT)) {
+        std::vector<uint32_t> tab(256 + GZ_THREADS);
+        csq_gz_host_tables(tab.data(), tab.data() + 256);
+        e = cudaMalloc((void**)&plan->gz_tables, tab.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(plan->gz_tables, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
+    }
     for (int i = 0; i < CSQ_N_SLOTS && e == cudaSuccess; i++) {
         Slot& s = plan->slots[i];
         e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -674,6 +734,7 @@ int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, 
         for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&s.ev[k]);
         if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.totals_host, 16 * 8, cudaHostAllocDefault);
         if (e == cudaSuccess) memset(s.totals_host, 0, 16 * 8);
+        if (e == cudaSuccess && (flags & CSQ_PLAN_GZIP_OUT)) e = cudaHostAlloc((void**)&s.gz_totals_host, 8 * 8, cudaHostAllocDefault);
     }
     if (e != cudaSuccess) {
         rc = fail(CSQ_ERR_CUDA, "plan setup: %s", cudaGetErrorString(e));
@@ -705,10 +766,13 @@ void csq_plan_destroy(csq_plan* plan) {
         s.dest.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
         for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.totals_host) cudaFreeHost(s.totals_host);
+        if (s.gz_totals_host) cudaFreeHost(s.gz_totals_host);
+        s.gz_misc.release(); s.gz_slots.release(); s.gz_msize.release(); s.gz_moff.release(); s.gz_packed.release();
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (plan->counters) cudaFree(plan->counters);
     if (plan->error_flag) cudaFree(plan->error_flag);
+    if (plan->gz_tables) cudaFree(plan->gz_tables);
     delete plan;
 }
 
@@ -774,40 +838,59 @@ int csq_wait(csq_plan* plan, int slot) {
     if (!s.pending) return fail(CSQ_ERR_INVALID, "nothing submitted on slot %d", slot);
     csq_batch_out* out = s.pending;
     s.pending = nullptr;
-    CUDA_TRY(cudaStreamSynchronize(s.stream));
-    int rc = check_device_error(s);
-    if (rc) return rc;
-    for (int d = 0; d < CSQ_N_DEST; d++)
-        for (int m = 0; m < 2; m++) {
-            csq_text_out& t = out->text[d][m];
-            t.bytes = s.totals_host[d * 2 + m];
-            t.records = (m < s.n_mates) ? s.totals_host[8 + d] : 0;
-        }
-    for (int d = 0; d < CSQ_N_DEST; d++)
-        for (int m = 0; m < 2; m++) {
-            csq_text_out& t = out->text[d][m];
-            if (t.bytes > t.capacity || (t.bytes && !t.data)) {
-                // every .bytes field already holds the needed size: the caller may enlarge its buffers
-                // and call csq_wait() again for this slot
-                s.pending = out;
-                return fail(CSQ_ERR_CAPACITY, "output buffer [%d][%d] holds %llu bytes, %llu needed", d, m,
-                            (unsigned long long)t.capacity, (unsigned long long)t.bytes);
+    const bool gz = (plan->flags & CSQ_PLAN_GZIP_OUT) != 0;
+    int rc;
+    // every .bytes field holds the needed size when a buffer is too small: the caller may enlarge its buffers and call
+    // csq_wait() again for this slot
+    auto capacity_ok = [&]() -> int {
+        for (int d = 0; d < CSQ_N_DEST; d++)
+            for (int m = 0; m < 2; m++) {
+                csq_text_out& t = out->text[d][m];
+                if (t.bytes > t.capacity || (t.bytes && !t.data)) {
+                    s.pending = out;
+                    return fail(CSQ_ERR_CAPACITY, "output buffer [%d][%d] holds %llu bytes, %llu needed", d, m,
+                                (unsigned long long)t.capacity, (unsigned long long)t.bytes);
+                }
             }
+        return 0;
+    };
+    if (!s.gz_ready) {
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        if ((rc = check_device_error(s))) return rc;
+        for (int d = 0; d < CSQ_N_DEST; d++)
+            for (int m = 0; m < 2; m++) {
+                csq_text_out& t = out->text[d][m];
+                t.bytes = s.totals_host[d * 2 + m];
+                t.records = (m < s.n_mates) ? s.totals_host[8 + d] : 0;
+            }
+        if (!gz && (rc = capacity_ok())) return rc;
+        if ((rc = size_outputs(s))) return rc;
+        CUDA_TRY(cudaEventRecord(s.ev[3], s.stream));
+        if ((rc = enqueue_emit(plan, s, nullptr, s.stream))) return rc;
+        if (gz) {
+            // the text never leaves the device: members are encoded there, their packed sizes come back first
+            if ((rc = enqueue_gz(plan, s, nullptr, s.stream))) return rc;
+            CUDA_TRY(cudaEventRecord(s.ev[4], s.stream));
+            CUDA_TRY(cudaStreamSynchronize(s.stream));
+            s.gz_ready = true;
+        } else {
+            CUDA_TRY(cudaEventRecord(s.ev[4], s.stream));
         }
-    if ((rc = size_outputs(s))) return rc;
-    CUDA_TRY(cudaEventRecord(s.ev[3], s.stream));
-    if ((rc = enqueue_emit(plan, s, nullptr, s.stream))) return rc;
-    CUDA_TRY(cudaEventRecord(s.ev[4], s.stream));
+    }
+    if (gz) {
+        for (int d = 0; d < CSQ_N_DEST; d++)
+            for (int m = 0; m < 2; m++) out->text[d][m].bytes = m < s.n_mates ? s.gz_totals_host[d * 2 + m] : 0;
+        if ((rc = capacity_ok())) return rc;
+        s.gz_ready = false;
+    }
     for (int d = 0; d < CSQ_N_DEST; d++)
         for (int m = 0; m < s.n_mates; m++) {
             csq_text_out& t = out->text[d][m];
-            if (t.bytes) CUDA_TRY(cudaMemcpyAsync(t.data, s.out[d][m].p, t.bytes, cudaMemcpyDeviceToHost, s.stream));
+            const void* src = gz ? (const void*)s.gz_packed_ptr[d * 2 + m] : s.out[d][m].p;
+            if (t.bytes) CUDA_TRY(cudaMemcpyAsync(t.data, src, t.bytes, cudaMemcpyDeviceToHost, s.stream));
         }
-    // k_emit compares the mate ids (PairedEndRenamer) while it copies them: fetch the flag again
-    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 13, plan->error_flag, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaEventRecord(s.ev[5], s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
-    if ((rc = check_device_error(s, 13))) return rc;
     float h2d = 0, front = 0, emit = 0, d2h = 0;
     cudaEventElapsedTime(&h2d, s.ev[0], s.ev[1]);
     cudaEventElapsedTime(&front, s.ev[1], s.ev[2]);

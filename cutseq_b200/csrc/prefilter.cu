@@ -249,15 +249,13 @@ __global__ void __launch_bounds__(256) k_prefilter(const __grid_constant__ Align
 // On sm_100 LOP3 / SHF / IADD3 / VIMNMX issue on the ALU pipe and IMAD on the FMA pipe, each at one warp instruction
 // per two cycles and scheduler (B300_MICROARCH.md, "fma vs alu split"); k_prefilter<1,...> above spends ~17 of its 19
 // instructions per column on the ALU pipe and is bound by it (ncu: 85 % ALU, 64 % issue).  Here a column costs
-//   ALU: 7 LOP3 (the Myers / Hyyro recurrences) + 1 PRMT (character)                                      = 8
-//   FMA: 1 IMAD (the carry-propagating add) + 2 IMAD (<< 1) + 2 IMAD.HI (row-m deltas) + 1 IMAD (table address) = 6   + 1 LDS
+//   ALU: 7 LOP3 (the Myers / Hyyro recurrences) + 1 PRMT (character) + 1 VIMNMX (running minimum of row m)      = 9
+//   FMA: 1 IMAD (the carry-propagating add) + 2 IMAD (<< 1) + 2 IMAD.HI + 1 IMAD (row-m cost) + 1 IMAD (table address) = 7   + 1 LDS
 // * the adapter sits in the TOP m bits of the word (row m = bit 31); the low 32 - m bits are rows that match every
 //   character and start with vertical delta 0 - with a free read start (row 0 == 0 everywhere) they stay 0 for good
 //   and hand a horizontal delta of 0 to the adapter's first row, exactly what the boundary row does;
 // * the row-m horizontal deltas are bit 31 of Ph / Mh: mad.hi(x, 2, acc) == acc + (x >> 31) counts them on the FMA
-//   pipe, 16 columns at a time, instead of tracking the score and its minimum in every column.  A chunk can only
-//   hold a column with cost[m][j] <= thr[m] if  cost at its start - decrements in it <= thr[m]; only those chunks
-//   (the ones next to a real adapter copy) are walked again, column by column, from the saved vertical deltas;
+//   pipe, and cost[m][j] - m = up - dn is one more mad.lo; only the running minimum is an ALU instruction;
 // * adds and shifts are written as mad.lo with multipliers that come in as kernel arguments, so that ptxas cannot
 //   fold them back into ALU-pipe forms.
 // Same necessary condition, same survivor lists, same column window as k_prefilter<1, REV, false, *>.
@@ -275,7 +273,7 @@ __device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b, uint32_t c) 
 template <bool REV>
 __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ AlignParams P, uint32_t* __restrict__ list,
                                                       uint32_t* __restrict__ list_count, const uint32_t one, const uint32_t two,
-                                                      const uint32_t four) {
+                                                      const uint32_t four, const uint32_t minus_one) {
     __shared__ uint32_t lut[256];
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut);
     const int m = P.m, sft = 32 - m;
@@ -301,8 +299,7 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
         const int max_n = n, min_n = 0;  // flags 14: read start and read end are free
         cells = (unsigned int)(m * n);
         uint32_t Pv = ~low, Mv = 0u;
-        int score = m;             // cost[m][0]
-        int smin = 0x7FFFFFFF;     // exact wherever it is <= thr[m]
+        int smin = 0x7FFFFFFF;     // minimum over the columns of cost[m][j] - m
         const int T = (int)P.thr[m];
         int fc = -1, jc = 0;
         // one column without bookkeeping: returns Ph, Mh before the shift (bit 31 = horizontal delta of row m)
@@ -319,9 +316,12 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
             Pv = Mh1 | ~(Xv | Ph1);
             Mv = Ph1 & Xv;
         };
+        // 16 columns: the row-m cost of every column is m + up - dn (running counts of the +1 / -1 horizontal deltas of
+        // row m, bit 31 of Ph / Mh, kept by mad.hi on the FMA pipe); its running minimum costs one ALU instruction.
+        // (A first form only counted per chunk and re-walked "suspicious" chunks column by column: one suspicious
+        // lane makes its whole warp walk again, 24 instead of 17 instructions per column on average.)
+        uint32_t up = 0, dn = 0;
         auto chunk16 = [&](const uint32_t (&w4)[4]) {
-            const uint32_t Pv0 = Pv, Mv0 = Mv;
-            uint32_t up = 0, dn = 0;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int x = REV ? 15 - i : i;
@@ -329,22 +329,9 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
                 column(w4, x, Ph, Mh);
                 up = imad_hi(Ph, two, up);
                 dn = imad_hi(Mh, two, dn);
+                smin = min(smin, (int)imad_lo(dn, minus_one, up));
             }
-            if (score - (int)dn <= T) {  // a column of this chunk may reach thr[m]: walk it again, column by column
-                Pv = Pv0;
-                Mv = Mv0;
-                int s = score;
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int x = REV ? 15 - i : i;
-                    uint32_t Ph, Mh;
-                    column(w4, x, Ph, Mh);
-                    s += (int)(Ph >> 31) - (int)(Mh >> 31);
-                    smin = min(smin, s);
-                }
-                if (fc < 0 && smin <= T) fc = jc;
-            }
-            score += (int)up - (int)dn;
+            if (fc < 0 && smin <= T - m) fc = jc;
             jc += 16;
         };
         // The characters come in as aligned 128-bit vectors, ONE load per 16 columns: the chunk at byte offset o of the
@@ -386,11 +373,13 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
                 const int x = REV ? 15 - i : i;
                 uint32_t Ph, Mh;
                 column(w4, x, Ph, Mh);
-                score += (int)(Ph >> 31) - (int)(Mh >> 31);
-                smin = min(smin, score);
+                up = imad_hi(Ph, two, up);
+                dn = imad_hi(Mh, two, dn);
+                smin = min(smin, (int)imad_lo(dn, minus_one, up));
             }
-            if (fc < 0 && smin <= T) fc = jc;
+            if (fc < 0 && smin <= T - m) fc = jc;
         }
+        smin = smin == 0x7FFFFFFF ? smin : smin + m;  // from "relative to cost[m][0] = m" to the cost itself
         if (max_n > min_n && smin <= T) pass = true;
         if (!pass) {  // last column (max_n == n): rows i >= first_i = 0 (REFERENCE_END), cost[0][n] = 0
             int d = 0;
@@ -519,9 +508,9 @@ cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t*
     }
     if (p.flags == 14 && p.m <= 32 && !getenv("CSQ_PREFILTER_V1")) {  // BACK / RightmostFront: the two-pipe form
         if (p.reversed)
-            k_prefilter_fs<true><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u);
+            k_prefilter_fs<true><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
         else
-            k_prefilter_fs<false><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u);
+            k_prefilter_fs<false><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
         return cudaGetLastError();
     }
     switch ((p.m + 31) / 32) {

@@ -77,6 +77,8 @@ def lib():
         L.csq_after_kth_newline.restype = C.c_uint64
         L.csq_gunzip_mem.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, u64p]
         L.csq_format_fastq.argtypes = [C.POINTER(A.csq_mate_in), u32, vp, C.c_uint64, u64p]
+        L.csq_gz_deflate_host.argtypes = [vp, C.c_uint64, vp, C.c_uint64, u64p]
+        L.csq_gz_inflate_host.argtypes = [vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]
     if hasattr(L, "csq_synth_batch"):
         L.csq_synth_batch.argtypes = [C.POINTER(A.csq_synth), C.c_uint64, u32, i32, C.POINTER(A.csq_batch_in)]
         L.csq_synth_free.restype = None
@@ -339,6 +341,24 @@ def int_peak(device: int = 0):
     a, b = C.c_double(), C.c_double()
     check(lib().csq_int_peak(device, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def gz_deflate_host(text: bytes) -> bytes:
+    """The device gzip writer's algorithm on the host (``csq_gz_deflate_host``): text -> concatenated BGZF members."""
+    src = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(1, dtype=np.uint8)
+    out = np.empty(len(text) + (len(text) // 32000 + 2) * 64 + 64, dtype=np.uint8)
+    n = C.c_uint64()
+    check(lib().csq_gz_deflate_host(src.ctypes.data, len(text), out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def gz_inflate_host(data: bytes, capacity: int):
+    """The device gzip reader's decoder on the host (``csq_gz_inflate_host``): BGZF members -> (text, line ends)."""
+    src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, dtype=np.uint8)
+    out = np.empty(max(capacity, 1), dtype=np.uint8)
+    n, lines = C.c_uint64(), C.c_uint64()
+    check(lib().csq_gz_inflate_host(src.ctypes.data, len(data), out.ctypes.data, capacity, C.byref(n), C.byref(lines)))
+    return out[: n.value].tobytes(), lines.value
 
 
 def pcie_peak(device: int, bytes_h2d: int, bytes_d2h: int, reps: int = 4, mode: int = 2):

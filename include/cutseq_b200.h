@@ -222,6 +222,10 @@ typedef struct csq_plan csq_plan;
 #define CSQ_PLAN_ONE_STREAM 64u   /* run the chains of mate 1 and mate 2 on one stream (default: side by side) */
 #define CSQ_PLAN_EMIT_G16 256u    /* emit FASTQ text with the direct (global -> global) k_emit, 16 lanes per record, instead of
                                      the default k_emit_stage (staged through shared memory); A/B runs, initcheck runs   */
+#define CSQ_PLAN_GZIP_OUT 4096u   /* csq_wait delivers every output stream as concatenated gzip members (BGZF framing, <= 64 KiB
+                                     each, dynamic-Huffman DEFLATE encoded on the device) instead of FASTQ text:
+                                     csq_text_out.bytes = compressed bytes; what xopen does behind the reference's
+                                     default .fastq.gz outputs (run.py:1058-1093), without the text crossing PCIe    */
 #define CSQ_PLAN_NO_EXACT_STOP 1024u /* exact DP walks every column even after an error-free full match (results are the same; A/B) */
 /* (flag values 8, 16, 32, 128, 512, 2048 selected slower kernel variants in round 1 - per-pair / 8- / 32-lane emitters,
  * one-pass parse, one-lane / one-column homopolymer DP; those kernels were removed after measurement and the bits are ignored) */
@@ -321,6 +325,11 @@ uint64_t csq_count_newlines(const uint8_t* text, uint64_t n_bytes);
 uint64_t csq_after_kth_newline(const uint8_t* text, uint64_t n_bytes, uint64_t k);
 /* gzip data in memory -> dst, decoded in pieces of `piece` bytes with the library's own inflate (tests). */
 int csq_gunzip_mem(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t piece, uint64_t* out_n);
+/* The device gzip writer's algorithm run on the host, piece by piece (CPU tests of the code construction, the block
+ * header, the bit packing and the CRC folding): text -> concatenated BGZF members. */
+int csq_gz_deflate_host(const uint8_t* text, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_n);
+/* The device gzip reader's decoder run on the host, member by member (CPU tests): BGZF members -> text; *lines = '\n' found. */
+int csq_gz_inflate_host(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t* out_n, uint64_t* lines);
 /* SoA batch -> FASTQ text of one mate ("@name\nseq\n+\nqual\n"), for tests and benchmarks. */
 int csq_format_fastq(const csq_mate_in* mate, uint32_t n_reads, uint8_t* out, uint64_t capacity,
                      uint64_t* bytes);
