@@ -100,6 +100,15 @@ class csq_batch_text(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_mates", C.c_uint32), ("first_record", C.c_uint64), ("mate", csq_text_in * 2)]
 
 
+class csq_bgzf_in(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("bytes", C.c_uint64), ("member_off", C.c_void_p), ("text_off", C.c_void_p),
+                ("n_members", C.c_uint32), ("skip_lines", C.c_uint32), ("append_newline", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class csq_batch_bgzf(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_mates", C.c_uint32), ("first_record", C.c_uint64), ("mate", csq_bgzf_in * 2)]
+
+
 class csq_text_out(C.Structure):
     _fields_ = [("data", C.c_void_p), ("capacity", C.c_uint64), ("bytes", C.c_uint64), ("records", C.c_uint64)]
 

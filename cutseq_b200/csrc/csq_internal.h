@@ -60,6 +60,11 @@ struct ParseParams {  // FASTQ text of one mate -> record index (parse.cu)
     uint32_t *seq_off, *qual_off, *seq_len, *name_off, *name_end;
     unsigned long long* perr;  // smallest (record << 3 | kind) of a malformed record, ~0 when clean
     uint32_t* any_cr;          // [1] set by k_nl_count when the text holds a '\r' anywhere (CRLF files)
+    // BGZF batches: the text is what a run of whole members inflates to, the batch's records sit somewhere inside -
+    // `skip` line ends lie in front of the first record (its start is left in *first_off by k_nl_index), lines behind
+    // the 4 n of the batch are ignored
+    uint32_t skip;
+    uint32_t* first_off;       // [1] byte offset of the first record (0 when skip == 0)
 };
 
 struct AlignParams {

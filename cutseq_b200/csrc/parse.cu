@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(1024) k_tile_scan(uint32_t n_tiles, uint32_t* 
 // Pass 2 reads only the masks: thread t of a tile owns the 64 bytes at 64 t (four masks = one 64-bit word),
 // ranks its line ends by a CTA-wide scan and writes their byte offsets, nl[r] = offset of the r-th '\n'.
 __global__ void __launch_bounds__(TILE_THREADS) k_nl_index(const uint16_t* __restrict__ masks, const uint32_t* __restrict__ tile_base,
-                                                           uint32_t* __restrict__ nl, uint32_t nl_cap) {
+                                                           uint32_t* __restrict__ nl, uint32_t nl_cap, uint32_t skip,
+                                                           uint32_t* __restrict__ first_off) {
     __shared__ uint32_t wsum[TILE_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long m = reinterpret_cast<const unsigned long long*>(masks + (size_t)blockIdx.x * TILE_CHUNKS)[threadIdx.x];
@@ -191,7 +192,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_nl_index(const uint16_t* __res
     while (m) {
         const int bit = __ffsll((long long)m) - 1;
         m &= m - 1;
-        if (r < nl_cap) nl[r] = off + (uint32_t)bit;
+        // line end r of the text is line end r - skip of the batch; the one in front of it marks the first record
+        if (r >= skip && r - skip < nl_cap) nl[r - skip] = off + (uint32_t)bit;
+        if (r + 1 == skip) first_off[0] = off + (uint32_t)bit + 1u;
         r++;
     }
 }
@@ -205,7 +208,8 @@ __device__ __forceinline__ void report(unsigned long long* perr, uint32_t rec, i
 
 __global__ void __launch_bounds__(256) k_records(const ParseParams P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool count_ok = P.nl_total[0] == 4u * P.n;
+    // plain text batches hold exactly their records; BGZF batches may hold more lines on either side
+    const bool count_ok = P.first_off ? P.nl_total[0] >= P.skip + 4u * P.n : P.nl_total[0] == 4u * P.n;
     if (i == 0 && !count_ok) report(P.perr, 0, PERR_COUNT);
     if (i >= P.n) return;
     if (!count_ok) {  // nl[] is not fully defined: every record becomes an empty one, the host rejects the batch
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(256) k_records(const ParseParams P) {
     // fetches the header and the end of the bases anyway (this kernel used to pull ~5 DRAM sectors per record, 93 %
     // of the text, for six bytes).
     const uint4 e = reinterpret_cast<const uint4*>(P.nl)[i];  // the four line ends of record i
-    uint32_t s0 = i ? P.nl[4u * i - 1] + 1u : 0u;
+    uint32_t s0 = i ? P.nl[4u * i - 1] + 1u : (P.first_off ? P.first_off[0] : 0u);
     uint32_t e0 = e.x, e1 = e.y, e3 = e.w;
     const uint32_t s1 = e.x + 1, s3 = e.z + 1;
     if (P.any_cr[0]) {
@@ -263,7 +267,11 @@ cudaError_t csq_launch_parse(const ParseParams& p, void* tile_buf, uint16_t* mas
         if (e != cudaSuccess) return e;
         k_nl_count<<<tiles, TILE_THREADS, 0, stream>>>(p.text, p.bytes, masks, tile_cnt, p.any_cr);
         k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_cnt, p.nl_total);
-        k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(masks, tile_cnt, p.nl, 4u * p.n);
+        if (p.first_off) {
+            e = cudaMemsetAsync(p.first_off, 0, 4, stream);
+            if (e != cudaSuccess) return e;
+        }
+        k_nl_index<<<tiles, TILE_THREADS, 0, stream>>>(masks, tile_cnt, p.nl, 4u * p.n, p.skip, p.first_off);
     } else {
         cudaError_t e = cudaMemsetAsync(p.nl_total, 0, 4, stream);
         if (e != cudaSuccess) return e;

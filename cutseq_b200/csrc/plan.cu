@@ -89,6 +89,10 @@ struct Slot {
     unsigned long long* gz_totals_host = nullptr;            // pinned: packed bytes per stream
     const uint8_t* gz_packed_ptr[CSQ_N_DEST * 2] = {};
     bool gz_ready = false;                                   // packed streams of the pending batch are on the device
+    DevBuf comp[2], gz_idx[2], gz_lines;   // BGZF batches: compressed members, member / text offsets, line ends per member
+    int32_t* inflate_status = nullptr;     // device: smallest (error kind + 16 * member), INT_MAX when clean
+    uint32_t skip_lines[2] = {0, 0};
+    bool bgzf_mode = false;
     uint64_t text_bytes[2] = {0, 0};
     uint64_t first_record = 0;
     bool text_mode = false;
@@ -348,6 +352,7 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
     s.n_mates = plan->n_mates;
     s.front_done = false;
     s.text_mode = true;
+    s.bgzf_mode = false;
     s.first_record = in->first_record;
     int rc;
     for (int m = 0; m < plan->n_mates; m++) {
@@ -376,12 +381,84 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
     return ensure_common(plan, s, n);
 }
 
+// One mate's BGZF members -> device, inflated into the slot's text buffer (k_gz_inflate, one thread per member).
+// lines_dev != nullptr: also the line ends per member.  The text buffer is laid out as for csq_submit_text.
+int inflate_mate(csq_plan* plan, Slot& s, int m, const csq_bgzf_in& bi, uint32_t* lines_dev, cudaStream_t st) {
+    if (bi.n_members && (!bi.data || !bi.member_off || !bi.text_off)) return fail(CSQ_ERR_INVALID, "mate %d: null BGZF arrays", m + 1);
+    const uint32_t nm = bi.n_members;
+    const uint64_t text_bytes = nm ? bi.text_off[nm] : 0, comp_bytes = nm ? bi.member_off[nm] : 0;
+    if (comp_bytes > bi.bytes) return fail(CSQ_ERR_INVALID, "mate %d: member offsets run past the data", m + 1);
+    if (text_bytes + 1 >= (1ull << 32) - 4096 || comp_bytes >= (1ull << 32)) return fail(CSQ_ERR_LIMIT, "batch text must stay below 4 GiB");
+    const uint64_t bytes = text_bytes + (bi.append_newline ? 1 : 0);
+    s.text_bytes[m] = bytes;
+    const size_t padded = (size_t)((bytes + 63) & ~(uint64_t)63);
+    int rc;
+    if ((rc = s.text[m].ensure(TEXT_FRONT_PAD + padded + 128))) return rc;
+    if ((rc = s.comp[m].ensure((size_t)comp_bytes + 64))) return rc;
+    if ((rc = s.gz_idx[m].ensure(((size_t)nm + 1) * 8 + 16))) return rc;
+    uint8_t* base = (uint8_t*)s.text[m].p;
+    uint32_t* moff = (uint32_t*)s.gz_idx[m].p;
+    uint32_t* ooff = moff + nm + 1;
+    CUDA_TRY(cudaMemsetAsync(base, 0, TEXT_FRONT_PAD, st));
+    CUDA_TRY(cudaMemsetAsync(base + TEXT_FRONT_PAD + (bytes & ~(uint64_t)63), 0, padded - (bytes & ~(uint64_t)63) + 128, st));
+    if (nm) {
+        CUDA_TRY(cudaMemcpyAsync(s.comp[m].p, bi.data, comp_bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync((uint8_t*)s.comp[m].p + comp_bytes, 0, 64, st));
+        CUDA_TRY(cudaMemcpyAsync(moff, bi.member_off, ((size_t)nm + 1) * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ooff, bi.text_off, ((size_t)nm + 1) * 4, cudaMemcpyHostToDevice, st));
+        InflateParams ip;
+        ip.comp = (const uint8_t*)s.comp[m].p;
+        ip.moff = moff;
+        ip.ooff = ooff;
+        ip.n_members = nm;
+        ip.out = base + TEXT_FRONT_PAD;
+        ip.lines = lines_dev;
+        ip.status = s.inflate_status;
+        CUDA_TRY(csq_launch_inflate(ip, st));
+        plan->launches += 1;
+    }
+    if (bi.append_newline) CUDA_TRY(cudaMemsetAsync(base + TEXT_FRONT_PAD + text_bytes, '\n', 1, st));
+    return 0;
+}
+
+int upload_bgzf(csq_plan* plan, Slot& s, const csq_batch_bgzf* in) {
+    const uint32_t n = in->n_reads;
+    s.n = n;
+    s.n_mates = plan->n_mates;
+    s.front_done = false;
+    s.text_mode = true;
+    s.bgzf_mode = true;
+    s.first_record = in->first_record;
+    int rc;
+    CUDA_TRY(cudaMemsetAsync(s.inflate_status, 0x7F, sizeof(int32_t), s.stream));
+    for (int m = 0; m < plan->n_mates; m++) {
+        s.skip_lines[m] = in->mate[m].skip_lines;
+        if ((rc = inflate_mate(plan, s, m, in->mate[m], nullptr, s.stream))) return rc;
+        const uint64_t bytes = s.text_bytes[m];
+        if ((rc = s.seq_off[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.qual_off[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.seq_len[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.name_off[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.name_end[m].ensure((size_t)n * 4 + 16))) return rc;
+        if ((rc = s.nl[m].ensure(((size_t)n * 4 + 8) * 4))) return rc;
+        if ((rc = s.masks[m].ensure(((size_t)csq_parse_tiles(bytes) + 1) * 2048))) return rc;
+        if ((rc = s.tiles[m].ensure(((size_t)csq_parse_tiles(bytes) + 4) * 8))) return rc;
+        if ((rc = s.state[m].ensure((size_t)n * sizeof(ReadState) + 32))) return rc;
+        if ((plan->flags & CSQ_PLAN_KEEP_MATCHES) && plan->prog[m].n_align)
+            if ((rc = s.matches[m].ensure((size_t)n * plan->prog[m].n_align * sizeof(csq_match) + 16))) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 16, s.inflate_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    if ((rc = s.parse_misc.ensure(64))) return rc;
+    return ensure_common(plan, s, n);
+}
+
 int upload(csq_plan* plan, Slot& s, const csq_batch_in* in) {
     const uint32_t n = in->n_reads;
     s.n = n;
     s.n_mates = plan->n_mates;
     s.front_done = false;
     s.text_mode = false;
+    s.bgzf_mode = false;
     for (int m = 0; m < plan->n_mates; m++) {
         const csq_mate_in& mi = in->mate[m];
         int rc;
@@ -467,6 +544,8 @@ int enqueue_mate(csq_plan* plan, Slot& s, int m, KernelTimer* kt, cudaStream_t s
         pp.name_end = (uint32_t*)s.name_end[m].p;
         pp.perr = (unsigned long long*)((uint8_t*)s.parse_misc.p + 16) + m;
         pp.any_cr = (uint32_t*)((uint8_t*)s.parse_misc.p + 40) + m;
+        pp.skip = s.bgzf_mode ? s.skip_lines[m] : 0u;
+        pp.first_off = s.bgzf_mode ? (uint32_t*)((uint8_t*)s.parse_misc.p + 48) + m : nullptr;
         CUDA_TRY(csq_launch_parse(pp, s.tiles[m].p, (uint16_t*)s.masks[m].p, st));
         plan->launches += csq_parse_tiles(pp.bytes) ? 4 : 1;
         if (kt) kt->mark(m == 0 ? "k_parse.r1" : "k_parse.r2");
@@ -627,6 +706,10 @@ int enqueue_gz(csq_plan* plan, Slot& s, KernelTimer* kt, cudaStream_t st) {
 // FASTQ format errors found by k_records, worded like dnaio's FastqFormatError
 int check_parse_error(Slot& s) {
     if (!s.text_mode) return 0;
+    if (s.bgzf_mode) {
+        const int32_t st = *(const int32_t*)(s.totals_host + 16);
+        if (st != 0x7F7F7F7F) return fail(CSQ_ERR_IO, "corrupt BGZF member %d of the batch (inflate error %d)", st / 16, st % 16);
+    }
     for (int m = 0; m < s.n_mates; m++) {
         const unsigned long long key = s.totals_host[14 + m];
         if (key == ~0ULL) continue;
@@ -732,8 +815,9 @@ int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, 
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming);
         for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&s.ev[k]);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.totals_host, 16 * 8, cudaHostAllocDefault);
-        if (e == cudaSuccess) memset(s.totals_host, 0, 16 * 8);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.totals_host, 24 * 8, cudaHostAllocDefault);
+        if (e == cudaSuccess) memset(s.totals_host, 0, 24 * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s.inflate_status, sizeof(int32_t));
         if (e == cudaSuccess && (flags & CSQ_PLAN_GZIP_OUT)) e = cudaHostAlloc((void**)&s.gz_totals_host, 8 * 8, cudaHostAllocDefault);
     }
     if (e != cudaSuccess) {
@@ -766,6 +850,9 @@ void csq_plan_destroy(csq_plan* plan) {
         s.dest.release(); s.block_tot.release(); s.block_cnt.release(); s.block_off.release(); s.totals.release();
         for (cudaEvent_t& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.totals_host) cudaFreeHost(s.totals_host);
+        if (s.inflate_status) cudaFree(s.inflate_status);
+        for (int m = 0; m < 2; m++) { s.comp[m].release(); s.gz_idx[m].release(); }
+        s.gz_lines.release();
         if (s.gz_totals_host) cudaFreeHost(s.gz_totals_host);
         s.gz_misc.release(); s.gz_slots.release(); s.gz_msize.release(); s.gz_moff.release(); s.gz_packed.release();
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -817,6 +904,40 @@ int csq_submit_text(csq_plan* plan, int slot, const csq_batch_text* in, csq_batc
     if ((rc = enqueue_front(plan, s, nullptr, s.stream, s.stream2))) return rc;
     CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
     s.pending = out;
+    return 0;
+}
+
+int csq_submit_bgzf(csq_plan* plan, int slot, const csq_batch_bgzf* in, csq_batch_out* out) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || !out || !in) return fail(CSQ_ERR_INVALID, "bad plan/slot/in/out");
+    if ((int)in->n_mates != plan->n_mates) return fail(CSQ_ERR_INVALID, "batch has %u mates, plan has %d", in->n_mates, plan->n_mates);
+    if ((uint64_t)in->n_reads * 4 >= (1ull << 30)) return fail(CSQ_ERR_LIMIT, "too many records in one batch (limit 2^28 - 1)");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (s.pending) return fail(CSQ_ERR_INVALID, "slot %d still has a batch in flight (call csq_wait)", slot);
+    int rc;
+    CUDA_TRY(cudaEventRecord(s.ev[0], s.stream));
+    if ((rc = upload_bgzf(plan, s, in))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[1], s.stream));
+    if ((rc = enqueue_front(plan, s, nullptr, s.stream, s.stream2))) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev[2], s.stream));
+    s.pending = out;
+    return 0;
+}
+
+int csq_bgzf_count_lines(csq_plan* plan, int slot, const csq_bgzf_in* in, uint32_t* lines) {
+    if (!plan || slot < 0 || slot >= CSQ_N_SLOTS || !in || (in->n_members && !lines)) return fail(CSQ_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(plan->device));
+    Slot& s = plan->slots[slot];
+    if (s.pending) return fail(CSQ_ERR_INVALID, "slot %d still has a batch in flight (call csq_wait)", slot);
+    int rc;
+    if ((rc = s.gz_lines.ensure((size_t)in->n_members * 4 + 16))) return rc;
+    CUDA_TRY(cudaMemsetAsync(s.inflate_status, 0x7F, sizeof(int32_t), s.stream));
+    if ((rc = inflate_mate(plan, s, 0, *in, (uint32_t*)s.gz_lines.p, s.stream))) return rc;
+    if (in->n_members) CUDA_TRY(cudaMemcpyAsync(lines, s.gz_lines.p, (size_t)in->n_members * 4, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(s.totals_host + 16, s.inflate_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    const int32_t st = *(const int32_t*)(s.totals_host + 16);
+    if (st != 0x7F7F7F7F) return fail(CSQ_ERR_IO, "corrupt BGZF member %d of the range (inflate error %d)", st / 16, st % 16);
     return 0;
 }
 

@@ -41,6 +41,8 @@ def lib():
     L.csq_submit.argtypes = [vp, i32, C.POINTER(A.csq_batch_in), C.POINTER(A.csq_batch_out)]
     L.csq_submit_text.argtypes = [vp, i32, C.POINTER(A.csq_batch_text), C.POINTER(A.csq_batch_out)]
     L.csq_upload_text.argtypes = [vp, i32, C.POINTER(A.csq_batch_text)]
+    L.csq_submit_bgzf.argtypes = [vp, i32, C.POINTER(A.csq_batch_bgzf), C.POINTER(A.csq_batch_out)]
+    L.csq_bgzf_count_lines.argtypes = [vp, i32, C.POINTER(A.csq_bgzf_in), vp]
     L.csq_wait.argtypes = [vp, i32]
     L.csq_slot_times.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.csq_upload.argtypes = [vp, i32, C.POINTER(A.csq_batch_in)]
@@ -163,6 +165,30 @@ class Plan:
     def wait(self, slot: int):
         check(lib().csq_wait(self._h, slot))
 
+    def bgzf_count_lines(self, members: "BgzfRun", slot: int = 3):
+        """Line ends per member of a run of BGZF members (``csq_bgzf_count_lines``). -> numpy uint32 array"""
+        out = np.zeros(max(members.c.n_members, 1), dtype=np.uint32)
+        check(lib().csq_bgzf_count_lines(self._h, slot, C.byref(members.c), out.ctypes.data))
+        return out[: members.c.n_members]
+
+    def run_bgzf(self, runs, n_reads: int, capacity: int, slot: int = 0, first_record: int = 0):
+        """BGZF member runs per mate (BgzfRun) through csq_submit_bgzf + csq_wait. -> out[d][m] bytes, records[d][m]"""
+        b = A.csq_batch_bgzf()
+        b.n_reads, b.n_mates, b.first_record = n_reads, len(runs), first_record
+        for m, r in enumerate(runs):
+            b.mate[m] = r.c
+        out = A.csq_batch_out()
+        bufs = [[np.empty(capacity, dtype=np.uint8) for _ in range(2)] for _ in range(A.CSQ_N_DEST)]
+        for d in range(A.CSQ_N_DEST):
+            for m in range(2):
+                out.text[d][m].data = bufs[d][m].ctypes.data
+                out.text[d][m].capacity = capacity
+        check(lib().csq_submit_bgzf(self._h, slot, C.byref(b), C.byref(out)))
+        self.wait(slot)
+        text = [[bufs[d][m][: out.text[d][m].bytes].tobytes() for m in range(2)] for d in range(A.CSQ_N_DEST)]
+        records = [[int(out.text[d][m].records) for m in range(2)] for d in range(A.CSQ_N_DEST)]
+        return text, records
+
     def slot_times(self, slot: int):
         t, k = C.c_float(), C.c_float()
         check(lib().csq_slot_times(self._h, slot, C.byref(t), C.byref(k)))
@@ -258,6 +284,34 @@ class TextBatch:
             self.keep.append(t)
             self.c.mate[m].text = ptr
             self.c.mate[m].bytes = size
+
+
+class BgzfRun:
+    """csq_bgzf_in over a bytes object holding whole BGZF members: walks the member headers ('BC' field, ISIZE)."""
+
+    def __init__(self, data: bytes, skip_lines: int = 0, append_newline: bool = False):
+        moff, ooff = [0], [0]
+        pos = 0
+        while pos < len(data):
+            if data[pos : pos + 4] != b"\x1f\x8b\x08\x04" or data[pos + 12 : pos + 14] != b"BC":
+                raise ValueError("not a BGZF member")
+            size = int.from_bytes(data[pos + 16 : pos + 18], "little") + 1
+            isize = int.from_bytes(data[pos + size - 4 : pos + size], "little")
+            pos += size
+            moff.append(pos)
+            ooff.append(ooff[-1] + isize)
+        self.data = np.frombuffer(data + b"\0" * 16, dtype=np.uint8)
+        self.moff = np.array(moff, dtype=np.uint32)
+        self.ooff = np.array(ooff, dtype=np.uint32)
+        self.c = A.csq_bgzf_in()
+        self.c.data = self.data.ctypes.data
+        self.c.bytes = len(data)
+        self.c.member_off = self.moff.ctypes.data
+        self.c.text_off = self.ooff.ctypes.data
+        self.c.n_members = len(moff) - 1
+        self.c.skip_lines = skip_lines
+        self.c.append_newline = int(append_newline)
+        self.text_bytes = ooff[-1]
 
 
 class TextReader:

@@ -171,6 +171,30 @@ typedef struct csq_batch_text {
     csq_text_in mate[2];
 } csq_batch_text;
 
+/* Batch in, BGZF form: per mate a run of WHOLE BGZF members (bgzip files, this library's own .gz output) as they stand
+ * in the file.  The device inflates them (one thread per member) and finds the records itself; the batch's n_reads
+ * records start behind `skip_lines` line ends of the inflated text, whatever follows them is ignored - so the host
+ * cuts batches at member boundaries and only has to know how many line ends every member holds
+ * (csq_bgzf_count_lines).  member_off / text_off are prefix sums over the members: compressed sizes (the 'BC' field)
+ * and ISIZE (the last four bytes of a member). */
+typedef struct csq_bgzf_in {
+    const uint8_t* data;          /* the members, back to back; readable 16 bytes past the end            */
+    uint64_t bytes;
+    const uint32_t* member_off;   /* n_members + 1 offsets into data                                      */
+    const uint32_t* text_off;     /* n_members + 1 offsets into the inflated text                         */
+    uint32_t n_members;
+    uint32_t skip_lines;          /* line ends of the inflated text in front of the batch's first record  */
+    uint32_t append_newline;      /* end of file without a final line end: add one behind the text        */
+    uint32_t reserved;
+} csq_bgzf_in;
+
+typedef struct csq_batch_bgzf {
+    uint32_t n_reads;
+    uint32_t n_mates;
+    uint64_t first_record;
+    csq_bgzf_in mate[2];
+} csq_batch_bgzf;
+
 /* Batch out: FASTQ text ("@name\nseq\n+\nqual\n" per record, input order) per
  * destination and mate, written into caller-owned buffers. */
 typedef struct csq_text_out {
@@ -246,6 +270,10 @@ void csq_plan_destroy(csq_plan* plan);
 #define CSQ_N_SLOTS 8
 int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* out);
 int csq_submit_text(csq_plan* plan, int slot, const csq_batch_text* in, csq_batch_out* out);
+int csq_submit_bgzf(csq_plan* plan, int slot, const csq_batch_bgzf* in, csq_batch_out* out);
+/* Inflates the members on the device and returns the number of line ends in each (host array of n_members); blocks.
+ * The file driver's first pass over a BGZF input: from these counts it cuts record-aligned batches. */
+int csq_bgzf_count_lines(csq_plan* plan, int slot, const csq_bgzf_in* in, uint32_t* lines);
 int csq_wait(csq_plan* plan, int slot);
 /* Device time of the last completed submit on this slot, in ms, by CUDA events on the
  * slot's stream: total (H2D + kernels + D2H) and kernels only. */

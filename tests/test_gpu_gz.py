@@ -78,3 +78,61 @@ def test_small_output_buffers_can_be_retried():
         for d in range(A.CSQ_N_DEST):
             for m in range(2):
                 assert gunzip_members(big[d][m][: out.text[d][m].bytes].tobytes()) == text[d][m]
+
+
+# ---- BGZF batches in: the device inflates whole members and finds the records itself ----
+def _bgzf(text, level=6, piece=0xFF00):
+    from tests.test_gz import bgzf
+
+    return bgzf(text, level, zlib.Z_DEFAULT_STRATEGY, piece)
+
+
+def _fastq(batch, m):
+    return bytes(native.format_fastq(batch, m))
+
+
+@pytest.mark.parametrize("level,piece", [(1, 0xFF00), (6, 0xFF00), (6, 5000), (0, 0xFF00)])
+def test_bgzf_batches_match_text_batches(level, piece):
+    prog = helpers.program_for(["-A", "TAKARAV3", "--trim-polyA"], 2)
+    n = 30000
+    batch = native.synth_batch(2, n, first_index=99, buffer=5)
+    texts = [_fastq(batch, m) for m in range(2)]
+    with native.Plan(prog, 0, 0) as plan:
+        want, wrec = plan.run_text(texts, n)
+        runs = [native.BgzfRun(_bgzf(t, level, piece)) for t in texts]
+        # pass 1 of the file driver: line ends per member
+        for m in range(2):
+            lines = plan.bgzf_count_lines(runs[m])
+            assert int(lines.sum()) == texts[m].count(b"\n") == 4 * n
+            assert lines[0] == texts[m][: min(piece, len(texts[m]))].count(b"\n")
+        got, rec = plan.run_bgzf(runs, n, capacity=len(texts[0]) + 64 * n)
+        assert got == want and rec == wrec
+        # a batch in the middle of the members: 1000 records in front of it, whatever follows is ignored
+        sub = 5000
+        wsub, _ = plan.run_text([b"".join(t.split(b"\n")[i] + b"\n" for i in range(4000, 4000 + 4 * sub)) for t in texts], sub)
+        runs2 = [native.BgzfRun(_bgzf(t, level, piece), skip_lines=4000) for t in texts]
+        gsub, _ = plan.run_bgzf(runs2, sub, capacity=len(texts[0]))
+        assert gsub == wsub
+
+
+def test_bgzf_in_gzip_out_round_trip_and_corrupt_member():
+    prog = helpers.program_for(["-A", "TAKARAV3"], 2)
+    n = 20000
+    batch = native.synth_batch(2, n, first_index=5, buffer=5)
+    texts = [_fastq(batch, m) for m in range(2)]
+    with native.Plan(prog, 0, 0) as plan:
+        want, _ = plan.run_text(texts, n)
+    with native.Plan(prog, 0, A.PLAN_GZIP_OUT) as plan:
+        z, _ = plan.run_bgzf([native.BgzfRun(_bgzf(t, 1)) for t in texts], n, capacity=len(texts[0]))
+        for d in range(A.CSQ_N_DEST):
+            for m in range(2):
+                assert gunzip_members(z[d][m]) == want[d][m]
+        # the library reads its own output: trimmed files as the next run's input
+        again = [native.BgzfRun(z[0][m]) for m in range(2)]
+        assert int(plan.bgzf_count_lines(again[0]).sum()) == want[0][0].count(b"\n")
+        bad = bytearray(_bgzf(texts[0], 6))
+        bad[len(bad) // 3] ^= 0xFF
+        bad[len(bad) // 3 + 1] ^= 0xFF
+        with pytest.raises(native.NativeError) as e:
+            plan.run_bgzf([native.BgzfRun(bytes(bad)), native.BgzfRun(_bgzf(texts[1], 6))], n, capacity=len(texts[0]))
+        assert e.value.code in (A.ERR_IO, A.ERR_FORMAT)
