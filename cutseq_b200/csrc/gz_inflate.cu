@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(INF_THREADS) k_gz_inflate(const __grid_constan
     uint32_t produced = 0, lines = 0;
     const int rc = gzi::inflate_member<INF_THREADS>(P.comp + s0, s1 - s0, P.out + o0, o1 - o0, tabs + threadIdx.x, &produced, &lines);
     if (rc != gzi::OK || produced != o1 - o0) atomicMin(P.status, (rc ? rc : (int)gzi::ERR_TRAILER) + 16 * (int)min(i, 0x7FFFFFu));
-    if (P.lines) P.lines[i] = lines;
+    // bit 31: the member's text does not end in a line end (the host needs that for the last member of a file)
+    if (P.lines) P.lines[i] = lines | ((produced && P.out[o0 + produced - 1] != '\n') ? 0x80000000u : 0u);
 }
 
 }  // namespace

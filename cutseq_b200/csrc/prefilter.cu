@@ -270,7 +270,8 @@ __device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b, uint32_t c) 
     return d;
 }
 
-template <bool REV>
+// TRACK: how the row-m cost is followed - 0: mad.hi counters (FMA pipe), 1: shifts + a three-input add (ALU pipe)
+template <bool REV, int TRACK>
 __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ AlignParams P, uint32_t* __restrict__ list,
                                                       uint32_t* __restrict__ list_count, const uint32_t one, const uint32_t two,
                                                       const uint32_t four, const uint32_t minus_one) {
@@ -321,15 +322,24 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
         // (A first form only counted per chunk and re-walked "suspicious" chunks column by column: one suspicious
         // lane makes its whole warp walk again, 24 instead of 17 instructions per column on average.)
         uint32_t up = 0, dn = 0;
+        int rel = 0;  // TRACK 1: cost[m][j] - m
+        auto follow = [&](uint32_t Ph, uint32_t Mh) {
+            if (TRACK == 0) {
+                up = imad_hi(Ph, two, up);
+                dn = imad_hi(Mh, two, dn);
+                smin = min(smin, (int)imad_lo(dn, minus_one, up));
+            } else {
+                rel += (int)(Ph >> 31) - (int)(Mh >> 31);
+                smin = min(smin, rel);
+            }
+        };
         auto chunk16 = [&](const uint32_t (&w4)[4]) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int x = REV ? 15 - i : i;
                 uint32_t Ph, Mh;
                 column(w4, x, Ph, Mh);
-                up = imad_hi(Ph, two, up);
-                dn = imad_hi(Mh, two, dn);
-                smin = min(smin, (int)imad_lo(dn, minus_one, up));
+                follow(Ph, Mh);
             }
             if (fc < 0 && smin <= T - m) fc = jc;
             jc += 16;
@@ -373,9 +383,7 @@ __global__ void __launch_bounds__(256) k_prefilter_fs(const __grid_constant__ Al
                 const int x = REV ? 15 - i : i;
                 uint32_t Ph, Mh;
                 column(w4, x, Ph, Mh);
-                up = imad_hi(Ph, two, up);
-                dn = imad_hi(Mh, two, dn);
-                smin = min(smin, (int)imad_lo(dn, minus_one, up));
+                follow(Ph, Mh);
             }
             if (fc < 0 && smin <= T - m) fc = jc;
         }
@@ -507,10 +515,14 @@ cudaError_t csq_launch_prefilter(const AlignParams& p, uint32_t* list, uint32_t*
         return cudaGetLastError();
     }
     if (p.flags == 14 && p.m <= 32 && !getenv("CSQ_PREFILTER_V1")) {  // BACK / RightmostFront: the two-pipe form
-        if (p.reversed)
-            k_prefilter_fs<true><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
-        else
-            k_prefilter_fs<false><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
+        static const int track = getenv("CSQ_PF_TRACK") ? atoi(getenv("CSQ_PF_TRACK")) : 0;
+        if (p.reversed) {
+            if (track) k_prefilter_fs<true, 1><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
+            else k_prefilter_fs<true, 0><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
+        } else {
+            if (track) k_prefilter_fs<false, 1><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
+            else k_prefilter_fs<false, 0><<<grid, block, 0, stream>>>(p, list, list_count, 1u, 2u, 4u, 0xFFFFFFFFu);
+        }
         return cudaGetLastError();
     }
     switch ((p.m + 31) / 32) {

@@ -169,7 +169,7 @@ class Plan:
         """Line ends per member of a run of BGZF members (``csq_bgzf_count_lines``). -> numpy uint32 array"""
         out = np.zeros(max(members.c.n_members, 1), dtype=np.uint32)
         check(lib().csq_bgzf_count_lines(self._h, slot, C.byref(members.c), out.ctypes.data))
-        return out[: members.c.n_members]
+        return out[: members.c.n_members] & np.uint32(0x7FFFFFFF)
 
     def run_bgzf(self, runs, n_reads: int, capacity: int, slot: int = 0, first_record: int = 0):
         """BGZF member runs per mate (BgzfRun) through csq_submit_bgzf + csq_wait. -> out[d][m] bytes, records[d][m]"""

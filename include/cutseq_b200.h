@@ -271,7 +271,8 @@ void csq_plan_destroy(csq_plan* plan);
 int csq_submit(csq_plan* plan, int slot, const csq_batch_in* in, csq_batch_out* out);
 int csq_submit_text(csq_plan* plan, int slot, const csq_batch_text* in, csq_batch_out* out);
 int csq_submit_bgzf(csq_plan* plan, int slot, const csq_batch_bgzf* in, csq_batch_out* out);
-/* Inflates the members on the device and returns the number of line ends in each (host array of n_members); blocks.
+/* Inflates the members on the device and returns the number of line ends in each (host array of n_members; bit 31 of
+ * an entry is set when that member's text does not end in a line end); blocks.
  * The file driver's first pass over a BGZF input: from these counts it cuts record-aligned batches. */
 int csq_bgzf_count_lines(csq_plan* plan, int slot, const csq_bgzf_in* in, uint32_t* lines);
 int csq_wait(csq_plan* plan, int slot);

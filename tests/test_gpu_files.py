@@ -122,3 +122,96 @@ def test_multi_gpu_file_run_is_order_preserving(tmp_path):
     run.main(case["argv"] + ["-O", prefix, "--gpus", "2", "--batch-reads", "97", "-t", "2"] + helpers.golden_input_paths(case))
     for key in case["outputs"]:
         assert read_maybe_gz(f"{prefix}_{key}.fastq.gz") == helpers.golden_expected(case, key), key
+
+
+def _as_bgzf(src_gz, dst, piece=0xFF00, strip_final_newline=False, eof_marker=True):
+    from scripts.bench_files import BGZF_EOF, bgzf_member
+
+    text = gzip.open(src_gz).read()
+    if strip_final_newline:
+        text = text.rstrip(b"\n")
+    with open(dst, "wb") as f:
+        for o in range(0, len(text), piece):
+            f.write(bgzf_member(text[o : o + piece], 6))
+        if eof_marker:
+            f.write(BGZF_EOF)
+    return dst
+
+
+@pytest.mark.parametrize("batch_reads,piece", [("257", 0xFF00), ("100000", 0xFF00), ("64", 3000), ("1000", 70)])
+def test_bgzf_inputs_take_the_device_inflate_path(tmp_path, batch_reads, piece, capsys):
+    """bgzip-style inputs: member runs go to the device (csq_submit_bgzf), batches are cut from the line counts the
+    GPU returns (csq_bgzf_count_lines); pieces of 70 bytes put several members inside every record."""
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_polya"][0]
+    ins = [_as_bgzf(p, str(tmp_path / f"in_R{m + 1}.fq.gz"), piece) for m, p in enumerate(helpers.golden_input_paths(case))]
+    prefix = str(tmp_path / "out")
+    run.main(case["argv"] + ["-O", prefix, "--batch-reads", batch_reads] + ins)
+    err = capsys.readouterr().err
+    for key in case["outputs"]:
+        assert read_maybe_gz(f"{prefix}_{key}.fastq.gz") == helpers.golden_expected(case, key), key
+    assert case["minimal_report"][-1] in err.splitlines()
+
+
+def test_bgzf_and_plain_inputs_without_a_final_line_end(tmp_path):
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_synth_polya"][0]
+    ins = [_as_bgzf(p, str(tmp_path / f"in_R{m + 1}.fq.gz"), strip_final_newline=True, eof_marker=(m == 0))
+           for m, p in enumerate(helpers.golden_input_paths(case))]
+    prefix = str(tmp_path / "out")
+    run.main(case["argv"] + ["-O", prefix, "--batch-reads", "199"] + ins)
+    for key in case["outputs"]:
+        assert read_maybe_gz(f"{prefix}_{key}.fastq.gz") == helpers.golden_expected(case, key), key
+    plain = []
+    for m, p in enumerate(helpers.golden_input_paths(case)):
+        q = str(tmp_path / f"in_R{m + 1}.fq")
+        with open(q, "wb") as f:
+            f.write(gzip.open(p).read().rstrip(b"\n") if m == 1 else gzip.open(p).read() + b"\n\n")
+        plain.append(q)
+    o1, o2 = str(tmp_path / "p1.fq"), str(tmp_path / "p2.fq")
+    run.main(case["argv"] + ["-o", o1, o2, "--batch-reads", "199", "-t", "5"] + plain)
+    assert open(o1, "rb").read() == helpers.golden_expected(case, "trimmed_R1")
+    assert open(o2, "rb").read() == helpers.golden_expected(case, "trimmed_R2")
+
+
+def test_mismatched_pair_files_and_corrupt_members_fail_and_leave_no_outputs(tmp_path):
+    from cutseq_b200 import native
+
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_synth_polya"][0]
+    p1, p2 = helpers.golden_input_paths(case)
+    a = _as_bgzf(p1, str(tmp_path / "a.fq.gz"))
+    text2 = gzip.open(p2).read()
+    short = str(tmp_path / "b.fq.gz")
+    from scripts.bench_files import bgzf_member
+
+    with open(short, "wb") as f:
+        f.write(bgzf_member(b"\n".join(text2.split(b"\n")[:400]) + b"\n", 6))
+    with pytest.raises(native.NativeError):
+        run.main(case["argv"] + ["-O", str(tmp_path / "o"), a, short])
+    assert not [f for f in os.listdir(tmp_path) if f.startswith("o_")]
+    bad = bytearray(open(a, "rb").read())
+    bad[len(bad) // 2] ^= 0xFF
+    bad[len(bad) // 2 + 7] ^= 0xFF
+    (tmp_path / "bad.fq.gz").write_bytes(bytes(bad))
+    with pytest.raises(native.NativeError):
+        run.main(case["argv"] + ["-O", str(tmp_path / "o2"), str(tmp_path / "bad.fq.gz"), _as_bgzf(p2, str(tmp_path / "b2.fq.gz"))])
+    assert not [f for f in os.listdir(tmp_path) if f.startswith("o2_")]
+
+
+@pytest.mark.parametrize("kind", ["plain", "bgzf"])
+def test_multi_gpu_runs_of_the_fast_paths_are_order_preserving(tmp_path, kind):
+    from cutseq_b200 import native
+
+    if native.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_polya"][0]
+    ins = []
+    for m, p in enumerate(helpers.golden_input_paths(case)):
+        if kind == "bgzf":
+            ins.append(_as_bgzf(p, str(tmp_path / f"in_R{m + 1}.fq.gz"), 4000))
+        else:
+            q = str(tmp_path / f"in_R{m + 1}.fq")
+            open(q, "wb").write(gzip.open(p).read())
+            ins.append(q)
+    prefix = str(tmp_path / "out")
+    run.main(case["argv"] + ["-O", prefix, "--gpus", "2", "--batch-reads", "61", "-t", "4"] + ins)
+    for key in case["outputs"]:
+        assert read_maybe_gz(f"{prefix}_{key}.fastq.gz") == helpers.golden_expected(case, key), key

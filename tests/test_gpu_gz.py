@@ -109,7 +109,7 @@ def test_bgzf_batches_match_text_batches(level, piece):
         assert got == want and rec == wrec
         # a batch in the middle of the members: 1000 records in front of it, whatever follows is ignored
         sub = 5000
-        wsub, _ = plan.run_text([b"".join(t.split(b"\n")[i] + b"\n" for i in range(4000, 4000 + 4 * sub)) for t in texts], sub)
+        wsub, _ = plan.run_text([b"\n".join(t.split(b"\n")[4000 : 4000 + 4 * sub]) + b"\n" for t in texts], sub)
         runs2 = [native.BgzfRun(_bgzf(t, level, piece), skip_lines=4000) for t in texts]
         gsub, _ = plan.run_bgzf(runs2, sub, capacity=len(texts[0]))
         assert gsub == wsub
