@@ -233,6 +233,83 @@ def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
     return out
 
 
+def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, max_over_ranks):
+    """csq_submit_bgzf / csq_wait with CSQ_PLAN_GZIP_OUT: the two pinned text batches of the e2e leg, compressed once on the
+    host into BGZF members (64 KiB, zlib level 1 - what bgzip or this library's own writer produces), go through the
+    device inflate, the chain and the device deflate; compressed bytes only cross PCIe in both directions."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from cutseq_b200 import _abi as A
+    from cutseq_b200 import native
+    from scripts import bench_files
+
+    threads = max(2, (os.cpu_count() or 4) // max(1, world))
+    inputs = []  # per batch: (csq_batch_bgzf, keep-alive)
+    comp_bytes = 0
+    for tb in batches:
+        b = A.csq_batch_bgzf()
+        b.n_reads, b.n_mates, b.first_record = P, 2, tb.c.first_record
+        keep = []
+        for m in range(2):
+            text = memoryview(tb.keep[m].numpy())
+            z = bench_files.bgzf_compress(text, threads)
+            run = native.BgzfRun(z)
+            pinned = torch.empty(len(z) + 64, dtype=torch.uint8, pin_memory=True)
+            pinned[: len(z)] = torch.frombuffer(bytearray(z), dtype=torch.uint8)
+            b.mate[m] = run.c
+            b.mate[m].data = pinned.data_ptr()
+            keep += [run, pinned]
+            comp_bytes += len(z) if tb is batches[0] else 0
+        inputs.append((b, keep))
+    plan = native.Plan(prog, device, plan_flags | A.PLAN_GZIP_OUT)
+    try:
+        text_bytes = int(sum(batches[0].c.mate[m].bytes for m in range(2)))
+        cap = text_bytes // 3 + 4096
+        n_fly = 3
+        outs, keep_out = [], []
+        for s in range(n_fly):
+            out = A.csq_batch_out()
+            for d in range(A.CSQ_N_DEST):
+                for m in range(2):
+                    size = cap if d == 0 else cap // 4
+                    buf = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+                    keep_out.append(buf)
+                    out.text[d][m].data = buf.data_ptr()
+                    out.text[d][m].capacity = size
+            outs.append(out)
+
+        def run_batches(k):
+            d2h, submitted = 0, 0
+            for i in range(k):
+                while submitted < k and submitted < i + n_fly:
+                    native.check(native.lib().csq_submit_bgzf(plan._h, submitted % n_fly, C.byref(inputs[submitted % len(inputs)][0]), C.byref(outs[submitted % n_fly])))
+                    submitted += 1
+                plan.wait(i % n_fly)
+                o = outs[i % n_fly]
+                d2h += sum(o.text[d][m].bytes for d in range(A.CSQ_N_DEST) for m in range(2))
+            return d2h
+
+        steps = max(2, min(args.steps, 12))
+        run_batches(3)
+        barrier()
+        w0 = time.perf_counter()
+        d2h = run_batches(steps * B)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        barrier()
+        dt = max_over_ranks(w1 - w0)
+        return {"value": world * steps * B * P / dt, "unit": UNIT, "h2d_bytes_per_step": comp_bytes * B, "d2h_bytes_per_step": int(d2h // steps),
+                "ms_per_step": dt / steps * 1e3, "steps": steps, "text_bytes_per_step": text_bytes * B,
+                "input": "BGZF members (zlib level 1, 0xFF00-byte pieces), inflated on the device, one thread per member",
+                "output": "gzip members (BGZF framing, dynamic-Huffman literal coding) encoded on the device",
+                "timing": f"wall clock between device-synchronised points, {n_fly} batches in flight through csq_submit_bgzf/csq_wait, max over ranks"}
+    finally:
+        plan.close()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -273,6 +350,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the GPU's NUMA node (A/B runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-gz", action="store_true", help="skip the end-to-end leg with compressed host buffers (BGZF in, gzip out)")
     ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
     ap.add_argument("--file-pairs", type=int, default=20_000_000, help="pairs in the plain whole-file leg (config 5: streamed, <= 20M-pair on-disk file)")
     ap.add_argument("--file-pairs-gz", type=int, default=8_000_000, help="pairs in the .gz whole-file leg")
@@ -315,8 +393,9 @@ def main():
 
     prog = takara_program()
     P, B = args.batch_pairs, args.batches
-    plan = native.Plan(prog, local_rank, (A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16}[args.emit]
-                       | (A.PLAN_ONE_STREAM if args.one_stream else 0) | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
+    plan_flags = ((A.PLAN_NO_PREFILTER if args.no_prefilter else 0) | {"stage": 0, "g16": A.PLAN_EMIT_G16}[args.emit]
+                  | (A.PLAN_ONE_STREAM if args.one_stream else 0) | (A.PLAN_NO_EXACT_STOP if args.no_exact_stop else 0))
+    plan = native.Plan(prog, local_rank, plan_flags)
     # this rank's contiguous index range of the workload: [rank*B*P, (rank+1)*B*P)
     # Host copies: batches 0 and 1 stay in pinned memory for the end-to-end leg; later batches reuse one
     # staging buffer (csq_upload is synchronous), so a rank pins three batches, not B.
@@ -444,6 +523,15 @@ def main():
         except native.NativeError as exc:
             roofline_e2e = {"error": str(exc)}
 
+    # ---- the same end to end with COMPRESSED host buffers: BGZF members in (device inflate), gzip members out (device
+    # deflate) - what the reference's default .fastq.gz files hold; ~1/3 of the bytes cross PCIe ----
+    e2e_gz = None
+    if not args.no_e2e and not args.no_e2e_gz and text_mode:
+        try:
+            e2e_gz = e2e_gz_leg(args, prog, plan_flags, local_rank, batches, P, B, world, barrier, max_over_ranks)
+        except Exception as exc:
+            e2e_gz = {"error": repr(exc)}
+
     native.unbind_host()  # the host legs below (files, CPU baseline) use every core of the box
     if rank != 0:
         plan.close()
@@ -547,7 +635,7 @@ def main():
         "roofline": roofline, "roofline_e2e": roofline_e2e, "roofline_dp_executed": roofline_dp_executed,
         "int_peak_Gops": {"alu_only": alu_peak / 1e9, "alu_fma_mix": mixed_peak / 1e9},
         "kernels": [{"kernel": n, "ms": t} for n, t in ktimes], "kernels_note": "one batch of the step, one stream, CUDA event after every kernel",
-        "dp_kernels": dp_kernels, "cpu_baseline": cpu, "e2e": e2e, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
+        "dp_kernels": dp_kernels, "cpu_baseline": cpu, "e2e": e2e, "e2e_gz": e2e_gz, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
         "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
         "sources_sha256_16": src_hash,
     }

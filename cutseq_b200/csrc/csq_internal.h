@@ -168,8 +168,10 @@ struct InflateParams {
     uint8_t* out;
     uint32_t* lines;         // nullable: '\n' per member
     int32_t* status;         // atomicMin of (error kind + 16 * member index); INT_MAX when clean
+    const uint32_t* crc_tables;  // tables of csq_gz_crc_check_tables: the CRC-32 of every member is verified (error kind 7)
 };
 cudaError_t csq_launch_inflate(const InflateParams& p, cudaStream_t stream);
+void csq_gz_crc_check_tables(uint32_t* t /*[768]*/);
 
 // word indices inside csq_counters viewed as uint64[]
 enum {

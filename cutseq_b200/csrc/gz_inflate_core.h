@@ -1,10 +1,16 @@
-// DEFLATE decoder for ONE gzip member by ONE thread (RFC 1951 / 1952), written for the device (gz_inflate.cu: one
-// thread per BGZF member, tens of thousands of members in flight) and compiled for the host as well so that the CPU
-// tests exercise the same code.  Canonical-Huffman decoding by code length (counts per length + symbols in code
-// order, as in zlib's contrib/puff): two tiny tables per code instead of multi-kilobyte lookup tables, so that a
-// thread's tables fit in ~700 bytes of shared memory.  Table element e of a thread lives at tab[e * STRIDE]
-// (device: the threads of a CTA interleave their tables, STRIDE = threads per CTA, so that the same element of
-// neighbouring threads falls into neighbouring banks; host: STRIDE = 1).
+// DEFLATE decoder for ONE gzip member by ONE group of LANES cooperating threads (RFC 1951 / 1952).  On the device a
+// group is a warp (gz_inflate.cu: one warp per BGZF member, every member of a batch in flight at once); the host twin
+// runs the same code with LANES = 1 for the CPU tests.
+//
+// Every lane of the group runs the whole bit-level decode REDUNDANTLY on the same bits (bit buffer, code tables and
+// control flow are warp-uniform: no divergence, no shuffles, shared-memory reads are broadcasts); what the lanes split
+// is the byte traffic: literals are collected one per lane and leave as one store of LANES bytes, match and stored-block
+// copies are strided over the lanes with their loads in flight together.  (The first version ran one THREAD per member:
+// 32 different decoder states per warp serialise completely and a batch is only a few hundred warps - 0.4 GB/s.)
+//
+// Huffman codes: canonical decoding by code length (counts per length + symbols in code order, as in zlib's
+// contrib/puff) is kept as the slow path for long codes and for validation; in front of it a direct table indexed by
+// the next LBITS / DBITS input bits answers codes of up to that length in one lookup.
 #pragma once
 
 #include <stdint.h>
@@ -14,13 +20,28 @@
 #else
 #define GZI_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define GZI_SYNC() __syncwarp()
+#define GZI_UNROLL _Pragma("unroll")
+#else
+#define GZI_SYNC() ((void)0)
+#define GZI_UNROLL
+#endif
 
 namespace gzi {
 
 constexpr int MAXBITS = 15, MAXLCODES = 286, MAXDCODES = 30, FIXLCODES = 288;
-constexpr int TAB_LCOUNT = 0, TAB_LSYM = 16, TAB_DCOUNT = 16 + 288, TAB_DSYM = 16 + 288 + 16, TAB_ELEMS = 16 + 288 + 16 + 32;
+constexpr int LBITS = 10, DBITS = 8;  // index bits of the direct tables
 
 enum Status { OK = 0, ERR_HEADER = 1, ERR_BLOCK = 2, ERR_CODE = 3, ERR_DIST = 4, ERR_OVERRUN = 5, ERR_TRAILER = 6 };
+
+struct Tables {  // per group (device: shared memory, 3.6 KB per warp)
+    uint16_t llut[1 << LBITS];  // (symbol << 4) | code length; 0: the code is longer than LBITS (or invalid)
+    uint16_t dlut[1 << DBITS];
+    uint16_t lcount[MAXBITS + 1], dcount[MAXBITS + 1];  // codes per length
+    uint16_t lsym[FIXLCODES], dsym[32];                 // symbols in code order
+    uint8_t lengths[MAXLCODES + MAXDCODES + 4];
+};
 
 struct BitIn {
     const uint8_t* p;    // next input byte
@@ -29,7 +50,7 @@ struct BitIn {
     int cnt;
 };
 
-GZI_HD void refill(BitIn& b) {  // at least 32 bits afterwards (zeros behind the end of the member)
+GZI_HD void refill(BitIn& b) {  // at least 33 bits afterwards (zeros behind the end of the member)
     while (b.cnt <= 32) {
         // four bytes at a time once the pointer is aligned; reading up to 3 bytes behind `end` is allowed (padding)
         if ((((uintptr_t)b.p) & 3u) == 0) {
@@ -51,18 +72,18 @@ GZI_HD uint32_t take(BitIn& b, int n) {  // n <= 16, after refill
     return v;
 }
 
-template <int STRIDE>
-GZI_HD int decode_sym(BitIn& b, const uint16_t* count, const uint16_t* symbol) {
+// canonical decode, one bit at a time (codes the direct table does not hold)
+GZI_HD int decode_slow(BitIn& b, const uint16_t* count, const uint16_t* symbol) {
     int code = 0, first = 0, index = 0;
     uint32_t bits = (uint32_t)b.buf;
     for (int len = 1; len <= MAXBITS; len++) {
         code |= (int)(bits & 1u);
         bits >>= 1;
-        const int c = count[len * STRIDE];
+        const int c = count[len];
         if (code - c < first) {
             b.buf >>= len;
             b.cnt -= len;
-            return symbol[(index + (code - first)) * STRIDE];
+            return symbol[index + (code - first)];
         }
         index += c;
         first += c;
@@ -72,36 +93,113 @@ GZI_HD int decode_sym(BitIn& b, const uint16_t* count, const uint16_t* symbol) {
     return -1;
 }
 
-// counts per length and symbols in code order from the code lengths; returns < 0 for an over-subscribed set,
-// > 0 for an incomplete one (only acceptable for a single code of one bit, checked by the caller), 0 when complete
-template <int STRIDE>
-GZI_HD int construct(uint16_t* count, uint16_t* symbol, const uint8_t* length, int n) {
-    for (int len = 0; len <= MAXBITS; len++) count[len * STRIDE] = 0;
-    for (int s = 0; s < n; s++) count[length[s] * STRIDE]++;
-    if (count[0] == n) return 0;  // no codes at all
+template <int BITS>
+GZI_HD int decode_sym(BitIn& b, const uint16_t* lut, const uint16_t* count, const uint16_t* symbol) {
+    const uint32_t e = lut[(uint32_t)b.buf & ((1u << BITS) - 1u)];
+    if (e) {
+        const int n = (int)(e & 15u);
+        b.buf >>= n;
+        b.cnt -= n;
+        return (int)(e >> 4);
+    }
+    return decode_slow(b, count, symbol);
+}
+
+GZI_HD uint32_t bit_reverse(uint32_t v, int n) {  // the low n bits of v, reversed
+#if defined(__CUDA_ARCH__)
+    return __brev(v) >> (32 - n);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+#endif
+}
+
+// Code lengths (already in shared memory, visible to every lane) -> counts per length, symbols in code order (lane 0)
+// and the direct table (all lanes).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one (only
+// acceptable for a single code of one bit, checked by the caller), 0 when complete.  The group is synchronised on
+// return.
+template <int LANES, int BITS>
+GZI_HD int construct(uint16_t* count, uint16_t* symbol, uint16_t* lut, const uint8_t* length, int n, int lane) {
+    // every lane derives the counts per length for itself (registers), lane 0 publishes them
+    uint32_t cnt[MAXBITS + 1];
+    GZI_UNROLL
+    for (int len = 0; len <= MAXBITS; len++) cnt[len] = 0;
+    for (int s = 0; s < n; s++) {
+        const int l = length[s];
+        GZI_UNROLL
+        for (int len = 0; len <= MAXBITS; len++) cnt[len] += (l == len) ? 1u : 0u;
+    }
     int left = 1;
+    bool over = false;
+    GZI_UNROLL
     for (int len = 1; len <= MAXBITS; len++) {
         left <<= 1;
-        left -= count[len * STRIDE];
-        if (left < 0) return left;
+        left -= (int)cnt[len];
+        over = over || left < 0;
     }
-    uint16_t offs[MAXBITS + 1];
+    if ((int)cnt[0] == n) left = 0;  // no codes at all
+    // offs[len]: index of the first symbol of that length in code order; first[len]: its code
+    uint32_t offs[MAXBITS + 2], first[MAXBITS + 2];
     offs[1] = 0;
-    for (int len = 1; len < MAXBITS; len++) offs[len + 1] = (uint16_t)(offs[len] + count[len * STRIDE]);
-    for (int s = 0; s < n; s++)
-        if (length[s] != 0) symbol[(offs[length[s]]++) * STRIDE] = (uint16_t)s;
+    first[1] = 0;
+    GZI_UNROLL
+    for (int len = 1; len <= MAXBITS; len++) {
+        offs[len + 1] = offs[len] + cnt[len];
+        first[len + 1] = (first[len] + cnt[len]) << 1;
+    }
+    GZI_SYNC();  // the previous tables are not read any more
+    if (lane == 0) {
+        GZI_UNROLL
+        for (int len = 0; len <= MAXBITS; len++) count[len] = (uint16_t)cnt[len];
+    }
+    for (int e = lane; e < (1 << BITS); e += LANES) lut[e] = 0;
+    if (over) {
+        GZI_SYNC();
+        return -1;
+    }
+    if (lane == 0) {
+        uint32_t next[MAXBITS + 1];
+        GZI_UNROLL
+        for (int len = 1; len <= MAXBITS; len++) next[len] = offs[len];
+        for (int s = 0; s < n; s++) {
+            const int l = length[s];
+            if (l == 0) continue;
+            uint32_t at = 0;
+            GZI_UNROLL
+            for (int len = 1; len <= MAXBITS; len++)
+                if (l == len) at = next[len]++;
+            symbol[at] = (uint16_t)s;
+        }
+    }
+    GZI_SYNC();
+    // direct table: the symbol at position idx of the code order has the code first[l] + (idx - offs[l]) of l bits,
+    // MSB first in the stream, i.e. bit-reversed in the (LSB first) bit buffer; every index whose low l bits equal it
+    const int total = (int)offs[MAXBITS + 1];
+    for (int idx = lane; idx < total; idx += LANES) {
+        const int s = symbol[idx];
+        const int l = length[s];
+        if (l > BITS) continue;
+        uint32_t f = 0, o = 0;
+        GZI_UNROLL
+        for (int len = 1; len <= MAXBITS; len++)
+            if (l == len) {
+                f = first[len];
+                o = offs[len];
+            }
+        const uint32_t code = f + ((uint32_t)idx - o);
+        const uint16_t entry = (uint16_t)(((uint32_t)s << 4) | (uint32_t)l);
+        for (uint32_t e = bit_reverse(code, l); e < (1u << BITS); e += 1u << l) lut[e] = entry;
+    }
+    GZI_SYNC();
     return left;
 }
 
-// One gzip member src[0 .. n) -> dst[0 .. cap); tab: TAB_ELEMS elements of this thread at stride STRIDE.
-// *produced = bytes written, *lines = '\n' among them.  Checks ISIZE (and that the member ends where it should); the
-// CRC-32 of the member is not verified here (the host checks BGZF members it inflates itself; a corrupt member that
-// still decodes to the right length would go through).
-template <int STRIDE>
-GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint16_t* tab, uint32_t* produced, uint32_t* lines) {
-    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+// One gzip member src[0 .. n) -> dst[0 .. cap).  *produced = bytes written (valid in every lane).  Checks ISIZE and
+// that the member ends where it should; the CRC-32 of the text is verified by the caller (k_gz_check / the host twin).
+template <int LANES>
+GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, Tables& T, int lane, uint32_t* produced) {
     *produced = 0;
-    *lines = 0;
     // gzip header (RFC 1952): magic, CM = 8, FLG, MTIME(4), XFL, OS, then the optional fields
     if (n < 18 || src[0] != 0x1f || src[1] != 0x8b || src[2] != 8) return ERR_HEADER;
     const uint32_t flg = src[3];
@@ -121,11 +219,14 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
     if (flg & 2u) pos += 2;
     if (pos + 8 > n) return ERR_HEADER;
     BitIn b = {src + pos, src + n, 0, 0};
-    uint16_t* const lcount = tab + TAB_LCOUNT * STRIDE;
-    uint16_t* const lsym = tab + TAB_LSYM * STRIDE;
-    uint16_t* const dcount = tab + TAB_DCOUNT * STRIDE;
-    uint16_t* const dsym = tab + TAB_DSYM * STRIDE;
-    uint32_t out = 0, nl = 0;
+    // out: bytes produced so far; the last out - flushed of them (< LANES, literals) still sit in `mine` of lanes
+    // 0 .. out - flushed - 1
+    uint32_t out = 0, flushed = 0;
+    uint8_t mine = 0;
+    auto flush = [&] {
+        if ((uint32_t)lane < out - flushed) dst[flushed + (uint32_t)lane] = mine;
+        flushed = out;
+    };
     int last;
     do {
         refill(b);
@@ -143,73 +244,89 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             b.buf = 0;
             b.cnt = 0;
             if (q + len > b.end || out + len > cap) return ERR_OVERRUN;
-            for (uint32_t i = 0; i < len; i++) {
-                const uint8_t c = q[i];
-                dst[out + i] = c;
-                nl += c == '\n';
-            }
+            flush();
+            for (uint32_t i = (uint32_t)lane; i < len; i += LANES) dst[out + i] = q[i];
             out += len;
+            flushed = out;
             b.p = q + len;
             continue;
         }
         if (type == 3) return ERR_BLOCK;
-        uint8_t lengths[MAXLCODES + MAXDCODES + 2];
         if (type == 1) {  // fixed codes
-            int s = 0;
-            for (; s < 144; s++) lengths[s] = 8;
-            for (; s < 256; s++) lengths[s] = 9;
-            for (; s < 280; s++) lengths[s] = 7;
-            for (; s < FIXLCODES; s++) lengths[s] = 8;
-            construct<STRIDE>(lcount, lsym, lengths, FIXLCODES);
-            for (s = 0; s < MAXDCODES; s++) lengths[s] = 5;
-            construct<STRIDE>(dcount, dsym, lengths, MAXDCODES);
+            GZI_SYNC();
+            for (int s = lane; s < FIXLCODES; s += LANES) T.lengths[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
+            for (int s = lane; s < MAXDCODES; s += LANES) T.lengths[FIXLCODES + s] = 5;
+            GZI_SYNC();
+            construct<LANES, LBITS>(T.lcount, T.lsym, T.llut, T.lengths, FIXLCODES, lane);
+            construct<LANES, DBITS>(T.dcount, T.dsym, T.dlut, T.lengths + FIXLCODES, MAXDCODES, lane);
         } else {  // dynamic codes
             refill(b);
             const int nlen = (int)take(b, 5) + 257, ndist = (int)take(b, 5) + 1, ncode = (int)take(b, 4) + 4;
             if (nlen > MAXLCODES || ndist > MAXDCODES) return ERR_CODE;
-            int idx = 0;
-            for (; idx < ncode; idx++) {
+            // the code-length code: 19 lengths of 3 bits in a fixed order, read by every lane, stored by lane 0
+            uint32_t packed[3] = {0, 0, 0};  // 19 x 3 bits, by position in the stream
+            for (int idx = 0; idx < ncode; idx++) {
                 refill(b);
-                lengths[order[idx]] = (uint8_t)take(b, 3);
+                const uint32_t v = take(b, 3);
+                if (idx < 10)
+                    packed[0] |= v << (3 * idx);
+                else
+                    packed[1] |= v << (3 * (idx - 10));
             }
-            for (; idx < 19; idx++) lengths[order[idx]] = 0;
-            if (construct<STRIDE>(lcount, lsym, lengths, 19) != 0) return ERR_CODE;  // the code-length code must be complete
-            idx = 0;
-            while (idx < nlen + ndist) {
-                refill(b);
-                int sym = decode_sym<STRIDE>(b, lcount, lsym);
-                if (sym < 0) return ERR_CODE;
-                if (sym < 16) {
-                    lengths[idx++] = (uint8_t)sym;
-                } else {
-                    int prev = 0, rep;
-                    if (sym == 16) {
-                        if (idx == 0) return ERR_CODE;
-                        prev = lengths[idx - 1];
-                        rep = 3 + (int)take(b, 2);
-                    } else if (sym == 17) {
-                        rep = 3 + (int)take(b, 3);
-                    } else {
-                        rep = 11 + (int)take(b, 7);
-                    }
-                    if (idx + rep > nlen + ndist) return ERR_CODE;
-                    while (rep--) lengths[idx++] = (uint8_t)prev;
+            (void)packed[2];
+            GZI_SYNC();
+            if (lane == 0) {
+                const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                for (int idx = 0; idx < 19; idx++) {
+                    const uint32_t v = idx < 10 ? (packed[0] >> (3 * idx)) & 7u : (packed[1] >> (3 * (idx - 10))) & 7u;
+                    T.lengths[order[idx]] = (uint8_t)(idx < ncode ? v : 0u);
                 }
             }
-            if (lengths[256] == 0) return ERR_CODE;  // no end-of-block code
-            int err = construct<STRIDE>(lcount, lsym, lengths, nlen);
-            if (err < 0 || (err > 0 && nlen - lcount[0] != 1)) return ERR_CODE;
-            err = construct<STRIDE>(dcount, dsym, lengths + nlen, ndist);
-            if (err < 0 || (err > 0 && ndist - dcount[0] != 1)) return ERR_CODE;
+            GZI_SYNC();
+            // its tables live where the distance tables will be (19 symbols, codes of at most 7 bits <= DBITS)
+            if (construct<LANES, DBITS>(T.dcount, T.dsym, T.dlut, T.lengths, 19, lane) != 0) return ERR_CODE;  // must be complete
+            int idx = 0, prev = 0;
+            bool have_eob = false;
+            while (idx < nlen + ndist) {
+                refill(b);
+                const int sym = decode_sym<DBITS>(b, T.dlut, T.dcount, T.dsym);
+                if (sym < 0) return ERR_CODE;
+                int rep = 1, val = sym;
+                if (sym == 16) {
+                    if (idx == 0) return ERR_CODE;
+                    val = prev;
+                    rep = 3 + (int)take(b, 2);
+                } else if (sym == 17) {
+                    val = 0;
+                    rep = 3 + (int)take(b, 3);
+                } else if (sym == 18) {
+                    val = 0;
+                    rep = 11 + (int)take(b, 7);
+                }
+                if (idx + rep > nlen + ndist) return ERR_CODE;
+                if (val != 0 && idx <= 256 && idx + rep > 256) have_eob = true;
+                // literal/length lengths at [0, nlen), distance lengths behind them at [nlen, nlen + ndist)
+                for (int r = lane; r < rep; r += LANES) T.lengths[idx + r] = (uint8_t)val;
+                idx += rep;
+                prev = val;
+            }
+            if (!have_eob) return ERR_CODE;  // no end-of-block code
+            GZI_SYNC();
+            // the distance code first: the code-length tables in its place are done with
+            int err = construct<LANES, DBITS>(T.dcount, T.dsym, T.dlut, T.lengths + nlen, ndist, lane);
+            if (err < 0 || (err > 0 && ndist - (int)T.dcount[0] != 1)) return ERR_CODE;
+            err = construct<LANES, LBITS>(T.lcount, T.lsym, T.llut, T.lengths, nlen, lane);
+            if (err < 0 || (err > 0 && nlen - (int)T.lcount[0] != 1)) return ERR_CODE;
         }
         for (;;) {  // the symbols of the block
             refill(b);
-            int sym = decode_sym<STRIDE>(b, lcount, lsym);
+            int sym = decode_sym<LBITS>(b, T.llut, T.lcount, T.lsym);
             if (sym < 0) return ERR_CODE;
             if (sym < 256) {
                 if (out >= cap) return ERR_OVERRUN;
-                dst[out++] = (uint8_t)sym;
-                nl += sym == '\n';
+                if ((uint32_t)lane == out - flushed) mine = (uint8_t)sym;
+                out++;
+                if (out - flushed == (uint32_t)LANES) flush();
                 continue;
             }
             if (sym == 256) break;
@@ -226,7 +343,7 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
                 len = ((4u + (uint32_t)(sym & 3)) << e) + 3u + take(b, e);
             }
             refill(b);
-            const int ds = decode_sym<STRIDE>(b, dcount, dsym);
+            const int ds = decode_sym<DBITS>(b, T.dlut, T.dcount, T.dsym);
             if (ds < 0 || ds >= 30) return ERR_DIST;
             uint32_t dist;  // 1..32768: codes 0..3 are 1..4, then pairs of codes per extra-bit count
             if (ds < 4) {
@@ -237,21 +354,38 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             }
             if (dist > out) return ERR_DIST;
             if (out + len > cap) return ERR_OVERRUN;
-            for (uint32_t i = 0; i < len; i++) {
-                const uint8_t c = dst[out - dist + i];
-                dst[out + i] = c;
-                nl += c == '\n';
+            // The copy: byte i of the match is byte (i mod dist) of the `dist` bytes in front of it, which all exist
+            // already - no lane waits for another one's store.  Up to four loads per lane are in flight before the
+            // first store (the source was written a moment ago: every load is a round trip to L2).
+            flush();
+            GZI_SYNC();  // the stores of the other lanes (literals, earlier copies) are visible
+            uint8_t* d = dst + out;
+            const uint8_t* sp = d - dist;
+            for (uint32_t base = 0; base < len; base += 4u * LANES) {
+                uint8_t v[4];
+                GZI_UNROLL
+                for (uint32_t k = 0; k < 4; k++) {
+                    const uint32_t i = base + k * LANES + (uint32_t)lane;
+                    if (i < len) v[k] = sp[i < dist ? i : i % dist];
+                }
+                GZI_UNROLL
+                for (uint32_t k = 0; k < 4; k++) {
+                    const uint32_t i = base + k * LANES + (uint32_t)lane;
+                    if (i < len) d[i] = v[k];
+                }
             }
             out += len;
+            flushed = out;
         }
     } while (!last);
-    // trailer: CRC-32 (not verified here), ISIZE
+    flush();
+    GZI_SYNC();
+    // trailer: CRC-32 (verified by the caller), ISIZE
     const uint8_t* tr = b.p - (b.cnt >> 3);
     if (tr + 8 > b.end) return ERR_TRAILER;
     const uint32_t isize = tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
     if (isize != out) return ERR_TRAILER;
     *produced = out;
-    *lines = nl;
     return OK;
 }
 

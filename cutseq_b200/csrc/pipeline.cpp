@@ -170,6 +170,7 @@ struct OutStream {
     bool gzip = false;
     int level = 1;
     uint64_t pos = 0;  // next free file offset
+    bool seekable = true;  // false: a pipe (the .bz2 / .xz transcoders, process substitution) - written in order with write()
 };
 
 bool ends_with_gz(const char* p) {
@@ -187,6 +188,19 @@ bool full_pwrite(int fd, const uint8_t* p, size_t n, uint64_t off) {
         p += w;
         n -= (size_t)w;
         off += (uint64_t)w;
+    }
+    return true;
+}
+
+bool full_write(int fd, const uint8_t* p, size_t n) {
+    while (n) {
+        const ssize_t w = write(fd, p, n);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += w;
+        n -= (size_t)w;
     }
     return true;
 }
@@ -465,6 +479,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     destroy_plans();
                     return CSQ_ERR_IO;
                 }
+                o.seekable = lseek(o.fd, 0, SEEK_CUR) != (off_t)-1;
             }
 
     Shared sh;
@@ -509,7 +524,17 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             const size_t n = o.gzip && !device_gzip ? pc.z.size() : pc.n;
             pc.file_off = o.pos;
             o.pos += n;
-            if (n) n_parts++;
+            if (n && !o.seekable) {  // batches are sized in order, so this is the stream order
+                const auto t0 = Clock::now();
+                if (!sh.stop && !full_write(o.fd, o.gzip && !device_gzip ? pc.z.data() : pc.src, n)) {
+                    char msg[512];
+                    snprintf(msg, sizeof(msg), "write to %s failed: %s", o.path.c_str(), strerror(errno));
+                    sh.fail(CSQ_ERR_IO, msg);
+                }
+                add_time(t_write, seconds_since(t0));
+            } else if (n) {
+                n_parts++;
+            }
         }
         if (n_parts == 0) {  // nothing to write (w_m is held)
             written++;
@@ -522,7 +547,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             OutStream& o = outs[pc.d][pc.m];
             const bool host_z = o.gzip && !device_gzip;
             const size_t n = host_z ? pc.z.size() : pc.n;
-            if (!n) continue;
+            if (!n || !o.seekable) continue;
             Job::Piece* p = &pc;
             pool.run([&, j, p, host_z, n] {
                 if (!sh.stop) {
@@ -1068,7 +1093,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             if (o.fd < 0) continue;
             if (o.gzip && o.pos == 0 && !sh.err_code) {  // an empty gzip file is still a valid (empty) member, like xopen writes
                 std::vector<uint8_t> z;
-                if (csqio::gzip_member((const uint8_t*)"", 0, o.level, z) || !full_pwrite(o.fd, z.data(), z.size(), 0))
+                if (csqio::gzip_member((const uint8_t*)"", 0, o.level, z) || !full_write(o.fd, z.data(), z.size()))
                     sh.fail(CSQ_ERR_IO, "cannot write the empty gzip member");
             }
             if (close(o.fd) != 0 && !sh.err_code) sh.fail(CSQ_ERR_IO, "closing an output file failed");

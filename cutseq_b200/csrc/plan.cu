@@ -117,6 +117,7 @@ struct csq_plan {
     unsigned long long* counters = nullptr;  // device csq_counters
     int* error_flag = nullptr;
     uint32_t* gz_tables = nullptr;           // device: CRC-32 byte table [256] | fold operators [GZ_THREADS]
+    uint32_t* crc_check_tables = nullptr;    // device: tables of the member CRC check behind the device inflate [768]
     uint64_t launches = 0;
 };
 
@@ -414,6 +415,7 @@ int inflate_mate(csq_plan* plan, Slot& s, int m, const csq_bgzf_in& bi, uint32_t
         ip.out = base + TEXT_FRONT_PAD;
         ip.lines = lines_dev;
         ip.status = s.inflate_status;
+        ip.crc_tables = plan->crc_check_tables;
         CUDA_TRY(csq_launch_inflate(ip, st));
         plan->launches += 1;
     }
@@ -708,7 +710,8 @@ int check_parse_error(Slot& s) {
     if (!s.text_mode) return 0;
     if (s.bgzf_mode) {
         const int32_t st = *(const int32_t*)(s.totals_host + 16);
-        if (st != 0x7F7F7F7F) return fail(CSQ_ERR_IO, "corrupt BGZF member %d of the batch (inflate error %d)", st / 16, st % 16);
+        if (st != 0x7F7F7F7F)
+            return fail(CSQ_ERR_IO, "corrupt BGZF member %d of the batch (%s)", st / 16, st % 16 == 7 ? "CRC-32 mismatch" : "invalid DEFLATE data");
     }
     for (int m = 0; m < s.n_mates; m++) {
         const unsigned long long key = s.totals_host[14 + m];
@@ -802,6 +805,12 @@ int csq_plan_create(const csq_op* ops_r1, int n1, const csq_op* ops_r2, int n2, 
     if (e == cudaSuccess) e = cudaMemset(plan->counters, 0, sizeof(csq_counters));
     if (e == cudaSuccess) e = cudaMalloc((void**)&plan->error_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(plan->error_flag, 0, sizeof(int));
+    if (e == cudaSuccess) {
+        std::vector<uint32_t> tab(768);
+        csq_gz_crc_check_tables(tab.data());
+        e = cudaMalloc((void**)&plan->crc_check_tables, tab.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(plan->crc_check_tables, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess && (flags & CSQ_PLAN_GZIP_OUT)) {
         std::vector<uint32_t> tab(256 + GZ_THREADS);
         csq_gz_host_tables(tab.data(), tab.data() + 256);
@@ -860,6 +869,7 @@ void csq_plan_destroy(csq_plan* plan) {
     if (plan->counters) cudaFree(plan->counters);
     if (plan->error_flag) cudaFree(plan->error_flag);
     if (plan->gz_tables) cudaFree(plan->gz_tables);
+    if (plan->crc_check_tables) cudaFree(plan->crc_check_tables);
     delete plan;
 }
 
@@ -937,7 +947,8 @@ int csq_bgzf_count_lines(csq_plan* plan, int slot, const csq_bgzf_in* in, uint32
     CUDA_TRY(cudaMemcpyAsync(s.totals_host + 16, s.inflate_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     const int32_t st = *(const int32_t*)(s.totals_host + 16);
-    if (st != 0x7F7F7F7F) return fail(CSQ_ERR_IO, "corrupt BGZF member %d of the range (inflate error %d)", st / 16, st % 16);
+    if (st != 0x7F7F7F7F)
+        return fail(CSQ_ERR_IO, "corrupt BGZF member %d of the range (%s)", st / 16, st % 16 == 7 ? "CRC-32 mismatch" : "invalid DEFLATE data");
     return 0;
 }
 
