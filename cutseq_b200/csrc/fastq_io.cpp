@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -32,42 +33,90 @@ int io_fail(int code, const char* fmt, ...) {
 const char* io_error() { return g_io_err; }
 
 // ---- pinned (or plain, when no CUDA context can be had) host memory ----------------------
+// cudaHostAlloc pins ~2 GB/s (one thread faults, zeroes and locks every page); a whole-file run needs a few GB of
+// batch buffers before its first batch, so large buffers are mapped here, first-touched by several threads and
+// then registered (cudaHostRegister only has to lock and map pages that exist): 5 - 8 GB/s, and several buffers can
+// be prepared side by side (measured: scripts/pin_probe2.py).
 static std::atomic<int> g_pinning(1);  // cleared after the first failure (CPU-only host): do not retry per buffer
+constexpr size_t MAP_THRESHOLD = 4u << 20;
 
-void* host_alloc(size_t bytes) {
-    if (!g_pinning.load(std::memory_order_relaxed)) return nullptr;
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p;
-    cudaGetLastError();
-    g_pinning.store(0, std::memory_order_relaxed);
-    return nullptr;
+static void first_touch(uint8_t* p, size_t bytes, int threads) {
+    const size_t page = 4096;
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > bytes / (8u << 20) + 1) threads = (int)(bytes / (8u << 20) + 1);
+    const size_t per = ((bytes + (size_t)threads - 1) / (size_t)threads + page - 1) & ~(page - 1);
+    auto work = [&](int t) {
+        const size_t lo = (size_t)t * per, hi = lo + per < bytes ? lo + per : bytes;
+        for (size_t o = lo; o < hi; o += page) ((volatile uint8_t*)p)[o] = 0;
+    };
+    std::vector<std::thread> helpers;
+    for (int t = 1; t < threads; t++) helpers.emplace_back(work, t);
+    work(0);
+    for (auto& h : helpers) h.join();
 }
 
 PinnedBuf::~PinnedBuf() { release(); }
 void PinnedBuf::release() {
     if (p) {
-        if (pinned)
+        if (kind == 1) {
             cudaFreeHost(p);
-        else
+        } else if (kind == 2 || kind == 3) {
+            if (kind == 2) cudaHostUnregister(p);
+            munmap(p, map_len);
+        } else {
             free(p);
+        }
     }
     p = nullptr;
     cap = 0;
+    kind = 0;
+    pinned = false;
 }
-bool PinnedBuf::reserve(size_t bytes, size_t keep) {
+bool PinnedBuf::reserve(size_t bytes, size_t keep, int touch_threads) {
     if (bytes <= cap) return true;
     // pinned allocations are expensive: grow geometrically (x2) and never below 64 KiB
     size_t want = bytes > 2 * cap ? bytes : 2 * cap;
     if (want < (64u << 10)) want = 64u << 10;
-    void* q = host_alloc(want);
-    bool pin = q != nullptr;
-    if (!q) q = malloc(want);
+    void* q = nullptr;
+    int k = 0;
+    size_t len = 0;
+    const bool try_pin = g_pinning.load(std::memory_order_relaxed) != 0;
+    if (try_pin && want >= MAP_THRESHOLD) {
+        len = (want + ((2u << 20) - 1)) & ~(size_t)((2u << 20) - 1);
+        void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, len, MADV_HUGEPAGE);
+            first_touch((uint8_t*)m, len, touch_threads);
+            if (cudaHostRegister(m, len, cudaHostRegisterPortable) == cudaSuccess) {
+                q = m;
+                k = 2;
+            } else {
+                cudaGetLastError();
+                munmap(m, len);
+            }
+        }
+    }
+    if (!q && try_pin) {
+        if (cudaHostAlloc(&q, want, cudaHostAllocPortable) == cudaSuccess) {
+            k = 1;
+        } else {
+            cudaGetLastError();
+            g_pinning.store(0, std::memory_order_relaxed);
+            q = nullptr;
+        }
+    }
+    if (!q) {
+        q = malloc(want);
+        k = 0;
+    }
     if (!q) return false;
     if (p && keep) memcpy(q, p, keep);
     release();
     p = (uint8_t*)q;
     cap = want;
-    pinned = pin;
+    kind = k;
+    map_len = len;
+    pinned = k == 1 || k == 2;
     return true;
 }
 

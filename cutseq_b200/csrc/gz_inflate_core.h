@@ -44,25 +44,28 @@ struct Tables {  // per group (device: shared memory, 3.6 KB per warp)
 };
 
 struct BitIn {
-    const uint8_t* p;    // next input byte
+    const uint8_t* p;    // next input word (4-byte aligned)
     const uint8_t* end;  // one past the member
     uint64_t buf;
     int cnt;
 };
 
-GZI_HD void refill(BitIn& b) {  // at least 33 bits afterwards (zeros behind the end of the member)
-    while (b.cnt <= 32) {
-        // four bytes at a time once the pointer is aligned; reading up to 3 bytes behind `end` is allowed (padding)
-        if ((((uintptr_t)b.p) & 3u) == 0) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(b.p);
-            b.buf |= (uint64_t)w << b.cnt;
-            b.cnt += 32;
-            b.p += 4;
-        } else {
-            b.buf |= (uint64_t)(*b.p) << b.cnt;
-            b.cnt += 8;
-            b.p += 1;
-        }
+// Input is read in aligned 32-bit words (the compressed buffer is padded, and reading the bytes in front of a member
+// is harmless): starting at byte address q means loading the word that holds it and dropping the bytes in front.
+GZI_HD void start(BitIn& b, const uint8_t* q) {
+    const uint32_t mis = (uint32_t)((uintptr_t)q & 3u);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(q - mis);
+    b.buf = (uint64_t)(w >> (8u * mis));
+    b.cnt = 32 - 8 * (int)mis;
+    b.p = q - mis + 4;
+}
+GZI_HD const uint8_t* byte_pos(const BitIn& b) { return b.p - (b.cnt >> 3); }  // next unread byte (at a byte boundary)
+GZI_HD void refill(BitIn& b) {  // at least 33 bits afterwards (whatever lies behind the member: zeros or the next one)
+    if (b.cnt <= 32) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(b.p);
+        b.buf |= (uint64_t)w << b.cnt;
+        b.cnt += 32;
+        b.p += 4;
     }
 }
 GZI_HD uint32_t take(BitIn& b, int n) {  // n <= 16, after refill
@@ -218,15 +221,12 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
     }
     if (flg & 2u) pos += 2;
     if (pos + 8 > n) return ERR_HEADER;
-    BitIn b = {src + pos, src + n, 0, 0};
-    // out: bytes produced so far; the last out - flushed of them (< LANES, literals) still sit in `mine` of lanes
-    // 0 .. out - flushed - 1
-    uint32_t out = 0, flushed = 0;
-    uint8_t mine = 0;
-    auto flush = [&] {
-        if ((uint32_t)lane < out - flushed) dst[flushed + (uint32_t)lane] = mine;
-        flushed = out;
-    };
+    BitIn b;
+    b.end = src + n;
+    start(b, src + pos);
+    // out: bytes in dst; behind them `pend` (< LANES) literals that still sit in `mine` of lanes 0 .. pend - 1
+    uint32_t out = 0, pend = 0;
+    uint32_t mine = 0;
     int last;
     do {
         refill(b);
@@ -239,16 +239,14 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             refill(b);
             const uint32_t nlen = take(b, 16);
             if ((len ^ 0xFFFFu) != nlen) return ERR_BLOCK;
-            // give the whole bytes in the bit buffer back
-            const uint8_t* q = b.p - (b.cnt >> 3);
-            b.buf = 0;
-            b.cnt = 0;
-            if (q + len > b.end || out + len > cap) return ERR_OVERRUN;
-            flush();
+            const uint8_t* q = byte_pos(b);  // the whole bytes in the bit buffer are given back
+            if (q + len > b.end || out + pend + len > cap) return ERR_OVERRUN;
+            if ((uint32_t)lane < pend) dst[out + (uint32_t)lane] = (uint8_t)mine;
+            out += pend;
+            pend = 0;
             for (uint32_t i = (uint32_t)lane; i < len; i += LANES) dst[out + i] = q[i];
             out += len;
-            flushed = out;
-            b.p = q + len;
+            start(b, q + len);
             continue;
         }
         if (type == 3) return ERR_BLOCK;
@@ -264,7 +262,7 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             const int nlen = (int)take(b, 5) + 257, ndist = (int)take(b, 5) + 1, ncode = (int)take(b, 4) + 4;
             if (nlen > MAXLCODES || ndist > MAXDCODES) return ERR_CODE;
             // the code-length code: 19 lengths of 3 bits in a fixed order, read by every lane, stored by lane 0
-            uint32_t packed[3] = {0, 0, 0};  // 19 x 3 bits, by position in the stream
+            uint32_t packed[2] = {0, 0};  // 19 x 3 bits, by position in the stream
             for (int idx = 0; idx < ncode; idx++) {
                 refill(b);
                 const uint32_t v = take(b, 3);
@@ -273,7 +271,6 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
                 else
                     packed[1] |= v << (3 * (idx - 10));
             }
-            (void)packed[2];
             GZI_SYNC();
             if (lane == 0) {
                 const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -319,14 +316,43 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             if (err < 0 || (err > 0 && nlen - (int)T.lcount[0] != 1)) return ERR_CODE;
         }
         for (;;) {  // the symbols of the block
-            refill(b);
-            int sym = decode_sym<LBITS>(b, T.llut, T.lcount, T.lsym);
-            if (sym < 0) return ERR_CODE;
-            if (sym < 256) {
-                if (out >= cap) return ERR_OVERRUN;
-                if ((uint32_t)lane == out - flushed) mine = (uint8_t)sym;
-                out++;
-                if (out - flushed == (uint32_t)LANES) flush();
+            // literals whose code sits in the direct table: the loop FASTQ text spends most of its symbols in
+            uint32_t e;
+            for (;;) {
+                refill(b);
+                e = T.llut[(uint32_t)b.buf & ((1u << LBITS) - 1u)];
+                if (e - 1u >= (256u << 4) - 1u) break;  // not in the table, a length code or the end of the block
+                const int nb = (int)(e & 15u);
+                b.buf >>= nb;
+                b.cnt -= nb;
+                if ((uint32_t)lane == pend) mine = e >> 4;
+                pend++;
+                if (pend == (uint32_t)LANES) {
+                    if (out + LANES > cap) return ERR_OVERRUN;
+                    dst[out + (uint32_t)lane] = (uint8_t)mine;
+                    out += LANES;
+                    pend = 0;
+                }
+            }
+            int sym;
+            if (e) {
+                const int nb = (int)(e & 15u);
+                b.buf >>= nb;
+                b.cnt -= nb;
+                sym = (int)(e >> 4);
+            } else {
+                sym = decode_slow(b, T.lcount, T.lsym);
+                if (sym < 0) return ERR_CODE;
+            }
+            if (sym < 256) {  // a literal with a long code
+                if ((uint32_t)lane == pend) mine = (uint32_t)sym;
+                pend++;
+                if (pend == (uint32_t)LANES) {
+                    if (out + LANES > cap) return ERR_OVERRUN;
+                    dst[out + (uint32_t)lane] = (uint8_t)mine;
+                    out += LANES;
+                    pend = 0;
+                }
                 continue;
             }
             if (sym == 256) break;
@@ -339,8 +365,8 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             } else if (sym == 28) {
                 len = 258u;
             } else {
-                const int e = (sym >> 2) - 1;
-                len = ((4u + (uint32_t)(sym & 3)) << e) + 3u + take(b, e);
+                const int x = (sym >> 2) - 1;
+                len = ((4u + (uint32_t)(sym & 3)) << x) + 3u + take(b, x);
             }
             refill(b);
             const int ds = decode_sym<DBITS>(b, T.dlut, T.dcount, T.dsym);
@@ -349,39 +375,60 @@ GZI_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             if (ds < 4) {
                 dist = 1u + (uint32_t)ds;
             } else {
-                const int e = (ds >> 1) - 1;
-                dist = ((2u + (uint32_t)(ds & 1)) << e) + 1u + take(b, e);
+                const int x = (ds >> 1) - 1;
+                dist = ((2u + (uint32_t)(ds & 1)) << x) + 1u + take(b, x);
             }
+            // the pending literals first
+            if (out + pend + len > cap) return ERR_OVERRUN;
+            if ((uint32_t)lane < pend) dst[out + (uint32_t)lane] = (uint8_t)mine;
+            out += pend;
+            pend = 0;
             if (dist > out) return ERR_DIST;
-            if (out + len > cap) return ERR_OVERRUN;
             // The copy: byte i of the match is byte (i mod dist) of the `dist` bytes in front of it, which all exist
-            // already - no lane waits for another one's store.  Up to four loads per lane are in flight before the
-            // first store (the source was written a moment ago: every load is a round trip to L2).
-            flush();
+            // already - no lane waits for another one's store.  The source was written a moment ago (every load is a
+            // round trip to L2), so the loads of a long copy are issued before its first store.
             GZI_SYNC();  // the stores of the other lanes (literals, earlier copies) are visible
             uint8_t* d = dst + out;
             const uint8_t* sp = d - dist;
-            for (uint32_t base = 0; base < len; base += 4u * LANES) {
-                uint8_t v[4];
-                GZI_UNROLL
-                for (uint32_t k = 0; k < 4; k++) {
-                    const uint32_t i = base + k * LANES + (uint32_t)lane;
-                    if (i < len) v[k] = sp[i < dist ? i : i % dist];
+            if (dist >= len) {
+                if (len <= (uint32_t)LANES) {
+                    if ((uint32_t)lane < len) d[lane] = sp[lane];
+                } else {
+                    for (uint32_t base = 0; base < len; base += 4u * LANES) {
+                        uint8_t v[4];
+                        GZI_UNROLL
+                        for (uint32_t k = 0; k < 4; k++) {
+                            const uint32_t i = base + k * LANES + (uint32_t)lane;
+                            if (i < len) v[k] = sp[i];
+                        }
+                        GZI_UNROLL
+                        for (uint32_t k = 0; k < 4; k++) {
+                            const uint32_t i = base + k * LANES + (uint32_t)lane;
+                            if (i < len) d[i] = v[k];
+                        }
+                    }
                 }
-                GZI_UNROLL
-                for (uint32_t k = 0; k < 4; k++) {
-                    const uint32_t i = base + k * LANES + (uint32_t)lane;
-                    if (i < len) d[i] = v[k];
+            } else if (dist == 1) {  // a run of one byte
+                const uint8_t c = sp[0];
+                for (uint32_t i = (uint32_t)lane; i < len; i += LANES) d[i] = c;
+            } else {  // a period shorter than the match
+                uint32_t r = (uint32_t)lane % dist;
+                const uint32_t step = (uint32_t)LANES % dist;
+                for (uint32_t i = (uint32_t)lane; i < len; i += LANES) {
+                    d[i] = sp[r];
+                    r += step;
+                    if (r >= dist) r -= dist;
                 }
             }
             out += len;
-            flushed = out;
         }
     } while (!last);
-    flush();
+    if (out + pend > cap) return ERR_OVERRUN;
+    if ((uint32_t)lane < pend) dst[out + (uint32_t)lane] = (uint8_t)mine;
+    out += pend;
     GZI_SYNC();
     // trailer: CRC-32 (verified by the caller), ISIZE
-    const uint8_t* tr = b.p - (b.cnt >> 3);
+    const uint8_t* tr = byte_pos(b);
     if (tr + 8 > b.end) return ERR_TRAILER;
     const uint32_t isize = tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
     if (isize != out) return ERR_TRAILER;

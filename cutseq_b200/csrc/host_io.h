@@ -18,8 +18,13 @@ struct PinnedBuf {  // growable host buffer, pinned when a CUDA context is avail
     uint8_t* p = nullptr;
     size_t cap = 0;
     bool pinned = false;
+    int kind = 0;        // 0 malloc, 1 cudaHostAlloc, 2 mmap + cudaHostRegister
+    size_t map_len = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
     ~PinnedBuf();
-    bool reserve(size_t bytes, size_t keep);
+    bool reserve(size_t bytes, size_t keep, int touch_threads = 4);
     void release();
 };
 

@@ -488,12 +488,88 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     Queue<Job*> free_q, ready_q;
     sh.free_q = &free_q;
     sh.ready_q = &ready_q;
-    for (int i = 0; i < n_jobs; i++) {
-        jobs.emplace_back(new Job());
-        free_q.push(jobs.back().get());
-    }
+    for (int i = 0; i < n_jobs; i++) jobs.emplace_back(new Job());
     std::unique_ptr<Pool> pool_owner(new Pool(std::max(2, n_threads)));
     Pool& pool = *pool_owner;
+
+    // ---- host buffers of the jobs: sized from a sample of the input and pinned side by side before the first batch
+    // (pinning is the fixed cost of a run: ~2 GB/s when the batches allocate one after the other as they come) ----
+    auto output_sizes = [&](const uint64_t text[2], uint32_t n, uint64_t want[CSQ_N_DEST][2]) {
+        for (int m = 0; m < 2; m++) {
+            uint64_t full = 64;
+            if (m < n_mates) {
+                full = text[m] + 64ull * n + 4096;  // renaming can only shorten a record, bar "_" + UMI
+                if (device_gzip) full = full / 2;   // the packed size is reported when this guess is too small
+            }
+            for (int d = 0; d < CSQ_N_DEST; d++) want[d][m] = m >= n_mates ? 64 : d == CSQ_DEST_TRIMMED ? full : full / 8 + 4096;
+        }
+    };
+    {
+        uint64_t est_text[2] = {0, 0}, est_load[2] = {0, 0};
+        double n_batches_est = 0;
+        bool have_est = mode != 2;
+        for (int m = 0; m < n_mates && have_est; m++) {
+            double bpr = 0, ratio = 1.0;  // text bytes per record, compressed / text bytes
+            uint64_t total_text = 0;
+            if (mode == 0) {
+                const size_t sample = (size_t)std::min<uint64_t>(inf[m].size, 4u << 20);
+                const uint64_t lines = csqio::count_newlines(inf[m].map, sample);
+                if (lines >= 4) bpr = (double)sample / ((double)lines / 4.0);
+                total_text = inf[m].size;
+            } else {
+                for (size_t i = 0; i < inf[m].isize.size() && bpr == 0; i++) {
+                    if (!inf[m].isize[i]) continue;
+                    std::vector<uint8_t> text(inf[m].isize[i] + 64);
+                    csqio::Inflater inflater;
+                    inflater.reset(inf[m].map + inf[m].moff[i], (size_t)(inf[m].moff[i + 1] - inf[m].moff[i]));
+                    const long got = inflater.read(text.data(), inf[m].isize[i]);
+                    const uint64_t lines = got > 0 ? csqio::count_newlines(text.data(), (size_t)got) : 0;
+                    if (lines >= 4) bpr = (double)got / ((double)lines / 4.0);
+                    break;
+                }
+                for (uint32_t v : inf[m].isize) total_text += v;
+                if (total_text) ratio = (double)inf[m].size / (double)total_text;
+            }
+            if (bpr <= 0) {
+                have_est = false;
+                break;
+            }
+            const double batch_text = std::min((double)batch_reads * bpr * 1.02 + 65536.0, (double)total_text + 65536.0);
+            est_text[m] = (uint64_t)batch_text;
+            est_load[m] = (uint64_t)(batch_text * ratio * (mode == 1 ? 1.06 : 1.0)) + 65536;
+            if (mode == 1) est_load[m] = std::max<uint64_t>(est_load[m], std::min<uint64_t>(inf[m].size, (48ull << 20) + 65536));
+            n_batches_est = std::max(n_batches_est, (double)total_text / std::max(1.0, (double)batch_reads * bpr));
+        }
+        const int n_warm = have_est ? (int)std::min<double>((double)n_jobs, n_batches_est + 1.0 + (mode == 1 ? 2.0 : 0.0)) : 0;
+        for (int i = 0; i < n_jobs; i++) {
+            Job* j = jobs[(size_t)i].get();
+            if (i >= n_warm) {
+                free_q.push(j);
+                continue;
+            }
+            uint64_t want[CSQ_N_DEST][2];
+            output_sizes(est_text, batch_reads, want);
+            j->parts = n_mates + CSQ_N_DEST * 2;
+            auto done_one = [&free_q, j] {
+                if (--j->parts == 0) free_q.push(j);
+            };
+            for (int m = 0; m < n_mates; m++) {
+                const size_t need = (size_t)est_load[m] + 64;
+                pool.run([j, m, need, done_one] {
+                    j->in_buf[m].reserve(need + need / 8, 0, 2);  // a failure shows when the batch reserves for real
+                    done_one();
+                });
+            }
+            for (int d = 0; d < CSQ_N_DEST; d++)
+                for (int m = 0; m < 2; m++) {
+                    const size_t need = (size_t)want[d][m];
+                    pool.run([j, d, m, need, done_one] {
+                        j->outbuf[d][m].reserve(need + need / 8, 0, 2);
+                        done_one();
+                    });
+                }
+        }
+    }
     std::atomic<double> t_read{0}, t_write{0};
     auto add_time = [](std::atomic<double>& a, double v) {
         double cur = a.load();
@@ -970,22 +1046,16 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     std::vector<std::thread> workers;
     std::vector<double> gpu_total((size_t)n_dev, 0.0), gpu_kernel((size_t)n_dev, 0.0);
     auto size_job_outputs = [&](Job& j, bool first_try) -> bool {
-        for (int m = 0; m < 2; m++) {
-            uint64_t full = 64;
-            if (m < n_mates) {
-                const uint64_t text = j.kind == J_BGZF ? (j.ooff[m].empty() ? 0 : j.ooff[m].back()) : j.tin.mate[m].bytes;
-                const uint32_t n = j.kind == J_BGZF ? j.bin.n_reads : j.tin.n_reads;
-                full = text + 64ull * n + 4096;  // renaming can only shorten a record, bar "_" + UMI
-                if (device_gzip) full = full / 2;  // the packed size is reported when this guess is too small
-            }
+        uint64_t text[2] = {0, 0}, first[CSQ_N_DEST][2];
+        for (int m = 0; m < n_mates; m++) text[m] = j.kind == J_BGZF ? (j.ooff[m].empty() ? 0 : j.ooff[m].back()) : j.tin.mate[m].bytes;
+        output_sizes(text, j.kind == J_BGZF ? j.bin.n_reads : j.tin.n_reads, first);
+        for (int m = 0; m < 2; m++)
             for (int d = 0; d < CSQ_N_DEST; d++) {
-                uint64_t want = first_try ? (d == CSQ_DEST_TRIMMED ? full : full / 8 + 4096) : j.out.text[d][m].bytes + 4096;
-                if (m >= n_mates) want = 64;
+                const uint64_t want = first_try || m >= n_mates ? first[d][m] : j.out.text[d][m].bytes + 4096;
                 if (want > j.outbuf[d][m].cap && !j.outbuf[d][m].reserve(want + want / 8, 0)) return false;
                 j.out.text[d][m].data = j.outbuf[d][m].p;
                 j.out.text[d][m].capacity = j.outbuf[d][m].cap;
             }
-        }
         return true;
     };
     for (int d = 0; d < n_dev; d++) {
@@ -1126,10 +1196,11 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     // tear down side by side: un-pinning the jobs' host buffers and freeing the plans' device buffers are slow driver calls
     pool_owner.reset();  // joins the pool: no task refers to a job any more
     {
-        std::thread unpin([&] { jobs.clear(); });
+        std::vector<std::thread> unpin;
+        for (auto& j : jobs) unpin.emplace_back([&j] { j.reset(); });
         if (reader) csq_text_reader_close(reader);
         destroy_plans();
-        unpin.join();
+        for (auto& t : unpin) t.join();
     }
     stamp("teardown done");
     if (sh.err_code) {
