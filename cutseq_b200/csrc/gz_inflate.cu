@@ -20,17 +20,22 @@
 
 namespace {
 
-constexpr int INF_WARPS = 8;
+constexpr int INF_LANES = 32;    // lanes per member (16: two members per warp - measured, no gain: the halves of a warp do not stay on one path)
+constexpr int INF_GROUPS = 4;    // members per CTA
 
-__global__ void __launch_bounds__(INF_WARPS * 32) k_gz_inflate(const __grid_constant__ InflateParams P) {
-    __shared__ gzi::Tables tabs[INF_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t i = blockIdx.x * INF_WARPS + warp;
+__global__ void __launch_bounds__(INF_GROUPS * INF_LANES) k_gz_inflate(const __grid_constant__ InflateParams P) {
+    __shared__ gzi::Tables tabs[INF_GROUPS];
+    const int g = threadIdx.x / INF_LANES;
+    gzi::Group<INF_LANES> G;
+    G.lane = threadIdx.x % INF_LANES;
+    G.base = (threadIdx.x & 31) - G.lane;
+    G.mask = (INF_LANES == 32 ? 0xFFFFFFFFu : ((1u << (INF_LANES & 31)) - 1u)) << G.base;
+    const uint32_t i = blockIdx.x * INF_GROUPS + g;
     if (i >= P.n_members) return;
     const uint32_t s0 = P.moff[i], s1 = P.moff[i + 1], o0 = P.ooff[i], o1 = P.ooff[i + 1];
     uint32_t produced = 0;
-    const int rc = gzi::inflate_member<32>(P.comp + s0, s1 - s0, P.out + o0, o1 - o0, tabs[warp], lane, &produced);
-    if (lane == 0 && (rc != gzi::OK || produced != o1 - o0)) atomicMin(P.status, (rc ? rc : (int)gzi::ERR_TRAILER) + 16 * (int)min(i, 0x7FFFFFu));
+    const int rc = gzi::inflate_member<INF_LANES>(P.comp + s0, s1 - s0, P.out + o0, o1 - o0, tabs[g], G, &produced);
+    if (G.lane == 0 && (rc != gzi::OK || produced != o1 - o0)) atomicMin(P.status, (rc ? rc : (int)gzi::ERR_TRAILER) + 16 * (int)min(i, 0x7FFFFFu));
 }
 
 // Thread t takes the 256 bytes at 256 t of the member's text (members hold at most 64 KiB): line ends, and the CRC-32
@@ -107,7 +112,7 @@ void csq_gz_crc_check_tables(uint32_t* t /*[768]*/) {
 
 cudaError_t csq_launch_inflate(const InflateParams& p, cudaStream_t stream) {
     if (p.n_members == 0) return cudaSuccess;
-    k_gz_inflate<<<(p.n_members + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, stream>>>(p);
+    k_gz_inflate<<<(p.n_members + INF_GROUPS - 1) / INF_GROUPS, INF_GROUPS * INF_LANES, 0, stream>>>(p);
     k_gz_check<<<p.n_members, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
@@ -129,7 +134,8 @@ extern "C" int csq_gz_inflate_host(const uint8_t* src, uint64_t n, uint8_t* dst,
         padded.assign(src + pos, src + pos + size);
         padded.resize(size + 16, 0);  // the decoder may look a few bytes behind the member
         uint32_t produced = 0;
-        const int rc = gzi::inflate_member<1>(padded.data(), size, dst + out, isize, tab[0], 0, &produced);
+        gzi::Group<1> one = {0, 1u, 0};
+        const int rc = gzi::inflate_member<1>(padded.data(), size, dst + out, isize, tab[0], one, &produced);
         if (rc != gzi::OK) return -100 - rc;
         uint32_t crc = 0xFFFFFFFFu;
         for (uint32_t q = 0; q < produced; q++) {
