@@ -200,7 +200,7 @@ def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
                 outs = {"trimmed": [os.path.join(tmp, f"out{nd}_trimmed_R{m}{ext}") for m in (1, 2)],
                         "short": [os.path.join(tmp, f"out{nd}_short_R{m}{ext}") for m in (1, 2)]}
                 best = None
-                for rep in range(2 if nd == n_devices else 1):
+                for rep in range(2):
                     for q in outs["trimmed"] + outs["short"]:  # a fresh run writes new files
                         if os.path.exists(q):
                             os.remove(q)
@@ -303,7 +303,7 @@ def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, ma
         dt = max_over_ranks(w1 - w0)
         return {"value": world * steps * B * P / dt, "unit": UNIT, "h2d_bytes_per_step": comp_bytes * B, "d2h_bytes_per_step": int(d2h // steps),
                 "ms_per_step": dt / steps * 1e3, "steps": steps, "text_bytes_per_step": text_bytes * B,
-                "input": "BGZF members (zlib level 1, 0xFF00-byte pieces), inflated on the device, one thread per member",
+                "input": "BGZF members (zlib level 1, 0xFF00-byte pieces), inflated on the device, one warp per member",
                 "output": "gzip members (BGZF framing, dynamic-Huffman literal coding) encoded on the device",
                 "timing": f"wall clock between device-synchronised points, {n_fly} batches in flight through csq_submit_bgzf/csq_wait, max over ranks"}
     finally:
@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--no-e2e-gz", action="store_true", help="skip the end-to-end leg with compressed host buffers (BGZF in, gzip out)")
     ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
     ap.add_argument("--file-pairs", type=int, default=20_000_000, help="pairs in the plain whole-file leg (config 5: streamed, <= 20M-pair on-disk file)")
-    ap.add_argument("--file-pairs-gz", type=int, default=8_000_000, help="pairs in the .gz whole-file leg")
+    ap.add_argument("--file-pairs-gz", type=int, default=20_000_000, help="pairs in the .gz whole-file leg")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="stage", choices=["stage", "g16"], help="emit kernel (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
     ap.add_argument("--no-exact-stop", action="store_true", help="exact DP walks on after an error-free full match (CSQ_PLAN_NO_EXACT_STOP, A/B runs)")

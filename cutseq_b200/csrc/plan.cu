@@ -722,6 +722,10 @@ int check_parse_error(Slot& s) {
             case 2: return fail(CSQ_ERR_FORMAT, "input file %d: line %llu is expected to start with '+'", m + 1, line + 3);
             case 3: return fail(CSQ_ERR_FORMAT, "input file %d: length of sequence and qualities differ (record at line %llu)", m + 1, line + 1);
             case 4: return fail(CSQ_ERR_LIMIT, "input file %d: read at line %llu exceeds the supported %d bases", m + 1, line + 1, CSQ_MAX_READ_LEN);
+            case 6:
+                return fail(CSQ_ERR_FORMAT, "input file %d: sequence descriptions don't match at line %llu (the second description must be empty or equal to the first)",
+                            m + 1, line + 3);
+            case 7: return fail(CSQ_ERR_LIMIT, "input file %d: header at line %llu exceeds the supported 65535 bytes", m + 1, line + 1);
             default: return fail(CSQ_ERR_FORMAT, "input file %d: the batch does not hold %u whole FASTQ records (4 lines each)", m + 1, s.n);
         }
     }

@@ -64,8 +64,21 @@ __device__ __forceinline__ uint32_t finish_mate(const FinishParams& P, uint32_t 
         if ((known >> 3) > (unsigned long long)idx) {
             const uint8_t* se = P.md.seq + P.md.seq_off[idx] + len0;  // the line end behind the bases
             int bad = 0;
+            const uint8_t* pl = se + (se[0] == '\r' ? 2 : 1);         // the third line
             if (nm[-1] != '@') bad = 1;                                // PERR_AT
-            else if (se[se[0] == '\r' ? 2 : 1] != '+') bad = 2;        // PERR_PLUS
+            else if (pl[0] != '+') bad = 2;                            // PERR_PLUS
+            else if (nl > 65535) bad = 7;                              // PERR_HEADER_LIMIT (16-bit id fields of ReadState)
+            else {
+                // dnaio: a repeated header behind the '+' must be the header ("Sequence descriptions don't match")
+                const uint8_t* qs = P.md.qual + P.md.qual_off[idx];    // first quality; the line end sits in front of it
+                int pn = (int)(qs - 1 - pl) - 1;
+                if (pn > 0 && pl[pn] == '\r') pn--;
+                if (pn > 0) {
+                    bool same = pn == nl;
+                    for (int i = 0; same && i < nl; i++) same = pl[1 + i] == nm[i];
+                    if (!same) bad = 6;                                // PERR_PLUS_NAME
+                }
+            }
             if (bad) atomicMin(P.perr, ((unsigned long long)idx << 3) | (unsigned long long)bad);
         }
     }

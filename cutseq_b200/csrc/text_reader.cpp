@@ -111,10 +111,11 @@ int RawSource::open(const char* path) {
     if (fill() < 0) return CSQ_ERR_IO;
     gz = in_len >= 2 && inbuf[0] == 0x1f && inbuf[1] == 0x8b;
     const char* use_zlib = getenv("CSQ_ZLIB_INFLATE");
-    if (gz && !(use_zlib && use_zlib[0] == '1')) {
-        // the built-in decoder sees the whole compressed file at once
-        struct stat sb;
-        if (fstat(fd, &sb) != 0 || sb.st_size <= 0) return io_fail(CSQ_ERR_IO, "cannot stat %s: %s", path, strerror(errno));
+    struct stat sb;
+    // the built-in decoder sees the whole compressed file at once (mmap); a pipe (stdin, process substitution) streams
+    // through zlib instead
+    const bool mappable = fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0;
+    if (gz && mappable && !(use_zlib && use_zlib[0] == '1')) {
         void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (m == MAP_FAILED) return io_fail(CSQ_ERR_IO, "cannot map %s: %s", path, strerror(errno));
         madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);

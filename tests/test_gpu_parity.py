@@ -530,15 +530,23 @@ def oracle_text(prog, texts):
     (b"@r1\nACGT\n+\nIII\n@r2\nACGT\n+\nIIII\n", A.ERR_FORMAT, "length of sequence and qualities differ (record at line 1)"),
     (b"@r1\nACGT\n+\nIIII\n@r2\n" + b"A" * 900 + b"\n+\n" + b"I" * 900 + b"\n", A.ERR_LIMIT, "line 5"),
     (b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n+\n", A.ERR_FORMAT, "whole FASTQ records"),
+    # dnaio: a description repeated behind the '+' must equal the header
+    (b"@r1 x\nACGT\n+r1 x\nIIII\n@r2\nACGT\n+r3\nIIII\n", A.ERR_FORMAT, "descriptions don't match at line 7"),
+    (b"@r1 x\nACGT\n+r1\nIIII\n@r2\nACGT\n+\nIIII\n", A.ERR_FORMAT, "descriptions don't match at line 3"),
+    (b"@r1\nACGT\n+\nIIII\n@" + b"h" * 70000 + b"\nACGT\n+\nIIII\n", A.ERR_LIMIT, "header at line 5"),
 ])
 @pytest.mark.parametrize("pflags", PARSE_FLAGS, ids=PARSE_IDS)
 def test_text_batch_format_errors(bad, code, needle, pflags):
     prog = helpers.program_for(["-A", "SMALLRNA"], 1)
     with native.Plan(prog, 0, pflags) as plan:
         with pytest.raises(native.NativeError) as e:
-            plan.run_text([bad], 2, capacity=8192)
+            plan.run_text([bad], 2, capacity=8192 + len(bad))
         assert e.value.code == code and needle in str(e.value), str(e.value)
         # the plan stays usable
         good = b"@r1\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
         got, records = plan.run_text([good], 1, capacity=8192)
         assert got[0][0] == good and records[0][0] == 1
+        # a repeated description that matches is fine (and is not written again, like dnaio's fastq_bytes)
+        twice = b"@r1 c\r\nACGTACGTACGTACGTACGTACGTACGT\r\n+r1 c\r\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\r\n"
+        got, records = plan.run_text([twice], 1, capacity=8192)
+        assert got[0][0] == b"@r1 c\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\n" and records[0][0] == 1

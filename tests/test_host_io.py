@@ -254,6 +254,40 @@ def test_text_reader_cuts_whole_records(tmp_path, gz, tail):
         assert got1 == "".join(recs1).encode() and got2 == "".join(recs2).encode()
 
 
+@pytest.mark.parametrize("gz", [False, True], ids=["plain", "gzip"])
+def test_text_reader_reads_pipes(tmp_path, gz):
+    """Inputs that cannot be mapped (named pipes, process substitution, stdin): plain text streams through read(),
+    gzip data through zlib (xopen reads such inputs for the reference, run.py:434, 751)."""
+    import threading
+
+    recs = [_records(800, seed=5), _records(800, seed=6)]
+    fifos = [tmp_path / "a.fifo", tmp_path / "b.fifo"]
+    for f in fifos:
+        os.mkfifo(f)
+
+    def feed(path, text):
+        data = gzip.compress(text.encode()) if gz else text.encode()
+        with open(path, "wb") as w:
+            w.write(data)
+
+    pumps = [threading.Thread(target=feed, args=(str(f), "".join(r)), daemon=True) for f, r in zip(fifos, recs)]
+    for t in pumps:
+        t.start()
+    got, total = [b"", b""], 0
+    with native.TextReader(str(fifos[0]), str(fifos[1])) as r:
+        while True:
+            n, texts, _ = r.next(300)
+            if n == 0:
+                break
+            got[0] += texts[0]
+            got[1] += texts[1]
+            total += n
+    for t in pumps:
+        t.join(timeout=10)
+    assert total == 800
+    assert got[0] == "".join(recs[0]).encode() and got[1] == "".join(recs[1]).encode()
+
+
 @pytest.mark.parametrize("threads", ["1", "4", "7"])
 def test_text_reader_parallel_pread_of_plain_files(tmp_path, monkeypatch, threads):
     """Plain regular files: several threads pread() pieces of a batch; batches of very different sizes in one file
