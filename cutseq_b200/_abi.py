@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 CSQ_MAX_ADAPTER = 128
 CSQ_MAX_READ_LEN = 895
@@ -145,6 +145,7 @@ class csq_counters(C.Structure):
         ("quality_trimmed_bp", C.c_uint64 * 2),
         ("with_adapters", (C.c_uint64 * CSQ_MAX_OPS) * 2),
         ("dp_cells", (C.c_uint64 * CSQ_MAX_OPS) * 2),
+        ("adjacent_bases", (C.c_uint64 * 6) * 2),
     ]
 
 

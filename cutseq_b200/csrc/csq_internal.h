@@ -88,6 +88,7 @@ struct AlignParams {
     uint8_t letter;                    // homopolymer base
     unsigned long long* counters;      // csq_counters on the device
     int32_t counter_index;             // word index of with_adapters[mate][op] inside csq_counters
+    int32_t adjacent_index;            // word index of adjacent_bases[mate] (first ALIGN op of a mate, 3' kinds), else -1
 };
 
 struct FinishParams {
@@ -176,7 +177,7 @@ void csq_gz_crc_check_tables(uint32_t* t /*[768]*/);
 // word indices inside csq_counters viewed as uint64[]
 enum {
     CNT_N = 0, CNT_TOTAL_BP = 1, CNT_WRITTEN = 3, CNT_WRITTEN_BP = 4, CNT_TOO_SHORT = 6, CNT_UNTRIMMED = 7,
-    CNT_QTRIM_BP = 8, CNT_WITH_ADAPTERS = 10, CNT_DP_CELLS = 10 + 2 * CSQ_MAX_OPS
+    CNT_QTRIM_BP = 8, CNT_WITH_ADAPTERS = 10, CNT_DP_CELLS = 10 + 2 * CSQ_MAX_OPS, CNT_ADJACENT = 10 + 4 * CSQ_MAX_OPS
 };
 
 // launchers implemented in kernels.cu (all asynchronous on `stream`)

@@ -198,6 +198,11 @@ int parse_records(const uint8_t* text, size_t n_bytes, bool at_eof, uint32_t max
             return io_fail(CSQ_ERR_FORMAT, "%s: line %llu is expected to start with '@'", fname, (unsigned long long)(*line_no + 1));
         if (ll[2] == 0 || ls[2][0] != '+')
             return io_fail(CSQ_ERR_FORMAT, "%s: line %llu is expected to start with '+'", fname, (unsigned long long)(*line_no + 3));
+        if (ll[2] > 1 && (ll[2] != ll[0] || memcmp(ls[2] + 1, ls[0] + 1, ll[0] - 1) != 0))
+            return io_fail(CSQ_ERR_FORMAT, "%s: sequence descriptions don't match at line %llu (the second description must be empty or equal to the first)",
+                           fname, (unsigned long long)(*line_no + 3));
+        if (ll[0] - 1 > 65535)
+            return io_fail(CSQ_ERR_LIMIT, "%s: header at line %llu exceeds the supported 65535 bytes", fname, (unsigned long long)(*line_no + 1));
         if (ll[1] != ll[3])
             return io_fail(CSQ_ERR_FORMAT, "%s: length of sequence and qualities differ (record at line %llu)", fname,
                            (unsigned long long)(*line_no + 1));

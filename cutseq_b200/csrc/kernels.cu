@@ -259,6 +259,17 @@ __device__ __noinline__ void dp_generic(const uint8_t* __restrict__ s, int a, in
 }
 
 // M > 0: column in registers (dp_exact<M>); M == 0: any m <= CSQ_MAX_ADAPTER with the column in local memory
+// EndStatistics.adjacent_bases of cutadapt's BackAdapterStatistics.add_match: the read base in front of a 3' match
+// (match.sequence[rstart - 1 : rstart]; the read is original[a:b] here).  Slots: A, C, G, T, none, other.
+__device__ __forceinline__ void count_adjacent(const AlignParams& P, const uint8_t* s, int a, int query_start) {
+    int slot = 4;
+    if (query_start > 0) {
+        const uint8_t c = s[a + query_start - 1];
+        slot = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 5;
+    }
+    atomicAdd(P.counters + P.adjacent_index + slot, 1ULL);
+}
+
 template <int M>
 __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignParams P) {
     constexpr int NW = (M > 0 ? (M + 31) / 32 : 1);
@@ -325,6 +336,7 @@ __global__ void __launch_bounds__(128) k_align(const __grid_constant__ AlignPara
         dp_generic(s, st.a, st.b, P, j0, r);
     if (r.found) {
         st.matched |= 0x80000000u | (P.adapter_bit >= 0 ? (1u << P.adapter_bit) : 0u);
+        if (P.adjacent_index >= 0) count_adjacent(P, s, st.a, r.query_start);
         if (P.trim_front)
             st.a = (uint16_t)(st.a + r.query_stop);  // RemoveBeforeMatch: read[rstop:]
         else
@@ -882,6 +894,7 @@ __global__ void __launch_bounds__(128, 4) k_align_split(const __grid_constant__ 
         best_to_match(best, M, n, P.reversed != 0, r);
         if (r.found) {
             st.matched |= 0x80000000u | (P.adapter_bit >= 0 ? (1u << P.adapter_bit) : 0u);
+            if (P.adjacent_index >= 0) count_adjacent(P, P.md.seq + P.md.seq_off[idx], st.a, r.query_start);
             if (P.trim_front)
                 st.a = (uint16_t)(st.a + r.query_stop);
             else

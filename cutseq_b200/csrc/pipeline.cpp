@@ -492,8 +492,12 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     std::unique_ptr<Pool> pool_owner(new Pool(std::max(2, n_threads)));
     Pool& pool = *pool_owner;
 
-    // ---- host buffers of the jobs: sized from a sample of the input and pinned side by side before the first batch
-    // (pinning is the fixed cost of a run: ~2 GB/s when the batches allocate one after the other as they come) ----
+    // ---- host buffers of the jobs: sized from a sample of the input and pinned side by side, by a few threads of their
+    // own, while the first batches are already on their way (pinning is the fixed cost of a run: ~2 GB/s when the
+    // batches allocate one after the other as they come; a job joins the circulation when its buffers are there) ----
+    std::unique_ptr<Pool> warm_owner(new Pool(std::max(2, std::min(8, n_threads / 2))));
+    Pool& warm = *warm_owner;
+    std::atomic<bool> warm_stop{false};  // the run is over: buffers nobody will use are not pinned any more
     auto output_sizes = [&](const uint64_t text[2], uint32_t n, uint64_t want[CSQ_N_DEST][2]) {
         for (int m = 0; m < 2; m++) {
             uint64_t full = 64;
@@ -555,16 +559,16 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             };
             for (int m = 0; m < n_mates; m++) {
                 const size_t need = (size_t)est_load[m] + 64;
-                pool.run([j, m, need, done_one] {
-                    j->in_buf[m].reserve(need + need / 8, 0, 2);  // a failure shows when the batch reserves for real
+                warm.run([j, m, need, done_one, &warm_stop, &sh] {
+                    if (!warm_stop && !sh.stop) j->in_buf[m].reserve(need + need / 8, 0, 2);  // a failure shows when the batch reserves for real
                     done_one();
                 });
             }
             for (int d = 0; d < CSQ_N_DEST; d++)
                 for (int m = 0; m < 2; m++) {
                     const size_t need = (size_t)want[d][m];
-                    pool.run([j, d, m, need, done_one] {
-                        j->outbuf[d][m].reserve(need + need / 8, 0, 2);
+                    warm.run([j, d, m, need, done_one, &warm_stop, &sh] {
+                        if (!warm_stop && !sh.stop) j->outbuf[d][m].reserve(need + need / 8, 0, 2);
                         done_one();
                     });
                 }
@@ -1155,6 +1159,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
         w_cv.wait(g, [&] { return sh.stop || (n_batches >= 0 && written >= n_batches); });
     }
     stamp("writer done");
+    warm_stop = true;
     free_q.close();
 
     for (int d = 0; d < CSQ_N_DEST; d++)
@@ -1194,6 +1199,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     }
     stamp("outputs closed");
     // tear down side by side: un-pinning the jobs' host buffers and freeing the plans' device buffers are slow driver calls
+    warm_owner.reset();  // (a run that ended early: the remaining buffers are still pinned and released right away)
     pool_owner.reset();  // joins the pool: no task refers to a job any more
     {
         std::vector<std::thread> unpin;

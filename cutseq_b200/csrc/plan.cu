@@ -252,6 +252,7 @@ int build_mate_program(const csq_op* ops, int n, int mate, MateProgram& mp) {
                 pending.clear();
                 s.ap.first = mp.segs.empty() ? 1 : 0;
                 s.ap.counter_index = CNT_WITH_ADAPTERS + mate * CSQ_MAX_OPS + t;
+                s.ap.adjacent_index = (mp.segs.empty() && !s.ap.trim_front) ? CNT_ADJACENT + mate * 6 : -1;
                 mp.align_slot[t] = mp.n_align++;
                 mp.segs.push_back(s);
                 break;

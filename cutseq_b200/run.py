@@ -117,6 +117,27 @@ def _error_lengths(length: int, rate: float):
     return out
 
 
+def _adjacent_bases(counters, mate):
+    """cutadapt ``EndStatistics.adjacent_bases`` of a 3' end: the read base in front of every match; a match at the
+    read start and a base outside ACGT both count under "" (cutadapt's ``except KeyError: adjacent_bases[""] = 1``
+    resets that entry instead of adding to it - a result that depends on how reads fall into worker chunks; the sum
+    is reported here)."""
+    a = counters.adjacent_bases[mate]
+    return {"A": int(a[0]), "C": int(a[1]), "G": int(a[2]), "T": int(a[3]), "": int(a[4]) + int(a[5])}
+
+
+def _dominant_adjacent_base(adjacent):
+    """cutadapt ``EndStatistics`` report rule: the base (or "none/other") in front of more than 80 % of at least 20
+    matches, else None."""
+    total = sum(adjacent.values())
+    if total < 20:
+        return None
+    for base in ("A", "C", "G", "T", ""):
+        if adjacent[base] / total > 0.8:
+            return base if base else "none/other"
+    return None
+
+
 def _adapter_entries(counters, mate, ops):
     """``adapters_read1`` / ``adapters_read2`` of cutadapt's ``Statistics.as_json()``.  With several AdapterCutters
     per mate only the FIRST one reaches the statistics (the reference swallows the assertion of the second,
@@ -133,7 +154,8 @@ def _adapter_entries(counters, mate, ops):
         end = {
             "type": kind, "sequence": op.adapter, "error_rate": op.max_error_rate, "indels": True,
             "error_lengths": None if anchored else _error_lengths(len(op.adapter), op.max_error_rate),
-            "matches": int(counters.with_adapters[mate][i]), "adjacent_bases": None, "dominant_adjacent_base": None,
+            "matches": int(counters.with_adapters[mate][i]), "adjacent_bases": None if five else _adjacent_bases(counters, mate),
+            "dominant_adjacent_base": None if five else _dominant_adjacent_base(_adjacent_bases(counters, mate)),
             "trimmed_lengths": [],
         }
         return [{"name": str(mate + 1), "total_matches": end["matches"], "on_reverse_complement": None, "linked": False,

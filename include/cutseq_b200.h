@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CSQ_ABI_VERSION 1
+#define CSQ_ABI_VERSION 2
 
 typedef enum csq_status {
     CSQ_OK = 0,
@@ -172,7 +172,7 @@ typedef struct csq_batch_text {
 } csq_batch_text;
 
 /* Batch in, BGZF form: per mate a run of WHOLE BGZF members (bgzip files, this library's own .gz output) as they stand
- * in the file.  The device inflates them (one thread per member) and finds the records itself; the batch's n_reads
+ * in the file.  The device inflates them (one warp per member) and finds the records itself; the batch's n_reads
  * records start behind `skip_lines` line ends of the inflated text, whatever follows them is ignored - so the host
  * cuts batches at member boundaries and only has to know how many line ends every member holds
  * (csq_bgzf_count_lines).  member_off / text_off are prefix sums over the members: compressed sizes (the 'BC' field)
@@ -237,6 +237,10 @@ typedef struct csq_counters {
     uint64_t with_adapters[2][CSQ_MAX_OPS]; /* matches per ALIGN op, indexed by op position */
     uint64_t dp_cells[2][CSQ_MAX_OPS];      /* nominal DP cells m*(max_n-min_n) per ALIGN op
                                                (the GCUPS numerator)         */
+    /* cutadapt's EndStatistics.adjacent_bases of the FIRST ALIGN op of every mate (the one whose statistics the
+     * reference's report keeps, run.py:58-73) when that adapter trims behind the match (3' kinds): the read base in
+     * front of the match - A, C, G, T, none (the match starts the read), any other character */
+    uint64_t adjacent_bases[2][6];
 } csq_counters;
 
 typedef struct csq_plan csq_plan;

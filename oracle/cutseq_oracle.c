@@ -256,6 +256,13 @@ static uint64_t nominal_cells(const csq_op* op, int n) {
     return (uint64_t)m * (uint64_t)(max_n - min_n);
 }
 
+/* EndStatistics.adjacent_bases slot of a 3' match: A, C, G, T, none (rstart == 0), other */
+static int adjacent_slot(const char* seq, int query_start) {
+    if (query_start <= 0) return 4;
+    char c = seq[query_start - 1];
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 5;
+}
+
 /* ---- per-read working record (the SequenceRecord + ModificationInfo of one mate) ---- */
 typedef struct orc_read {
     char* seq;   /* working copies, sliced by moving seq/qual and len */
@@ -502,6 +509,11 @@ static void* chunk_worker(void* arg) {
     const uint32_t n = J->n;
     orc_buf* b = J->b;
     csq_counters* k = J->k;
+    int first_align[2] = {-1, -1}; /* the AdapterCutter whose statistics the reference's report keeps (run.py:58-73) */
+    for (int t = n1 - 1; t >= 0; t--) {
+        if (ops1[t].kind == CSQ_OP_ALIGN) first_align[0] = t;
+        if (paired && ops2[t].kind == CSQ_OP_ALIGN) first_align[1] = t;
+    }
     for (uint32_t i = J->lo; i < J->hi; i++) {
         orc_read r[2];
         load_read(&r[0], &in->mate[0], i);
@@ -528,10 +540,13 @@ static void* chunk_worker(void* arg) {
             orc_match mt;
             memset(&mt, 0, sizeof(mt));
             if (ops1[t].kind == CSQ_OP_ALIGN) k->dp_cells[0][t] += nominal_cells(&ops1[t], r[0].len);
+            /* adjacent base of a 3' match of the mate's first ALIGN op (BackAdapterStatistics.add_match): looked up before the cut */
+            const char* seq_before[2] = {r[0].seq, r[1].seq};
             if (paired && ops2[t].kind == CSQ_OP_ALIGN) k->dp_cells[1][t] += nominal_cells(&ops2[t], r[1].len);
             apply_single(&ops1[t], &r[0], &mt, &k->quality_trimmed_bp[0]);
             if (ops1[t].kind == CSQ_OP_ALIGN) {
                 if (mt.found) k->with_adapters[0][t]++;
+                if (mt.found && t == first_align[0] && !kind_is_front(ops1[t].adapter_kind)) k->adjacent_bases[0][adjacent_slot(seq_before[0], mt.query_start)]++;
                 if (J->matches1) store_match(&J->matches1[(size_t)t * n + i], &mt);
             }
             if (paired) {
@@ -539,6 +554,7 @@ static void* chunk_worker(void* arg) {
                 apply_single(&ops2[t], &r[1], &mt, &k->quality_trimmed_bp[1]);
                 if (ops2[t].kind == CSQ_OP_ALIGN) {
                     if (mt.found) k->with_adapters[1][t]++;
+                    if (mt.found && t == first_align[1] && !kind_is_front(ops2[t].adapter_kind)) k->adjacent_bases[1][adjacent_slot(seq_before[1], mt.query_start)]++;
                     if (J->matches2) store_match(&J->matches2[(size_t)t * n + i], &mt);
                 }
             }

@@ -56,6 +56,8 @@ def test_parse_basic_and_edge_cases():
     (b"@r1\nACGT\n+\nIII\n", A.ERR_FORMAT),
     (b"@r1\nACGT\n+\n", A.ERR_FORMAT),
     (b"@r1\n" + b"A" * 900 + b"\n+\n" + b"I" * 900 + b"\n", A.ERR_LIMIT),
+    (b"@r1 c\nACGT\n+r1\nIIII\n", A.ERR_FORMAT),   # dnaio: the second description must be empty or equal to the first
+    (b"@" + b"h" * 70000 + b"\nACGT\n+\nIIII\n", A.ERR_LIMIT),
 ])
 def test_parse_errors(text, code):
     with pytest.raises(native.NativeError) as e:

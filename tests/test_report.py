@@ -64,6 +64,25 @@ def test_json_report_single_end(tmp_path):
     assert d["basepair_counts"]["quality_trimmed_read2"] is None
 
 
+def test_json_report_three_prime_end_has_adjacent_bases(tmp_path):
+    """A first cutter that is a 3' adapter (every scheme of run.py starts with the 5' p5 adapter, so only programs built
+    through the C ABI get here): cutadapt keeps the base in front of every match (EndStatistics.adjacent_bases) and
+    names a dominant one (> 80 % of >= 20 matches)."""
+    bc, prog, c = _setup(["-A", "SMALLRNA"], paired=False)
+    first = next(op for op in prog.ops_r1 if op.kind == A.OP_ALIGN)
+    first.adapter_kind = A.AD_BACK
+    for slot, v in enumerate((90, 3, 2, 1, 2, 1)):  # A, C, G, T, none, other
+        c.adjacent_bases[0][slot] = v
+    f = str(tmp_path / "r.json")
+    run.json_report(f, c, prog, bc, "a.fq", None, "o1", None, "s1", None, None, None)
+    end = json.load(open(f))["adapters_read1"][0]["three_prime_end"]
+    assert end["adjacent_bases"] == {"A": 90, "C": 3, "G": 2, "T": 1, "": 3} and end["dominant_adjacent_base"] == "A"
+    c.adjacent_bases[0][0] = 5
+    run.json_report(f, c, prog, bc, "a.fq", None, "o1", None, "s1", None, None, None)
+    end = json.load(open(f))["adapters_read1"][0]["three_prime_end"]
+    assert end["dominant_adjacent_base"] is None  # 14 matches: too few to call
+
+
 def test_minimal_report_uses_the_first_cutter_only():
     bc, prog, c = _setup(["-A", "TAKARAV3"])
     header, values = run.minimal_report_text(c, prog).split("\n")
