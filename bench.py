@@ -535,8 +535,10 @@ def main():
     native.unbind_host()  # the host legs below (files, CPU baseline) use every core of the box
     if rank != 0:
         plan.close()
-        # rank 0 drives every GPU of the job in the files leg: wait here so that the job ends together
-        group.barrier()
+        torch.cuda.synchronize()
+        # rank 0 drives every GPU of the job in the files leg: wait here so that the job ends together - on the host
+        # (a GPU barrier would spin on this rank's GPU while rank 0's file run needs it)
+        group.host_wait("csq_files_leg_done")
         group.close()
         return 0
 
@@ -612,7 +614,7 @@ def main():
             files = files_leg(prog, args.file_pairs, args.file_pairs_gz, world, os.cpu_count() or 4)
         except Exception as exc:  # the headline numbers must not die with a full /tmp
             files = {"error": repr(exc)}
-    group.barrier()
+    group.host_signal("csq_files_leg_done")
 
     cpu = None
     if not args.no_cpu and world == 1:

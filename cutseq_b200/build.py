@@ -27,20 +27,56 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+STAMP = os.path.join(HERE, "build", "sources.sha256")
+
+
+def _deps():
+    deps = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(HERE, "..", "include", "cutseq_b200.h"))
+    return deps
+
+
+def sources_hash() -> str:
+    """sha256 over everything the library is built from (contents, not time stamps: a checkout, a stash or the copy
+    to a GPU box changes mtimes without changing a byte)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in _deps():
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    deps.append(os.path.join(HERE, "..", "include", "cutseq_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() != sources_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    import fcntl
+
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    # one builder at a time (torchrun ranks, pytest workers): the others wait and find the work done
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        return _build_locked(objdir, verbose)
+
+
+def _build_locked(objdir: str, verbose: bool) -> str:
+    want = sources_hash()
     objs = []
     procs = []
     for src in sources():
@@ -55,8 +91,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
         if verbose or "warning" in out:
             sys.stderr.write(out)
-    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static", "-lz", "-lpthread"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + ["-cudart", "static", "-lz", "-lpthread"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)  # a process that maps the old file keeps it
+    with open(STAMP + ".tmp", "w") as f:
+        f.write(want + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

@@ -1201,11 +1201,13 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     // tear down side by side: un-pinning the jobs' host buffers and freeing the plans' device buffers are slow driver calls
     warm_owner.reset();  // (a run that ended early: the remaining buffers are still pinned and released right away)
     pool_owner.reset();  // joins the pool: no task refers to a job any more
+    stamp("pools joined");
     {
         std::vector<std::thread> unpin;
         for (auto& j : jobs) unpin.emplace_back([&j] { j.reset(); });
         if (reader) csq_text_reader_close(reader);
         destroy_plans();
+        stamp("plans destroyed");
         for (auto& t : unpin) t.join();
     }
     stamp("teardown done");

@@ -55,6 +55,19 @@ class Group:
         if self.dist is not None:
             self.dist.barrier()
 
+    # A barrier on the GPUs is a kernel that spins until the last rank arrives: ranks that only wait for rank 0's host-side
+    # work (the whole-file leg drives every GPU of the job from rank 0) must not do that - their spinning kernel would
+    # time-slice with the file run on their GPU.  These two go through the rendezvous store (a socket) instead.
+    def host_signal(self, key: str):
+        if self.dist is not None:
+            self.dist.distributed_c10d._get_default_store().set(key, "1")
+
+    def host_wait(self, key: str, timeout_s: float = 3600.0):
+        if self.dist is not None:
+            import datetime
+
+            self.dist.distributed_c10d._get_default_store().wait([key], datetime.timedelta(seconds=timeout_s))
+
     def max(self, x: float) -> float:
         if self.dist is None:
             return float(x)

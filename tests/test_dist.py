@@ -43,6 +43,14 @@ def _worker(rank, world, port, q):
     summed = g.sum_counters(out["counters"])
     slowest = g.max(float(rank + 1))
     g.barrier()
+    # host-side wait (no collective): rank 1 waits until rank 0 has "finished its host work"
+    if rank == 0:
+        import time
+
+        time.sleep(0.3)
+        g.host_signal("rank0_done")
+    else:
+        g.host_wait("rank0_done", timeout_s=60)
     q.put((rank, lo, hi, summed.n, summed.written, summed.too_short, list(summed.quality_trimmed_bp), slowest,
            out["text"][0][0][:64]))
     g.close()
