@@ -508,9 +508,16 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             for (int d = 0; d < CSQ_N_DEST; d++) want[d][m] = m >= n_mates ? 64 : d == CSQ_DEST_TRIMMED ? full : full / 8 + 4096;
         }
     };
+    int jobs_in_use = n_jobs;
+    // With several GPUs the jobs are released together, when the last one is pinned: a registration holds the driver's
+    // lock across every context of the process, and the first submits of N GPUs (device allocations, module loads) would
+    // queue behind each of them (measured at N = 4: first batch out after 0.97 s instead of 0.3 s).
+    std::atomic<int> warm_left{0};
+    std::vector<Job*> warm_held;
+    std::mutex warm_m;
     {
         uint64_t est_text[2] = {0, 0}, est_load[2] = {0, 0};
-        double n_batches_est = 0;
+        double n_batches_est = 0, all_text = 0;
         bool have_est = mode != 2;
         for (int m = 0; m < n_mates && have_est; m++) {
             double bpr = 0, ratio = 1.0;  // text bytes per record, compressed / text bytes
@@ -543,19 +550,50 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             est_load[m] = (uint64_t)(batch_text * ratio * (mode == 1 ? 1.06 : 1.0)) + 65536;
             if (mode == 1) est_load[m] = std::max<uint64_t>(est_load[m], std::min<uint64_t>(inf[m].size, (48ull << 20) + 65536));
             n_batches_est = std::max(n_batches_est, (double)total_text / std::max(1.0, (double)batch_reads * bpr));
+            all_text += (double)total_text;
         }
-        const int n_warm = have_est ? (int)std::min<double>((double)n_jobs, n_batches_est + 1.0 + (mode == 1 ? 2.0 : 0.0)) : 0;
-        for (int i = 0; i < n_jobs; i++) {
+        uint64_t want[CSQ_N_DEST][2];
+        output_sizes(est_text, batch_reads, want);
+        // How many jobs does this input deserve?  Pinning runs at a few GB/s and holds the driver's lock (a submit that
+        // meets it waits: measured, 15 jobs warming beside the first batches of a 4-GPU run delayed them by 2.4 s), so
+        // the jobs in circulation are bounded by ~15 % of the input's text: a 20 M-pair file gets 5 jobs on any number
+        // of GPUs (it cannot keep more than two or three busy), a 200 M-pair file all 3 N + 3.
+        int n_use = n_jobs;
+        if (have_est) {
+            double job_bytes = 0;
+            for (int m = 0; m < n_mates; m++) job_bytes += 1.125 * (double)est_load[m];
+            for (int d = 0; d < CSQ_N_DEST; d++)
+                for (int m = 0; m < n_mates; m++) job_bytes += 1.125 * (double)want[d][m];
+            const int by_size = (int)(0.15 * all_text / std::max(1.0, job_bytes));
+            const int by_batches = (int)(n_batches_est + 1.0 + (mode == 1 ? 2.0 : 0.0));
+            n_use = std::max(std::min(n_jobs, 4), std::min(n_jobs, std::min(by_size, by_batches)));
+            if (by_batches < n_use) n_use = std::max(1, by_batches);
+        }
+        if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  %d of %d jobs in circulation\n", seconds_since(t_start), n_use, n_jobs);
+        jobs_in_use = n_use;
+        const int n_warm = have_est ? n_use : 0;
+        warm_left = n_warm;
+        for (int i = 0; i < n_use; i++) {
             Job* j = jobs[(size_t)i].get();
             if (i >= n_warm) {
                 free_q.push(j);
                 continue;
             }
-            uint64_t want[CSQ_N_DEST][2];
-            output_sizes(est_text, batch_reads, want);
             j->parts = n_mates + CSQ_N_DEST * 2;
-            auto done_one = [&free_q, j] {
-                if (--j->parts == 0) free_q.push(j);
+            auto done_one = [&free_q, &warm_left, &warm_held, &warm_m, n_dev, j, i, trace, t_start] {
+                if (--j->parts == 0) {
+                    if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  job %d warmed\n", seconds_since(t_start), i);
+                    if (n_dev == 1) {
+                        free_q.push(j);
+                        return;
+                    }
+                    std::lock_guard<std::mutex> g(warm_m);
+                    warm_held.push_back(j);
+                    if (--warm_left == 0) {
+                        for (Job* h : warm_held) free_q.push(h);
+                        warm_held.clear();
+                    }
+                }
             };
             for (int m = 0; m < n_mates; m++) {
                 const size_t need = (size_t)est_load[m] + 64;
@@ -737,6 +775,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                         if (j->kind == J_TEXT)
                             for (int mm = 0; mm < n_mates; mm++)
                                 if (j->append_nl[mm]) j->in_buf[mm].p[j->load_len[mm]] = '\n';
+                        if (trace && j->index >= 0) fprintf(stderr, "[csq_run_files] %8.3f s  batch %ld loaded\n", seconds_since(t_start), j->index);
                         ready_q.push(j);
                         {
                             std::lock_guard<std::mutex> g(ld_m);
@@ -851,6 +890,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                 }
                 first_record += n[0];
                 j->index = index++;
+                if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  batch %ld cut\n", seconds_since(t_start), j->index);
                 load_and_ready(j);
             }
             finish();
@@ -992,7 +1032,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                         m_next = m;
                     }
                 }
-            if (m_next >= 0 && jobs_out < 2 * n_dev + 1) {
+            if (m_next >= 0 && jobs_out < std::max(1, std::min(2 * n_dev + 1, jobs_in_use / 2))) {
                 if (!free_q.pop(j)) break;
                 const int m = m_next;
                 size_t f = next_index_member[m], l = f;
@@ -1083,6 +1123,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
                     return false;
                 }
                 csq_slot_times(plan, j->slot, &j->total_ms, &j->kernel_ms);
+                if (trace) fprintf(stderr, "[csq_run_files] %8.3f s  batch %ld back from GPU %d (%.1f ms)\n", seconds_since(t_start), j->index, d, j->total_ms);
                 gpu_total[(size_t)d] += j->total_ms * 1e-3;
                 gpu_kernel[(size_t)d] += j->kernel_ms * 1e-3;
                 batch_done(j);
