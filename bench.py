@@ -173,7 +173,7 @@ def cpu_leg(prog, steps, warmup, sample_pairs, first_index=0):
     return steps * sample_pairs / dt, threads, dt / steps
 
 
-def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
+def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads, pairs_gzip=0):
     """FASTQ files on disk -> csq_run_files -> trimmed FASTQ files, plain and .gz (BGZF members in, gzip members out);
     host stages reported separately; with n_devices > 1 the same files also go through ONE GPU and the outputs must
     have the same sha256 (order-preserving reassembly, reference run.py:751-758 / 793-794 `-t N` runner)."""
@@ -186,13 +186,13 @@ def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
     tmp = tempfile.mkdtemp(dir=os.environ.get("CSQ_BENCH_TMP"))
     out = {"host_threads": threads, "n_devices": n_devices}
     try:
-        for variant, pairs in (("plain", pairs_plain), ("gz", pairs_gz)):
+        for variant, pairs in (("plain", pairs_plain), ("gz", pairs_gz), ("gzip", pairs_gzip)):
             if pairs <= 0:
                 continue
-            ext = ".fq.gz" if variant == "gz" else ".fq"
+            ext = ".fq" if variant == "plain" else ".fq.gz"
             ins = [os.path.join(tmp, f"in_R{m}{ext}") for m in (1, 2)]
             t0 = time.time()
-            bench_files.write_fixture(ins, pairs, variant == "gz", threads)
+            bench_files.write_fixture(ins, pairs, {"plain": False, "gz": "bgzf", "gzip": "gzip"}[variant], threads)
             gen_s = time.time() - t0
             res = {"pairs": pairs, "input_bytes": sum(os.path.getsize(p) for p in ins), "fixture_s": gen_s}
             hashes = {}
@@ -210,7 +210,7 @@ def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
                     if best is None or wall < best[0]:
                         best = (wall, timing, counters)
                 wall, timing, counters = best
-                hashes[nd] = bench_files.hash_outputs(outs["trimmed"] + outs["short"], variant == "gz")
+                hashes[nd] = bench_files.hash_outputs(outs["trimmed"] + outs["short"], variant != "plain")
                 res[f"n{nd}"] = {"pairs_per_s": pairs / wall, "wall_s": wall, "read_inflate_s": timing.read_inflate,
                                  "gpu_h2d_kernels_d2h_s": timing.h2d_kernels_d2h, "gpu_kernels_s": timing.kernels,
                                  "deflate_write_s": timing.write_deflate, "written_pairs": int(counters.written),
@@ -227,7 +227,9 @@ def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads):
                     os.remove(p)
         out["note"] = ("whole runs incl. plan set-up and pinned allocations; stage seconds are busy times of overlapping stages; "
                        "sha256 over the (decompressed) bytes of trimmed_R1, trimmed_R2, short_R1, short_R2; "
-                       ".gz input = BGZF members (64 KiB blocks, level 1), .gz output = concatenated gzip members")
+                       "gz: input = BGZF members (64 KiB blocks, level 1, inflated on the device); gzip: input = ordinary gzip, one member "
+                       "per 4 M pairs at level 6 (one DEFLATE stream, decoded by the host threads in parallel: csrc/pinflate.cpp); "
+                       ".gz output = concatenated gzip members made on the device")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return out
@@ -354,6 +356,7 @@ def main():
     ap.add_argument("--no-files", action="store_true", help="skip the whole-file leg (FASTQ files on disk -> csq_run_files -> files)")
     ap.add_argument("--file-pairs", type=int, default=20_000_000, help="pairs in the plain whole-file leg (config 5: streamed, <= 20M-pair on-disk file)")
     ap.add_argument("--file-pairs-gz", type=int, default=20_000_000, help="pairs in the .gz whole-file leg")
+    ap.add_argument("--file-pairs-gzip", type=int, default=4_000_000, help="pairs in the ordinary-gzip whole-file leg (single-member input)")
     ap.add_argument("--no-prefilter", action="store_true", help="exact DP on every read (CSQ_PLAN_NO_PREFILTER)")
     ap.add_argument("--emit", default="stage", choices=["stage", "g16"], help="emit kernel (A/B runs); stage (k_emit_stage, through shared memory) is the product default")
     ap.add_argument("--no-exact-stop", action="store_true", help="exact DP walks on after an error-free full match (CSQ_PLAN_NO_EXACT_STOP, A/B runs)")
@@ -611,7 +614,7 @@ def main():
     files = None
     if not args.no_files:
         try:
-            files = files_leg(prog, args.file_pairs, args.file_pairs_gz, world, os.cpu_count() or 4)
+            files = files_leg(prog, args.file_pairs, args.file_pairs_gz, world, os.cpu_count() or 4, pairs_gzip=args.file_pairs_gzip)
         except Exception as exc:  # the headline numbers must not die with a full /tmp
             files = {"error": repr(exc)}
     group.host_signal("csq_files_leg_done")

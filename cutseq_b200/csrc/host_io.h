@@ -98,11 +98,29 @@ class Inflater {
     const char* err_ = nullptr;
 };
 
+uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n);  // zlib's crc32() semantics, PCLMULQDQ folding where there is one
+
+// Ordinary (single-stream) gzip files decoded by several threads at once (pinflate.cpp): same interface as Inflater.
+class ParallelInflater {
+   public:
+    ParallelInflater(const uint8_t* data, size_t n, int threads);
+    ~ParallelInflater();
+    ParallelInflater(const ParallelInflater&) = delete;
+    ParallelInflater& operator=(const ParallelInflater&) = delete;
+    long read(uint8_t* dst, size_t n);  // bytes produced (< n only at the end of the input), -1 on error
+    const char* error() const;
+    struct Impl;
+
+   private:
+    Impl* p_;
+};
+
 struct RawSource {  // decompressed byte stream of a plain or gzip (multi-member) file, read into caller memory
     int fd = -1;
     bool gz = false, file_eof = false, stream_end = false;
     void* zs = nullptr;            // zlib stream (CSQ_ZLIB_INFLATE=1: A/B runs against the built-in decoder)
     Inflater* fast = nullptr;      // built-in decoder over the mmap-ed file
+    ParallelInflater* par = nullptr;  // ... by several threads (files of 16 MB and more)
     const uint8_t* map = nullptr;
     size_t map_len = 0;
     std::vector<uint8_t> inbuf;

@@ -137,6 +137,8 @@ inline uint32_t bit_reverse(uint32_t code, int len) {
 
 }  // namespace
 
+uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t n) { return crc32_update(crc, p, n); }
+
 struct Inflater::Tables {
     uint32_t ll[(1 << LL_BITS) + 2048];  // second-level tables behind the first 2^LL_BITS entries
     uint32_t dd[(1 << D_BITS) + 1024];

@@ -71,6 +71,8 @@ RawSource::~RawSource() { close(); }
 void RawSource::close() {
     delete fast;
     fast = nullptr;
+    delete par;
+    par = nullptr;
     if (map) munmap((void*)map, map_len);
     map = nullptr;
     map_len = 0;
@@ -121,6 +123,16 @@ int RawSource::open(const char* path) {
         madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
         map = (const uint8_t*)m;
         map_len = (size_t)sb.st_size;
+        // large files: several threads decode the one stream (pinflate.cpp); CSQ_INFLATE_THREADS=1 keeps the serial decoder
+        const char* pt = getenv("CSQ_INFLATE_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        int threads = pt ? atoi(pt) : (int)std::min(16u, std::max(2u, hw / 2));
+        const char* pm = getenv("CSQ_PINFLATE_MIN");  // smallest file that is worth the threads (tests lower it)
+        const size_t min_len = pm ? (size_t)atol(pm) : (size_t)(16u << 20);
+        if (map_len >= min_len && threads > 1) {
+            par = new ParallelInflater(map, map_len, threads);
+            return 0;
+        }
         fast = new Inflater();
         fast->reset(map, map_len);
         return 0;
@@ -158,6 +170,14 @@ long RawSource::read(uint8_t* dst, size_t n) {
             done += (size_t)got;
         }
         return (long)done;
+    }
+    if (par) {
+        const long got = par->read(dst, n);
+        if (got < 0) {
+            io_fail(CSQ_ERR_IO, "%s: %s", name.c_str(), par->error());
+            return -1;
+        }
+        return got;
     }
     if (fast) {
         const long got = fast->read(dst, n);

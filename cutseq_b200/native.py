@@ -81,6 +81,7 @@ def lib():
         L.csq_format_fastq.argtypes = [C.POINTER(A.csq_mate_in), u32, vp, C.c_uint64, u64p]
         L.csq_gz_deflate_host.argtypes = [vp, C.c_uint64, vp, C.c_uint64, u64p]
         L.csq_gz_inflate_host.argtypes = [vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]
+        L.csq_pinflate_mem.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_int, C.c_uint64, u64p]
     if hasattr(L, "csq_synth_batch"):
         L.csq_synth_batch.argtypes = [C.POINTER(A.csq_synth), C.c_uint64, u32, i32, C.POINTER(A.csq_batch_in)]
         L.csq_synth_free.restype = None
@@ -403,6 +404,15 @@ def gz_deflate_host(text: bytes) -> bytes:
     out = np.empty(len(text) + (len(text) // 32000 + 2) * 64 + 64, dtype=np.uint8)
     n = C.c_uint64()
     check(lib().csq_gz_deflate_host(src.ctypes.data, len(text), out.ctypes.data, out.size, C.byref(n)))
+    return out[: n.value].tobytes()
+
+
+def pinflate(data: bytes, capacity: int, threads: int = 4, span_bytes: int = 0) -> bytes:
+    """An ordinary gzip file in memory through the parallel decoder (``csq_pinflate_mem``)."""
+    src = np.frombuffer(bytes(data) + b"\0" * 16, dtype=np.uint8)
+    out = np.empty(max(capacity, 1), dtype=np.uint8)
+    n = C.c_uint64(0)
+    check(lib().csq_pinflate_mem(src.ctypes.data, len(data), out.ctypes.data, capacity, threads, span_bytes, C.byref(n)))
     return out[: n.value].tobytes()
 
 

@@ -363,6 +363,10 @@ int csq_gunzip_mem(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, u
 int csq_gz_deflate_host(const uint8_t* text, uint64_t n, uint8_t* out, uint64_t cap, uint64_t* out_n);
 /* The device gzip reader's decoder run on the host, member by member (CPU tests): BGZF members -> text; *lines = '\n' found. */
 int csq_gz_inflate_host(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, uint64_t* out_n, uint64_t* lines);
+/* The parallel decoder of ordinary (single-stream) gzip files (csrc/pinflate.cpp; the file driver uses it for .gz inputs
+ * without BGZF framing): a whole gzip file in memory -> text.  span_bytes: compressed bytes per thread and round
+ * (0: default); tests use small values. */
+int csq_pinflate_mem(const uint8_t* src, uint64_t n, uint8_t* dst, uint64_t cap, int threads, uint64_t span_bytes, uint64_t* out_n);
 /* SoA batch -> FASTQ text of one mate ("@name\nseq\n+\nqual\n"), for tests and benchmarks. */
 int csq_format_fastq(const csq_mate_in* mate, uint32_t n_reads, uint8_t* out, uint64_t capacity,
                      uint64_t* bytes);

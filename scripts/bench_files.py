@@ -47,6 +47,27 @@ def bgzf_compress(text, threads: int) -> bytes:
     return b"".join(members)
 
 
+def gzip_single_member(text, threads: int, level: int = 6, piece: int = 4 << 20) -> bytes:
+    """ONE gzip member holding `text` - what `gzip` / `pigz` and the sequencers' software write - compressed by several
+    threads the way pigz does it: every piece is deflated on its own and ends in a sync flush (an empty stored block,
+    byte aligned, not final), only the last piece carries the final block; CRC-32 over the whole text."""
+    view = memoryview(text)
+    pieces = [view[o:o + piece] for o in range(0, len(view), piece)] or [view]
+
+    def one(arg):
+        i, p = arg
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return c.compress(bytes(p)) + c.flush(zlib.Z_FINISH if i == len(pieces) - 1 else zlib.Z_SYNC_FLUSH)
+
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        bodies = list(ex.map(one, enumerate(pieces)))
+    crc = 0
+    for p in pieces:
+        crc = zlib.crc32(p, crc)
+    head = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\xff"
+    return head + b"".join(bodies) + struct.pack("<II", crc & 0xFFFFFFFF, len(view) & 0xFFFFFFFF)
+
+
 def write_fastq_from_soa(batch, paths):
     """Serialise a synthetic SoA batch to plain FASTQ files (csq_format_fastq of the product library is NOT used here:
     this also serves the CPU arm)."""
@@ -68,9 +89,11 @@ def write_fastq_from_soa(batch, paths):
                 f.write(b"@" + name[noff[i]:noff[i + 1]] + b"\n" + seq[soff[i]:soff[i] + slen[i]] + b"\n+\n" + qual[soff[i]:soff[i] + slen[i]] + b"\n")
 
 
-def write_fixture(paths, pairs: int, compress: bool, threads: int):
+def write_fixture(paths, pairs: int, compress, threads: int):
     """Config-2 FASTQ files of `pairs` pairs: blocks of up to 4 M generated pairs, the first block repeated (names
-    repeat too; both mates stay in step).  .gz = BGZF members of 0xFF00 bytes at level 1, then the BGZF EOF marker."""
+    repeat too; both mates stay in step).  compress = True / "bgzf": BGZF members of 0xFF00 bytes at level 1, then the
+    BGZF EOF marker; "gzip": ordinary gzip members (level 6, one per generated block - a file of up to 4 M pairs is a
+    single member, like the output of `gzip`)."""
     from cutseq_b200 import native
 
     block = min(pairs, BLOCK_PAIRS)
@@ -83,10 +106,10 @@ def write_fixture(paths, pairs: int, compress: bool, threads: int):
             batch = native.synth_batch(2, n, first_index=0, buffer=14)
             for m, f in enumerate(handles):
                 text = native.format_fastq(batch, m)
-                data = bgzf_compress(text, threads) if compress else memoryview(text)
+                data = gzip_single_member(text, threads) if compress == "gzip" else bgzf_compress(text, threads) if compress else memoryview(text)
                 for _ in range(times):
                     f.write(data)
-        if compress:
+        if compress and compress != "gzip":
             for f in handles:
                 f.write(BGZF_EOF)
     finally:
@@ -132,6 +155,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=8_000_000)
     ap.add_argument("--pairs-gz", type=int, default=None)
+    ap.add_argument("--pairs-gzip", type=int, default=4_000_000, help="pairs of the ordinary-gzip variant (single member in, .gz out)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--out", default=None)
@@ -141,7 +165,8 @@ def main():
 
     prog = bench.takara_program()
     v = args.variants.split(",")
-    res = bench.files_leg(prog, args.pairs if "plain" in v else 0, (args.pairs_gz or args.pairs) if "gz" in v else 0, args.gpus, args.threads)
+    res = bench.files_leg(prog, args.pairs if "plain" in v else 0, (args.pairs_gz or args.pairs) if "gz" in v else 0, args.gpus, args.threads,
+                          pairs_gzip=args.pairs_gzip if "gzip" in v else 0)
     print(json.dumps(res, indent=1))
     if args.out:
         with open(args.out, "w") as f:

@@ -112,3 +112,68 @@ def test_text_reader_built_in_and_zlib_agree(tmp_path, monkeypatch):
                 got += texts[0]
         outs.append(got)
     assert outs[0] == outs[1] == data
+
+
+# ---- the parallel decoder of ordinary gzip files (csrc/pinflate.cpp) ----
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_parallel_inflate_matches_zlib(level):
+    """One DEFLATE stream decoded by several threads: block starts searched behind every cut, spans decoded with
+    markers for the unknown window, resolved in order.  Small spans make many spans and rounds out of a small file."""
+    text = fastq(30000, seed=11)
+    comp = gz(text, level)
+    for span in (20_000, 150_000, 0):
+        for threads in (2, 3, 8):
+            assert native.pinflate(comp, len(text), threads, span) == text, (level, span, threads)
+
+
+def test_parallel_inflate_members_stored_fixed_and_binary():
+    text = fastq(8000, seed=12)
+    # members that end in the middle of spans, empty and one-byte members, zero padding behind the last one
+    parts = [text[:100], b"", text[100:300_000], text[300_000:300_001], text[300_001:]]
+    comp = b"".join(gz(p) for p in parts) + bytes(64)
+    for span in (5_000, 50_000, 1 << 20):
+        assert native.pinflate(comp, len(text), 4, span) == text
+    # stored and fixed blocks, tiny inputs
+    for data in (text[:200_000], b"", b"A", b"ACGT\n" * 3):
+        for level, strategy in ((0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_HUFFMAN_ONLY)):
+            assert native.pinflate(gz(data, level, strategy), len(data), 3, 10_000) == data
+    # content that is not text: no block start passes the search, the first span's decoder walks the whole stream
+    rng = random.Random(5)
+    blob = os.urandom(100_000) + bytes(rng.choice(b"\x00\x01\xfe\xffAB") for _ in range(1_000_000))
+    assert native.pinflate(gz(blob), len(blob), 4, 30_000) == blob
+
+
+def test_parallel_inflate_reports_damage():
+    text = fastq(20000, seed=13)
+    comp = bytearray(gz(text))
+    for pos in (30, len(comp) // 2, len(comp) - 6):
+        bad = bytearray(comp)
+        bad[pos] ^= 0x55
+        with pytest.raises(native.NativeError):
+            native.pinflate(bytes(bad), len(text) + 100_000, 4, 40_000)
+    with pytest.raises(native.NativeError):
+        native.pinflate(bytes(comp[: len(comp) // 2]), len(text), 4, 40_000)
+    with pytest.raises(native.NativeError) as e:
+        native.pinflate(bytes(comp), len(text) - 1, 4, 40_000)
+    assert e.value.code == -5  # CSQ_ERR_CAPACITY
+
+
+def test_text_reader_uses_the_parallel_decoder(tmp_path, monkeypatch):
+    """The file driver's text reader hands large ordinary .gz inputs to the parallel decoder (threshold lowered here)."""
+    recs = [fastq(3000, seed=21), fastq(3000, seed=22)]
+    paths = [tmp_path / "a.fq.gz", tmp_path / "b.fq.gz"]
+    for p, t in zip(paths, recs):
+        p.write_bytes(gz(t[: len(t) // 2]) + gz(t[len(t) // 2:]))  # two members
+    monkeypatch.setenv("CSQ_PINFLATE_MIN", "1000")
+    monkeypatch.setenv("CSQ_PINFLATE_SPAN", "30000")
+    monkeypatch.setenv("CSQ_INFLATE_THREADS", "4")
+    got, total = [b"", b""], 0
+    with native.TextReader(str(paths[0]), str(paths[1])) as r:
+        while True:
+            n, texts, _ = r.next(700)
+            if n == 0:
+                break
+            got[0] += texts[0]
+            got[1] += texts[1]
+            total += n
+    assert total == 3000 and got[0] == recs[0] and got[1] == recs[1]
