@@ -100,6 +100,8 @@ long RawSource::fill() {
     }
 }
 
+static std::atomic<int> g_streams_side_by_side(2);
+
 int RawSource::open(const char* path) {
     close();
     name = path;
@@ -126,7 +128,9 @@ int RawSource::open(const char* path) {
         // large files: several threads decode the one stream (pinflate.cpp); CSQ_INFLATE_THREADS=1 keeps the serial decoder
         const char* pt = getenv("CSQ_INFLATE_THREADS");
         const unsigned hw = std::thread::hardware_concurrency();
-        int threads = pt ? atoi(pt) : (int)std::min(16u, std::max(2u, hw / 2));
+        // the host's cores are shared by the mates that are read side by side (csq_text_reader_open says how many)
+        const unsigned share = (unsigned)std::max(1, g_streams_side_by_side.load());
+        int threads = pt ? atoi(pt) : (int)std::min(16u, std::max(2u, hw / share));
         const char* pm = getenv("CSQ_PINFLATE_MIN");  // smallest file that is worth the threads (tests lower it)
         const size_t min_len = pm ? (size_t)atol(pm) : (size_t)(16u << 20);
         if (map_len >= min_len && threads > 1) {
@@ -628,6 +632,7 @@ int csq_text_reader_open(const char* path1, const char* path2, csq_text_reader**
     }
     csq_text_reader* r = new csq_text_reader();
     r->n_mates = path2 ? 2 : 1;
+    g_streams_side_by_side = r->n_mates;
     int rc = r->mate[0].open(path1);
     if (!rc && path2) rc = r->mate[1].open(path2);
     if (rc) {
