@@ -450,6 +450,8 @@ void decode_span(const uint8_t* data, size_t n, Span& sp, size_t stop_bit) {
                 sp.error = "invalid dynamic block header";
                 return;
             }
+            const uint32_t* const llut = lit.lut.data();
+            const uint32_t* const dlut = dist.lut.data();
             for (;;) {
                 if (o + 640 > cap) {
                     grow(258);
@@ -463,7 +465,13 @@ void decode_span(const uint8_t* data, size_t n, Span& sp, size_t stop_bit) {
                     sp.error = "the DEFLATE stream ends in the middle of a block";
                     return;
                 }
-                uint32_t e = decode_entry(b, lit, 1);
+                uint32_t e = llut[(uint32_t)b.buf & ((1u << LBITS) - 1u)];
+                if (e) {
+                    b.drop((int)(e & 15u));
+                    e &= ~15u;
+                } else {
+                    e = decode_entry(b, lit, 1);
+                }
                 if (e >= 0x01000000u) {
                     if (e == E_BAD) {
                         sp.error = "invalid literal/length code";
@@ -471,23 +479,29 @@ void decode_span(const uint8_t* data, size_t n, Span& sp, size_t stop_bit) {
                     }
                     if (e & E_EOB) break;
                     out[o++] = (uint16_t)((e >> 8) & 0xFFu);
-                    // literal runs: up to three more without a refill (<= 15 bits each, 56 on hand)
-                    e = lit.lut[b.peek(LBITS)];
-                    if (e >= 0x80000000u && e != E_BAD) {
+                    // literal runs: up to two more without a refill (15 + 11 + 11 bits of the 56 on hand)
+                    e = llut[(uint32_t)b.buf & ((1u << LBITS) - 1u)];
+                    if (e >= 0x80000000u) {
                         b.drop((int)(e & 15u));
                         out[o++] = (uint16_t)((e >> 8) & 0xFFu);
-                        e = lit.lut[b.peek(LBITS)];
-                        if (e >= 0x80000000u && e != E_BAD) {
+                        e = llut[(uint32_t)b.buf & ((1u << LBITS) - 1u)];
+                        if (e >= 0x80000000u) {
                             b.drop((int)(e & 15u));
                             out[o++] = (uint16_t)((e >> 8) & 0xFFu);
                         }
                     }
                     continue;
                 }
+                // a match: length (<= 15 + 5 bits) and distance (<= 15 + 13) come out of the 56 bits on hand
                 const int x = (int)(e >> 4 & 15u);
                 const uint32_t len = (e >> 8) + b.take(x);
-                b.refill();
-                e = decode_entry(b, dist, 2);
+                e = dlut[(uint32_t)b.buf & ((1u << DBITS) - 1u)];
+                if (e) {
+                    b.drop((int)(e & 15u));
+                    e &= ~15u;
+                } else {
+                    e = decode_entry(b, dist, 2);
+                }
                 if (e == E_BAD) {
                     sp.error = "invalid distance code";
                     return;
@@ -512,10 +526,6 @@ void decode_span(const uint8_t* data, size_t n, Span& sp, size_t stop_bit) {
                     for (uint32_t i = 0; i < len; i++) t[i] = s[i];
                 }
                 o += len;
-                if (b.pos() > total_bits) {
-                    sp.error = "the DEFLATE stream ends in the middle of a block";
-                    return;
-                }
             }
         }
         if (last) {  // trailer of this member, then the next member's header or the end of the data
