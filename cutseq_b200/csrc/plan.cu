@@ -383,7 +383,7 @@ int upload_text(csq_plan* plan, Slot& s, const csq_batch_text* in) {
     return ensure_common(plan, s, n);
 }
 
-// One mate's BGZF members -> device, inflated into the slot's text buffer (k_gz_inflate, one thread per member).
+// One mate's BGZF members -> device, inflated into the slot's text buffer (k_gz_inflate, one warp per member; k_gz_check: CRC-32 and line ends).
 // lines_dev != nullptr: also the line ends per member.  The text buffer is laid out as for csq_submit_text.
 int inflate_mate(csq_plan* plan, Slot& s, int m, const csq_bgzf_in& bi, uint32_t* lines_dev, cudaStream_t st) {
     if (bi.n_members && (!bi.data || !bi.member_off || !bi.text_off)) return fail(CSQ_ERR_INVALID, "mate %d: null BGZF arrays", m + 1);

@@ -115,6 +115,39 @@ def test_bgzf_batches_match_text_batches(level, piece):
         assert gsub == wsub
 
 
+@pytest.mark.parametrize("strategy", [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY], ids=["default", "fixed", "rle", "huffman"])
+def test_device_inflate_on_every_kind_of_stream(strategy):
+    """Content that drives every path of the warp decoder: stored, fixed and dynamic blocks, long matches copied by all
+    lanes, runs (distance 1), short periods (distance < length), long codes behind the direct tables, literal-only
+    streams.  k_gz_check compares the CRC-32 of what was inflated with every member's trailer, so a wrong byte anywhere
+    is an error; the line ends per member are compared with the text."""
+    import os
+    import random
+
+    from tests.test_gz import bgzf
+
+    rng = random.Random(17)
+    contents = {
+        "fastq": _fastq(native.synth_batch(1, 3000, first_index=7, buffer=5), 0),
+        "runs": b"".join(bytes([rng.choice(b"ACGT\n")]) * rng.randint(1, 700) for _ in range(2000)),
+        "periods": b"".join((bytes(rng.choice(b"ACGT#I\n") for _ in range(p)) * (3000 // p)) for p in (2, 3, 5, 7, 8, 9, 15, 16, 17, 31, 33, 100)),
+        "random": os.urandom(200_000),
+        "skewed": bytes(rng.choice(b"A" * 200 + bytes(range(256))) for _ in range(300_000)),  # code lengths up to 15
+        "one": b"\n",
+    }
+    prog = helpers.program_for(["-A", "SMALLRNA"], 1)
+    with native.Plan(prog, 0, 0) as plan:
+        for name, text in contents.items():
+            for level in (1, 9):
+                for piece in (0xFF00, 4093):
+                    if not text:
+                        continue
+                    z = bgzf(text, level, strategy, piece)
+                    lines = plan.bgzf_count_lines(native.BgzfRun(z))
+                    want = [text[o:o + piece].count(b"\n") for o in range(0, len(text), piece)]
+                    assert [int(v) for v in lines] == want, (name, level, piece)
+
+
 def test_bgzf_in_gzip_out_round_trip_and_corrupt_member():
     prog = helpers.program_for(["-A", "TAKARAV3"], 2)
     n = 20000
