@@ -128,7 +128,7 @@ def test_device_inflate_on_every_kind_of_stream(strategy):
 
     rng = random.Random(17)
     contents = {
-        "fastq": _fastq(native.synth_batch(1, 3000, first_index=7, buffer=5), 0),
+        "fastq": _fastq(native.synth_batch(2, 3000, first_index=7, buffer=5), 0),
         "runs": b"".join(bytes([rng.choice(b"ACGT\n")]) * rng.randint(1, 700) for _ in range(2000)),
         "periods": b"".join((bytes(rng.choice(b"ACGT#I\n") for _ in range(p)) * (3000 // p)) for p in (2, 3, 5, 7, 8, 9, 15, 16, 17, 31, 33, 100)),
         "random": os.urandom(200_000),
