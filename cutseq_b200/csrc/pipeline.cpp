@@ -518,11 +518,32 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
     {
         uint64_t est_text[2] = {0, 0}, est_load[2] = {0, 0};
         double n_batches_est = 0, all_text = 0;
-        bool have_est = mode != 2;
+        bool have_est = true;
         for (int m = 0; m < n_mates && have_est; m++) {
             double bpr = 0, ratio = 1.0;  // text bytes per record, compressed / text bytes
             uint64_t total_text = 0;
-            if (mode == 0) {
+            if (mode == 2) {
+                // the serial reader's inputs: a sample of a regular file's text tells the batch size (the reader's own
+                // buffers would grow by doubling, every step a pinned allocation); pipes cannot be sampled
+                if (!inf[m].regular || !inf[m].map || inf[m].size == 0) {
+                    have_est = false;
+                    break;
+                }
+                std::vector<uint8_t> text((size_t)1 << 20);
+                long got = 0;
+                if (inf[m].gz) {
+                    csqio::Inflater inflater;
+                    inflater.reset(inf[m].map, (size_t)std::min<uint64_t>(inf[m].size, 1u << 20));
+                    got = inflater.read(text.data(), text.size() / 2);  // (a truncated view: stop well inside what it holds)
+                    total_text = inf[m].size * 4;                       // a guess; only bounds the number of jobs
+                } else {
+                    got = (long)std::min<uint64_t>(inf[m].size, text.size());
+                    memcpy(text.data(), inf[m].map, (size_t)got);
+                    total_text = inf[m].size;
+                }
+                const uint64_t lines = got > 0 ? csqio::count_newlines(text.data(), (size_t)got) : 0;
+                if (lines >= 4) bpr = (double)got / ((double)lines / 4.0);
+            } else if (mode == 0) {
                 const size_t sample = (size_t)std::min<uint64_t>(inf[m].size, 4u << 20);
                 const uint64_t lines = csqio::count_newlines(inf[m].map, sample);
                 if (lines >= 4) bpr = (double)sample / ((double)lines / 4.0);
@@ -548,6 +569,7 @@ extern "C" int csq_run_files(const csq_op* ops_r1, int n1, const csq_op* ops_r2,
             const double batch_text = std::min((double)batch_reads * bpr * 1.02 + 65536.0, (double)total_text + 65536.0);
             est_text[m] = (uint64_t)batch_text;
             est_load[m] = (uint64_t)(batch_text * ratio * (mode == 1 ? 1.06 : 1.0)) + 65536;
+            if (mode == 2) est_load[m] += 5u << 20;  // the reader asks for a piece (<= 4 MiB) more than the batch holds
             if (mode == 1) est_load[m] = std::max<uint64_t>(est_load[m], std::min<uint64_t>(inf[m].size, (48ull << 20) + 65536));
             n_batches_est = std::max(n_batches_est, (double)total_text / std::max(1.0, (double)batch_reads * bpr));
             all_text += (double)total_text;
