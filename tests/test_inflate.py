@@ -177,3 +177,39 @@ def test_text_reader_uses_the_parallel_decoder(tmp_path, monkeypatch):
             got[1] += texts[1]
             total += n
     assert total == 3000 and got[0] == recs[0] and got[1] == recs[1]
+
+
+def test_parallel_inflate_random_streams():
+    """Random contents, members, levels, strategies, memory levels (tiny blocks), span sizes down to 1 KB and thread counts
+    against zlib."""
+    rng = random.Random(99)
+
+    def reads(n):
+        out = []
+        for i in range(n):
+            ln = rng.randint(1, 300)
+            out.append(f"@M{rng.randint(0, 9)}:{i} {'x' * rng.randint(0, 30)}\n{''.join(rng.choice('ACGTN') for _ in range(ln))}\n+\n"
+                       f"{''.join(rng.choice('FFFFFF:,#') for _ in range(ln))}\n")
+        return "".join(out).encode()
+
+    for it in range(40):
+        kind = rng.choice(["fastq", "fastq", "mixed", "binary", "lines"])
+        if kind == "fastq":
+            data = reads(rng.randint(1, 4000))
+        elif kind == "mixed":
+            data = reads(rng.randint(100, 1500)) + os.urandom(rng.randint(0, 50000)) + reads(rng.randint(100, 1500))
+        elif kind == "binary":
+            data = os.urandom(rng.randint(0, 150000))
+        else:
+            data = b"".join(bytes(rng.choice(b"ab\n") for _ in range(rng.randint(0, 80))) + b"\n" for _ in range(rng.randint(0, 15000)))
+        cuts = sorted(rng.randint(0, len(data)) for _ in range(rng.randint(0, 3)))
+        parts = [data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])]
+        comp = b""
+        for p in parts:
+            c = zlib.compressobj(rng.choice([1, 1, 4, 6, 6, 9]), zlib.DEFLATED, 31, rng.choice([1, 8, 9]),
+                                 rng.choice([zlib.Z_DEFAULT_STRATEGY] * 4 + [zlib.Z_FIXED, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FILTERED]))
+            comp += c.compress(p) + c.flush()
+        if rng.random() < 0.2:
+            comp += bytes(rng.randint(1, 40))  # zero padding behind the last member
+        span, threads = rng.choice([1000, 3000, 10000, 40000, 200000, 0]), rng.choice([2, 3, 4, 8, 16])
+        assert native.pinflate(comp, len(data) + 1, threads, span) == data, (it, kind, len(data), span, threads)
