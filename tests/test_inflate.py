@@ -213,3 +213,17 @@ def test_parallel_inflate_random_streams():
             comp += bytes(rng.randint(1, 40))  # zero padding behind the last member
         span, threads = rng.choice([1000, 3000, 10000, 40000, 200000, 0]), rng.choice([2, 3, 4, 8, 16])
         assert native.pinflate(comp, len(data) + 1, threads, span) == data, (it, kind, len(data), span, threads)
+
+
+def test_bench_fixture_writes_one_valid_gzip_member():
+    """scripts/bench_files.gzip_single_member (the ordinary-gzip fixture of the bench): pieces deflated side by side and
+    joined by sync flushes are ONE member that gzip, zlib and both of the library's decoders read."""
+    from scripts import bench_files
+
+    text = fastq(5000, seed=31)
+    comp = bench_files.gzip_single_member(text, 4, level=6, piece=100_000)
+    assert gzip.decompress(comp) == text
+    d = zlib.decompressobj(31)
+    assert d.decompress(comp) == text and d.eof and d.unused_data == b""  # a single member
+    assert gunzip(comp, 1 << 20, len(text)) == text
+    assert native.pinflate(comp, len(text), 4, 50_000) == text
