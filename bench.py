@@ -235,10 +235,12 @@ def files_leg(prog, pairs_plain, pairs_gz, n_devices, threads, pairs_gzip=0):
     return out
 
 
-def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, max_over_ranks):
+def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, max_over_ranks, bgzf_in=True):
     """csq_submit_bgzf / csq_wait with CSQ_PLAN_GZIP_OUT: the two pinned text batches of the e2e leg, compressed once on the
     host into BGZF members (64 KiB, zlib level 1 - what bgzip or this library's own writer produces), go through the
-    device inflate, the chain and the device deflate; compressed bytes only cross PCIe in both directions."""
+    device inflate, the chain and the device deflate; compressed bytes only cross PCIe in both directions.
+    bgzf_in=False: the pinned FASTQ text goes up as it is (csq_submit_text) and only the outputs are gzip members - plain
+    files in, the reference's default .fastq.gz out: the upload has the link to itself."""
     import ctypes as C
 
     import numpy as np
@@ -251,7 +253,7 @@ def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, ma
     threads = max(2, (os.cpu_count() or 4) // max(1, world))
     inputs = []  # per batch: (csq_batch_bgzf, keep-alive)
     comp_bytes = 0
-    for tb in batches:
+    for tb in batches if bgzf_in else []:
         b = A.csq_batch_bgzf()
         b.n_reads, b.n_mates, b.first_record = P, 2, tb.c.first_record
         keep = []
@@ -287,7 +289,10 @@ def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, ma
             d2h, submitted = 0, 0
             for i in range(k):
                 while submitted < k and submitted < i + n_fly:
-                    native.check(native.lib().csq_submit_bgzf(plan._h, submitted % n_fly, C.byref(inputs[submitted % len(inputs)][0]), C.byref(outs[submitted % n_fly])))
+                    if bgzf_in:
+                        native.check(native.lib().csq_submit_bgzf(plan._h, submitted % n_fly, C.byref(inputs[submitted % len(inputs)][0]), C.byref(outs[submitted % n_fly])))
+                    else:
+                        plan.submit_text(submitted % n_fly, batches[submitted % len(batches)].c, outs[submitted % n_fly])
                     submitted += 1
                 plan.wait(i % n_fly)
                 o = outs[i % n_fly]
@@ -303,11 +308,14 @@ def e2e_gz_leg(args, prog, plan_flags, device, batches, P, B, world, barrier, ma
         w1 = time.perf_counter()
         barrier()
         dt = max_over_ranks(w1 - w0)
-        return {"value": world * steps * B * P / dt, "unit": UNIT, "h2d_bytes_per_step": comp_bytes * B, "d2h_bytes_per_step": int(d2h // steps),
+        return {"value": world * steps * B * P / dt, "unit": UNIT, "h2d_bytes_per_step": (comp_bytes if bgzf_in else text_bytes) * B,
+                "d2h_bytes_per_step": int(d2h // steps),
                 "ms_per_step": dt / steps * 1e3, "steps": steps, "text_bytes_per_step": text_bytes * B,
-                "input": "BGZF members (zlib level 1, 0xFF00-byte pieces), inflated on the device, one warp per member",
+                "input": "BGZF members (zlib level 1, 0xFF00-byte pieces), inflated on the device, one warp per member" if bgzf_in
+                         else "pinned FASTQ text (csq_submit_text)",
                 "output": "gzip members (BGZF framing, dynamic-Huffman literal coding) encoded on the device",
-                "timing": f"wall clock between device-synchronised points, {n_fly} batches in flight through csq_submit_bgzf/csq_wait, max over ranks"}
+                "timing": f"wall clock between device-synchronised points, {n_fly} batches in flight through "
+                          f"{'csq_submit_bgzf' if bgzf_in else 'csq_submit_text'}/csq_wait, max over ranks"}
     finally:
         plan.close()
 
@@ -528,12 +536,16 @@ def main():
 
     # ---- the same end to end with COMPRESSED host buffers: BGZF members in (device inflate), gzip members out (device
     # deflate) - what the reference's default .fastq.gz files hold; ~1/3 of the bytes cross PCIe ----
-    e2e_gz = None
+    e2e_gz = e2e_gzout = None
     if not args.no_e2e and not args.no_e2e_gz and text_mode:
         try:
             e2e_gz = e2e_gz_leg(args, prog, plan_flags, local_rank, batches, P, B, world, barrier, max_over_ranks)
         except Exception as exc:
             e2e_gz = {"error": repr(exc)}
+        try:  # plain text up, gzip members down
+            e2e_gzout = e2e_gz_leg(args, prog, plan_flags, local_rank, batches, P, B, world, barrier, max_over_ranks, bgzf_in=False)
+        except Exception as exc:
+            e2e_gzout = {"error": repr(exc)}
 
     native.unbind_host()  # the host legs below (files, CPU baseline) use every core of the box
     if rank != 0:
@@ -640,7 +652,7 @@ def main():
         "roofline": roofline, "roofline_e2e": roofline_e2e, "roofline_dp_executed": roofline_dp_executed,
         "int_peak_Gops": {"alu_only": alu_peak / 1e9, "alu_fma_mix": mixed_peak / 1e9},
         "kernels": [{"kernel": n, "ms": t} for n, t in ktimes], "kernels_note": "one batch of the step, one stream, CUDA event after every kernel",
-        "dp_kernels": dp_kernels, "cpu_baseline": cpu, "e2e": e2e, "e2e_gz": e2e_gz, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
+        "dp_kernels": dp_kernels, "cpu_baseline": cpu, "e2e": e2e, "e2e_gz": e2e_gz, "e2e_gzout": e2e_gzout, "files": files, "gpu_launches": int(timed_launches), "clocks": clocks,
         "job_counters": {"pairs": int(job_counters.n), "written": int(job_counters.written), "too_short": int(job_counters.too_short)},
         "sources_sha256_16": src_hash,
     }
