@@ -1,4 +1,4 @@
-"""Compression formats that the native reader / writer does not speak itself.
+"""Compression formats - and the one record format - that the native reader / writer does not speak itself.
 
 The reference opens every file through xopen (behind cutadapt's ``InputPaths`` / ``OutputFiles``, run.py:434-436,
 751-753), which handles ``.gz``, ``.bz2``, ``.xz`` and ``.zst`` by file name.  The native library reads plain and gzip
@@ -6,12 +6,20 @@ The reference opens every file through xopen (behind cutadapt's ``InputPaths`` /
 file and the library and a Python thread on the other end of it (``bz2`` / ``lzma`` release the GIL while they
 work): the library sees a plain FASTQ stream, nothing below the C ABI changes.  ``.zst`` needs a module that this
 interpreter does not ship; it is refused with a clear message instead of being misread as plain text.
+
+FASTA input (records without qualities; the reference hands ``qualities=has_qualities()`` on to its output files,
+run.py:439, 756) takes the same route: the pump turns every record into a FASTQ record with a constant quality far above
+any cutoff - quality trimming has nothing to remove, as for a read without qualities - and the output pumps write
+``>name`` / sequence records again (dnaio's FASTA writer does not wrap lines), compressed as the file name says.
+(Whether the reference itself survives FASTA input is doubtful - run.py:416 / 720 always add cutadapt's QualityTrimmer,
+which takes the length of ``read.qualities`` - see DESIGN.md section 7; here such input simply works.)
 """
 
 from __future__ import annotations
 
 import bz2
 import errno
+import gzip
 import lzma
 import os
 import shutil
@@ -35,6 +43,73 @@ def _opener(path):
     return None
 
 
+def _reader(path):
+    """Opener for reading a file of any supported compression (used for FASTA inputs and for sniffing)."""
+    return _opener(path) or (gzip.open if str(path).lower().endswith(".gz") else open)
+
+
+def _writer(path):
+    """Opener for writing FASTA outputs: compression as the file name says (gzip at level 1 like the native writer)."""
+    fn = _opener(path)
+    if fn:
+        return fn
+    if str(path).lower().endswith(".gz"):
+        return lambda p, mode: gzip.open(p, mode, compresslevel=1)
+    return open
+
+
+def is_fasta(path) -> bool:
+    """dnaio tells the formats apart by the first character of the content: '>' is FASTA, '@' FASTQ."""
+    try:
+        if not os.path.isfile(path):
+            return False
+        with _reader(path)(path, "rb") as f:
+            while True:
+                c = f.read(1)
+                if not c:
+                    return False
+                if c not in b" \t\r\n":
+                    return c == b">"
+    except (OSError, EOFError, lzma.LZMAError):
+        return False
+
+
+FASTA_QUALITY = b"I"  # Q40 at base 33: above any cutoff, so that quality trimming leaves such reads alone
+
+
+def fasta_to_fastq(src, dst):
+    """FASTA records (sequences may span lines) -> FASTQ records with a constant quality."""
+    name, parts = None, []
+
+    def flush():
+        if name is not None:
+            seq = b"".join(parts)
+            dst.write(b"@" + name + b"\n" + seq + b"\n+\n" + FASTA_QUALITY * len(seq) + b"\n")
+
+    for line in src:
+        if line.startswith(b">"):
+            flush()
+            name, parts = line[1:].rstrip(b"\r\n"), []
+        elif name is None:
+            if line.strip():
+                raise ValueError("FASTA input does not start with a '>' header")
+        else:
+            parts.append(line.strip())
+    flush()
+
+
+def fastq_to_fasta(src, dst):
+    """FASTQ records as the library writes them (four lines each) -> '>name' / sequence records."""
+    while True:
+        header = src.readline()
+        if not header:
+            return
+        seq = src.readline()
+        src.readline()
+        src.readline()
+        dst.write(b">" + header[1:] + seq)
+
+
 class Transcoders:
     """Context manager: ``tc.inputs`` / ``tc.outputs`` are what the library should open instead of the given paths."""
 
@@ -46,8 +121,16 @@ class Transcoders:
         self._tmp = None
         in_jobs = [(i, p, _opener(p)) for i, p in enumerate(self.inputs)]
         out_jobs = [(k, m, p, _opener(p)) for k, v in self.outputs.items() if v for m, p in enumerate(v)]
-        self._in_jobs = [j for j in in_jobs if j[2]]
-        self._out_jobs = [j for j in out_jobs if j[3]]
+        fasta = [is_fasta(p) for p in self.inputs if p]
+        self.fasta = bool(fasta) and all(fasta)
+        if any(fasta) and not self.fasta:
+            raise ValueError("the input files differ in format (FASTA and FASTQ)")
+        if self.fasta:  # every input and every output goes through a converting pump
+            self._in_jobs = [(i, p, _reader(p)) for i, p, _ in in_jobs if p]
+            self._out_jobs = [(k, m, p, _writer(p)) for k, m, p, _ in out_jobs if p]
+        else:
+            self._in_jobs = [j for j in in_jobs if j[2]]
+            self._out_jobs = [j for j in out_jobs if j[3]]
 
     def __enter__(self):
         if not self._in_jobs and not self._out_jobs:
@@ -57,12 +140,12 @@ class Transcoders:
             fifo = os.path.join(self._tmp, f"in_{i}.fq")
             os.mkfifo(fifo)
             self.inputs[i] = fifo
-            self._start(self._feed, (path, opener, fifo), fifo, "in")
+            self._start(self._feed_fasta if self.fasta else self._feed, (path, opener, fifo), fifo, "in")
         for k, m, path, opener in self._out_jobs:
             fifo = os.path.join(self._tmp, f"out_{k}_{m}.fq")  # no compression suffix: the library writes plain text
             os.mkfifo(fifo)
             self.outputs[k][m] = fifo
-            self._start(self._drain, (path, opener, fifo), fifo, "out")
+            self._start(self._drain_fasta if self.fasta else self._drain, (path, opener, fifo), fifo, "out")
         return self
 
     def _start(self, fn, args, fifo, side):
@@ -87,6 +170,16 @@ class Transcoders:
     def _drain(path, opener, fifo):
         with open(fifo, "rb") as src, opener(path, "wb") as dst:
             shutil.copyfileobj(src, dst, 1 << 20)
+
+    @staticmethod
+    def _feed_fasta(path, opener, fifo):
+        with opener(path, "rb") as src, open(fifo, "wb", buffering=1 << 20) as dst:
+            fasta_to_fastq(src, dst)
+
+    @staticmethod
+    def _drain_fasta(path, opener, fifo):
+        with open(fifo, "rb", buffering=1 << 20) as src, opener(path, "wb") as dst:
+            fastq_to_fasta(src, dst)
 
     def __exit__(self, exc_type, exc, tb):
         # The library has returned: a pump that is still running is either busy (it ends at the end of its pipe) or

@@ -65,6 +65,39 @@ def test_bz2_and_xz_files_through_the_cli(tmp_path):
         run.main(case["argv"] + ["-O", str(tmp_path / "z")] + [str(tmp_path / "a.fq.zst"), str(tmp_path / "b.fq.zst")])
 
 
+def test_fasta_files_through_the_cli(tmp_path):
+    """Records without qualities (reference run.py:439, 756 hand has_qualities() on to the writers): FASTA in, FASTA out,
+    the same reads as a FASTQ run whose qualities are far above the cutoff."""
+    import io
+
+    from cutseq_b200 import transcode
+
+    case = [c for c in helpers.golden_cases() if c["case"] == "takarav3_synth_polya"][0]
+    fq, fa = [], []
+    for m, p in enumerate(helpers.golden_input_paths(case)):
+        lines = gzip.open(p).read().split(b"\n")
+        recs = [(lines[i][1:], lines[i + 1]) for i in range(0, len(lines) - 1, 4)]
+        q = str(tmp_path / f"in_R{m + 1}.fq")
+        with open(q, "wb") as f:
+            f.write(b"".join(b"@" + n + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for n, s in recs))
+        a = str(tmp_path / f"in_R{m + 1}.fa.gz")
+        with gzip.open(a, "wb") as f:  # sequences wrapped at 60 columns, as FASTA files often are
+            f.write(b"".join(b">" + n + b"\n" + b"\n".join(s[o:o + 60] for o in range(0, max(len(s), 1), 60)) + b"\n" for n, s in recs))
+        fq.append(q)
+        fa.append(a)
+    want = [str(tmp_path / n) for n in ("w1.fq", "w2.fq", "ws1.fq", "ws2.fq")]
+    run.main(case["argv"] + ["-o", want[0], want[1], "-s", want[2], want[3], "--batch-reads", "500"] + fq)
+    got = [str(tmp_path / n) for n in ("g1.fa", "g2.fa.gz", "gs1.fa", "gs2.fa.bz2")]
+    run.main(case["argv"] + ["-o", got[0], got[1], "-s", got[2], got[3], "--batch-reads", "500"] + fa)
+    import bz2
+
+    for w, g, opener in zip(want, got, (open, gzip.open, open, bz2.open)):
+        expect = io.BytesIO()
+        transcode.fastq_to_fasta(io.BytesIO(open(w, "rb").read()), expect)
+        assert opener(g, "rb").read() == expect.getvalue(), g
+    assert open(want[0], "rb").read().count(b"\n") > 4000  # (the run did trim and write reads)
+
+
 def test_batch_size_does_not_change_output(tmp_path):
     case = [c for c in helpers.golden_cases() if c["case"] == "inline_custom_ensure"][0]
     outs = []

@@ -74,3 +74,61 @@ def test_zstd_is_refused_with_a_message(tmp_path):
     with pytest.raises(ValueError) as e:
         Transcoders([str(tmp_path / "a.fq.zst")], {})
     assert "zstd" in str(e.value)
+
+
+# ---- FASTA input: records without qualities go through converting pumps ----
+def test_fasta_converters():
+    import io
+
+    from cutseq_b200 import transcode
+
+    src = io.BytesIO(b">r1 desc\nACGT\nAC\n\n>r2\n\n>r3\r\nGG\r\n")
+    dst = io.BytesIO()
+    transcode.fasta_to_fastq(src, dst)
+    assert dst.getvalue() == b"@r1 desc\nACGTAC\n+\nIIIIII\n@r2\n\n+\n\n@r3\nGG\n+\nII\n"
+    back = io.BytesIO()
+    transcode.fastq_to_fasta(io.BytesIO(dst.getvalue()), back)
+    assert back.getvalue() == b">r1 desc\nACGTAC\n>r2\n\n>r3\nGG\n"
+    with pytest.raises(ValueError):
+        transcode.fasta_to_fastq(io.BytesIO(b"ACGT\n>r1\nAC\n"), io.BytesIO())
+
+
+@pytest.mark.parametrize("ext", ["", ".gz", ".bz2"])
+def test_fasta_files_go_in_and_come_out_as_fasta(tmp_path, ext):
+    import gzip
+
+    from cutseq_b200 import transcode
+
+    fasta = b"".join(b">read%d some comment\nACGTACGTAC\nGTACGTNN\n" % i for i in range(5000))
+    want = b"".join(b">read%d some comment\nACGTACGTACGTACGTNN\n" % i for i in range(5000))
+    opener = {"": open, ".gz": gzip.open, ".bz2": bz2.open}[ext]
+    src = str(tmp_path / ("in.fa" + ext))
+    with opener(src, "wb") as f:
+        f.write(fasta)
+    assert transcode.is_fasta(src) and not transcode.is_fasta(__file__)
+    outs = {"trimmed": [str(tmp_path / ("o1.fa" + ext))], "short": [str(tmp_path / "s1.fa")], "untrimmed": None}
+    with Transcoders([src], outs) as tc:
+        assert tc.fasta and tc.inputs[0] != src and tc.outputs["trimmed"][0] != outs["trimmed"][0]
+        # stand-in for csq_run_files: FASTQ records arrive on the input pipe ...
+        with native.TextReader(tc.inputs[0]) as r, open(tc.outputs["trimmed"][0], "wb") as w, open(tc.outputs["short"][0], "wb"):
+            total = 0
+            while True:
+                n, texts, first = r.next(1024)
+                if n == 0:
+                    break
+                assert texts[0].count(b"\n+\nIIIIIIIIIIIIIIIIII\n") == n  # constant qualities, one per base
+                w.write(texts[0])  # ... and FASTQ records leave on the output pipes
+                total += n
+        assert total == 5000
+    with opener(outs["trimmed"][0], "rb") as f:
+        assert f.read() == want
+    assert open(outs["short"][0], "rb").read() == b""
+
+
+def test_mixed_fasta_and_fastq_inputs_are_refused(tmp_path):
+    a, b = tmp_path / "a.fa", tmp_path / "b.fq"
+    a.write_bytes(b">r\nACGT\n")
+    b.write_bytes(b"@r\nACGT\n+\nIIII\n")
+    with pytest.raises(ValueError) as e:
+        Transcoders([str(a), str(b)], {})
+    assert "differ in format" in str(e.value)
