@@ -95,7 +95,7 @@ def test_fasta_files_through_the_cli(tmp_path):
         expect = io.BytesIO()
         transcode.fastq_to_fasta(io.BytesIO(open(w, "rb").read()), expect)
         assert opener(g, "rb").read() == expect.getvalue(), g
-    assert open(want[0], "rb").read().count(b"\n") > 4000  # (the run did trim and write reads)
+    assert open(want[0], "rb").read().count(b"\n") > 2000  # (the run did trim and write reads: 695 of the 700 pairs)
 
 
 def test_batch_size_does_not_change_output(tmp_path):
