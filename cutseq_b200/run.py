@@ -300,7 +300,7 @@ def build_parser() -> argparse.ArgumentParser:
         description="Trim sequencing adapters, barcodes, UMIs and masks from NGS reads on NVIDIA B200 GPUs "
         "(cutseq-compatible command line).",
         epilog="Limits (explicit errors, no CPU fallback): reads <= 895 bases, adapters <= 128, headers <= 65535 bytes; "
-        "sm_100 GPUs only; .zst inputs are refused.",
+        "sm_100 GPUs only; .zst files need the zstandard module or the zstd program.",
     )
     p.add_argument("input_file", type=str, nargs="*", help="One (single-end) or two (paired-end) FASTQ files: plain, .gz (incl. bgzip), .bz2 or .xz.")
     p.add_argument("-a", "--adapter-scheme", type=str,

@@ -4,8 +4,9 @@ The reference opens every file through xopen (behind cutadapt's ``InputPaths`` /
 751-753), which handles ``.gz``, ``.bz2``, ``.xz`` and ``.zst`` by file name.  The native library reads plain and gzip
 (incl. BGZF) files and writes plain and gzip.  For ``.bz2`` and ``.xz`` this module puts a named pipe between the
 file and the library and a Python thread on the other end of it (``bz2`` / ``lzma`` release the GIL while they
-work): the library sees a plain FASTQ stream, nothing below the C ABI changes.  ``.zst`` needs a module that this
-interpreter does not ship; it is refused with a clear message instead of being misread as plain text.
+work): the library sees a plain FASTQ stream, nothing below the C ABI changes.  ``.zst`` goes the same way through the
+``zstandard`` module or the ``zstd`` program when the system has one of them (xopen's fallbacks); this image has neither,
+and such files are refused with a clear message instead of being misread as plain text.
 
 FASTA input (records without qualities; the reference hands ``qualities=has_qualities()`` on to its output files,
 run.py:439, 756) takes the same route: the pump turns every record into a FASTQ record with a constant quality far above
@@ -27,16 +28,77 @@ import tempfile
 import threading
 
 _OPENERS = {".bz2": bz2.open, ".xz": lzma.open, ".lzma": lzma.open}
-_UNSUPPORTED = (".zst", ".zstd")
+_ZSTD = (".zst", ".zstd")
+
+
+class _PipedProgram:
+    """File object over an external (de)compressor, the way xopen falls back to programs: ``zstd -dc file`` for reading,
+    ``zstd -c > file`` for writing."""
+
+    def __init__(self, argv, path, mode):
+        import subprocess
+
+        self._writing = "w" in mode
+        if self._writing:
+            self._sink = open(path, "wb")
+            self._p = subprocess.Popen(argv, stdin=subprocess.PIPE, stdout=self._sink)
+            self._f = self._p.stdin
+        else:
+            self._sink = None
+            self._p = subprocess.Popen(argv + [path], stdout=subprocess.PIPE)
+            self._f = self._p.stdout
+
+    def read(self, n=-1):
+        return self._f.read(n)
+
+    def readline(self):
+        return self._f.readline()
+
+    def __iter__(self):
+        return iter(self._f)
+
+    def write(self, data):
+        return self._f.write(data)
+
+    def close(self):
+        self._f.close()
+        rc = self._p.wait()
+        if self._sink:
+            self._sink.close()
+        if rc != 0:
+            raise OSError(f"{self._p.args[0]} exited with status {rc}")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def _zstd_opener(path):
+    """zstd through the ``zstandard`` module or the ``zstd`` program, whichever the system has (xopen's order); neither
+    ships with this image, where such files are refused with a clear message instead of being misread as plain text."""
+    try:
+        import zstandard  # noqa: F401
+
+        return lambda p, mode: zstandard.open(p, mode)
+    except ImportError:
+        pass
+    prog = shutil.which("zstd")
+    if prog:
+        return lambda p, mode: _PipedProgram([prog, "-q", "-c"] if "w" in mode else [prog, "-q", "-dc"], p, mode)
+    raise ValueError(f"{path}: zstd-compressed files need the zstandard module or the zstd program, and this system has neither "
+                     "(use .gz, .bz2, .xz or plain FASTQ)")
 
 
 def _opener(path):
     if path is None:
         return None
     low = str(path).lower()
-    for ext in _UNSUPPORTED:
+    for ext in _ZSTD:
         if low.endswith(ext):
-            raise ValueError(f"{path}: zstd-compressed files are not supported by this build (use .gz, .bz2, .xz or plain FASTQ)")
+            return _zstd_opener(path)
     for ext, fn in _OPENERS.items():
         if low.endswith(ext):
             return fn

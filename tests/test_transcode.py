@@ -132,3 +132,28 @@ def test_mixed_fasta_and_fastq_inputs_are_refused(tmp_path):
     with pytest.raises(ValueError) as e:
         Transcoders([str(a), str(b)], {})
     assert "differ in format" in str(e.value)
+
+
+def test_zstd_goes_through_the_program_when_there_is_one(tmp_path, monkeypatch):
+    """xopen falls back to the `zstd` program; the plumbing is tested with a stand-in program of that name (gzip behind
+    zstd's command line: -dc file / -c)."""
+    import gzip
+    import stat
+
+    fake = tmp_path / "bin" / "zstd"
+    fake.parent.mkdir()
+    fake.write_text("#!/bin/sh\nif [ \"$2\" = \"-dc\" ]; then exec gzip -dc \"$3\"; else exec gzip -1 -c; fi\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(fake.parent) + os.pathsep + os.environ["PATH"])
+    src = str(tmp_path / "in.fq.zst")
+    with gzip.open(src, "wb") as f:
+        f.write(TEXT)
+    outs = {"trimmed": [str(tmp_path / "o.fq.zst")], "short": [None], "untrimmed": None}
+    with Transcoders([src], outs) as tc:
+        with native.TextReader(tc.inputs[0]) as r, open(tc.outputs["trimmed"][0], "wb") as w:
+            while True:
+                n, texts, first = r.next(4096)
+                if n == 0:
+                    break
+                w.write(texts[0])
+    assert gzip.open(outs["trimmed"][0]).read() == TEXT
